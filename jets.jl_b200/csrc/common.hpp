@@ -1,0 +1,292 @@
+// Internal declarations shared by the translation units of libjets_b200.so.
+// Nothing here is part of the ABI (include/jets_b200.h is).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/jets_b200.h"
+
+namespace jets {
+
+// ------------------------------------------------------------------ errors ---------------
+void set_error(const char* fmt, ...);
+struct Fail {
+  int code;
+};
+#define JETS_FAIL(code, ...)        \
+  do {                              \
+    ::jets::set_error(__VA_ARGS__); \
+    throw ::jets::Fail{code};       \
+  } while (0)
+#define JETS_CHECK(cond, code, ...)              \
+  do {                                           \
+    if (!(cond)) JETS_FAIL(code, __VA_ARGS__);   \
+  } while (0)
+#define CUDA_TRY(expr)                                                                   \
+  do {                                                                                   \
+    cudaError_t e__ = (expr);                                                            \
+    if (e__ != cudaSuccess)                                                              \
+      JETS_FAIL(JETS_ERR_CUDA, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(e__),   \
+                __FILE__, __LINE__, #expr);                                              \
+  } while (0)
+
+// Wraps an ABI body: converts Fail / std exceptions into status codes.
+template <class F>
+int guard(F&& f) {
+  try {
+    f();
+    return JETS_OK;
+  } catch (const Fail& e) {
+    return e.code;
+  } catch (const std::exception& e) {
+    set_error("internal error: %s", e.what());
+    return JETS_ERR_INVALID;
+  }
+}
+
+// ------------------------------------------------------------------ context --------------
+struct Context {
+  bool ready = false;
+  int device = -1;
+  int sm_count = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int64_t launches = 0;
+  int fused_engine = 0;  // 0 auto, 1 TMA, 2 LDG
+  double* host_scratch = nullptr;  // pinned, 64 doubles
+  double* dev_scratch = nullptr;   // device partials for reductions
+  size_t dev_scratch_elems = 0;
+  bool capturing = false;
+};
+Context& ctx();
+void require_ready();
+inline size_t dsize(int dt) { return dt == JETS_F32 ? 4 : 8; }
+
+// ------------------------------------------------------------------ storage --------------
+constexpr size_t kGuardBytes = 256;  // readable slack before/after every owned allocation
+
+struct Storage {
+  void* alloc = nullptr;  // cudaMalloc'ed base (owned) or nullptr (wrapped)
+  char* data = nullptr;   // first logical byte
+  size_t bytes = 0;       // logical bytes
+  bool guarded = false;   // kGuardBytes readable on both sides
+  ~Storage();
+};
+
+}  // namespace jets
+
+// Handle types live in the global namespace (they are the ABI's opaque structs).
+struct jets_buf_s {
+  int refs = 1;
+  int dtype = JETS_F64;
+  std::shared_ptr<jets::Storage> st;
+  int64_t off = 0;                 // element offset of this view inside st
+  std::vector<int64_t> blk_off;    // nblocks+1 cumulative element offsets (0-based), relative
+  int64_t length() const { return blk_off.back(); }
+  int32_t nblocks() const { return (int32_t)blk_off.size() - 1; }
+  char* ptr() const { return st->data + (size_t)off * jets::dsize(dtype); }
+  char* block_ptr(int b) const { return ptr() + (size_t)blk_off[b] * jets::dsize(dtype); }
+  bool guarded() const { return st->guarded; }
+};
+
+struct jets_scalar_s {
+  double* dev = nullptr;
+};
+
+namespace jets {
+
+// A JetSpace (one block, is_block=false) or a JetBSpace (is_block=true).
+struct Space {
+  std::vector<int64_t> len;  // per-block lengths
+  bool is_block = false;
+  int64_t total() const {
+    int64_t s = 0;
+    for (auto l : len) s += l;
+    return s;
+  }
+  bool same_layout(const Space& o) const { return len == o.len; }
+};
+
+enum Kind : int {
+  K_DIAG, K_SCALE, K_PW, K_STENCIL, K_DENSE, K_ZERO,  // leaves
+  K_LNVIEW, K_ADJ,                                    // wrappers
+  K_COMPOSE, K_SUM, K_BLOCK                           // combinators
+};
+
+struct Plan;
+
+}  // namespace jets
+
+struct jets_op_s {
+  int refs = 1;
+  jets::Kind kind;
+  int dtype = JETS_F64;
+  jets::Space dom, rng;
+  bool linear = true;  // JopLn-like (df! == f!) or an explicit linear view
+  // leaf state
+  jets_buf w = nullptr;      // diagonal / dense matrix (retained)
+  double a = 0, p = 0;       // scale constant / pointwise parameter
+  int fn = 0;                // pointwise fn or stencil kind
+  int64_t rows = 0, cols = 0, nrhs = 1;
+  jets_buf mo = nullptr;     // linearization point of a pointwise leaf (retained, by reference)
+  // children
+  std::vector<jets_op> kids;  // retained
+  std::vector<int> sgn;       // K_SUM
+  int R = 0, C = 0;           // K_BLOCK (kids column-major)
+  // plan cache, keyed by mode | accumulate<<2 | engine<<3 ; invalidated when `version` bumps
+  uint64_t version = 0;
+  std::map<int, std::shared_ptr<jets::Plan>> plans;
+  ~jets_op_s();
+};
+
+namespace jets {
+
+// ------------------------------------------------------------------ fused engine tables --
+// One "stage" of an elementwise/stencil chain, interpreted per 128-bit vector.
+enum StageOp : int {
+  S_SCALE = 0,   // v *= c0
+  S_DIAG = 1,    // v *= stream[p]
+  S_PW_F = 2,    // v = phi(v)
+  S_PW_J = 3,    // v = phi'(stream[p]) * v
+  S_FDIFF = 4,   // v[p] = p+1<n ? v[p+1]-v[p] : 0
+  S_BDIFF = 5,   // adjoint of FDIFF: v[p] = (p>=1 ? v[p-1] : 0) - (p+1<n ? v[p] : 0)
+  S_LAP = 6,     // v[p] = ((p>=1?v[p-1]:0) - 2 v[p]) + (p+1<n?v[p+1]:0)
+  S_NEG = 7,     // v = -v
+  S_ZERO = 8     // v = 0
+};
+
+struct FStage {      // 32 bytes
+  int32_t op;
+  int32_t fn;
+  const void* ptr;   // operand stream, position 0 of the block (absolute), or null
+  double c0;
+  double c1;
+};
+struct FTerm {       // 32 bytes
+  int64_t in_off;    // element offset of the input block relative to the `in` base
+  const void* in_abs;  // absolute input pointer (overrides in_off when non-null)
+  int32_t stage_begin, stage_end;
+  int32_t sign;      // +1 / -1
+  int32_t nstreams;  // 1 (input) + stages with ptr
+};
+struct FRow {        // 40 bytes
+  int64_t out_off;   // element offset of the output block relative to the `out` base
+  int64_t len;
+  int32_t term_begin, term_end;
+  int32_t init;      // 0 zero-init, 1 accumulate onto existing out, 2 leave untouched
+  int32_t ntiles;
+  int64_t pad;
+};
+struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
+  int64_t tile_begin;
+  int64_t pos_begin;
+  int32_t nactive;
+  int32_t pad;
+};
+
+struct FusedTables {
+  std::vector<FStage> stages;
+  std::vector<FTerm> terms;
+  std::vector<FRow> rows;
+  int hl = 0, hr = 0;     // halo (elements) the chains need on the left / right
+  int max_streams = 1;
+  bool tma_ok = false;    // all streams 16B aligned + guarded
+};
+
+struct DevFused {   // device copy + launch geometry
+  FStage* stages = nullptr;
+  FTerm* terms = nullptr;
+  FRow* rows = nullptr;
+  FSeg* segs = nullptr;
+  int32_t* order = nullptr;  // rows sorted by ntiles (desc)
+  int32_t nrows = 0, nsegs = 0;
+  int64_t ntiles = 0;   // real tiles
+  int64_t nitems = 0;   // (row, chunk-of-tiles) work items
+  int hl = 0, hr = 0, max_streams = 1;
+  int tile_elems = 0;
+  bool use_tma = false;
+  void* blob = nullptr;
+};
+
+// Dense block table entry: out[out_off + i] (+)= sum_j A[i + j*lda] * in[in_off + j]  (trans=0)
+//                          out[out_off + j] (+)= sum_i A[i + j*lda] * in[in_off + i]  (trans=1)
+struct DBlock {
+  const void* A;
+  int64_t in_off, out_off;
+  int32_t rows, cols;   // of the stored matrix
+  int32_t lda;
+  int32_t trans;
+  int32_t nrhs;
+  int32_t pad;
+};
+
+enum StepKind : int { ST_FUSED, ST_GEMV, ST_FILL0 };
+enum AccMode : int { ACC_SET = 0, ACC_ADD = 1, ACC_SUB = 2 };
+
+struct Ref {           // where a step reads / writes: 0 = apply's `in`, 1 = apply's `out`, >=2 tmp
+  int which = 0;
+  int64_t off = 0;     // element offset inside that buffer
+};
+
+struct Step {
+  StepKind kind;
+  Ref src, dst;
+  DevFused fused;              // ST_FUSED
+  std::vector<DBlock> dblocks; // ST_GEMV (host copy)
+  DBlock* d_dblocks = nullptr;
+  int32_t* d_row_ptr = nullptr;  // output-row grouping for GEMV
+  int32_t n_out_rows = 0;
+  int64_t gemv_tiles = 0;
+  int acc = ACC_SET;
+  int64_t fill_len = 0;
+};
+
+struct Plan {
+  std::vector<Step> steps;
+  std::vector<void*> tmps;       // device temporaries (owned)
+  std::vector<size_t> tmp_bytes;
+  std::vector<void*> blobs;      // device table blobs (owned)
+  int engines = 0;
+  uint64_t version = 0;
+  ~Plan();
+};
+
+// plan.cu
+std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
+void run_plan(Plan& p, int dtype, char* in, char* out);
+
+// kernels_fused.cu
+void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
+int fused_tile_elems(int dtype);
+int fused_tiles_per_item();
+int fused_max_terms_tma();
+
+// kernels_dense.cu
+void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);
+void gemv_tile_count(int dtype, bool trans, int32_t out_len, int32_t* ntiles);
+
+// kernels_vec.cu
+void vec_fill(int dtype, void* p, int64_t n, double a, cudaStream_t s);
+void vec_rand(int dtype, void* p, int64_t n, uint64_t seed, uint64_t off, int dist, cudaStream_t s);
+void vec_lincomb(int dtype, void* out, int64_t n, int k, const double* c, const void* const* x,
+                 cudaStream_t s);
+void vec_hadamard(int dtype, void* out, const void* x, const void* y, int64_t n, cudaStream_t s);
+// reductions: kind 0 dot, 1 sumsq, 2 sumabs, 3 count nonzero, 4 max|x|, 5 min|x|, 6 sum|x|^p,
+// 7 min, 8 max.  Result (f64) is written to dev_out (device pointer).
+void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, double p,
+                double* dev_out, cudaStream_t s);
+void scalar_op(double* out, char op, const double* a, const double* b, cudaStream_t s);
+void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca, int af,
+                   const void* x, const double* sb, double cb, int bf, const void* y,
+                   cudaStream_t s);
+void scalar_finish_norm(double* v, double p, cudaStream_t s);
+
+inline void count_launch(int n = 1) { ctx().launches += n; }
+
+}  // namespace jets

@@ -1,0 +1,240 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch.
+// NCCL is resolved lazily with dlopen so that (a) the library has no link-time NCCL dependency
+// and (b) inside a process that already loaded torch's bundled libnccl.so.2 the same copy is
+// reused (two NCCL copies in one process would each build their own transport state).
+#include <dlfcn.h>
+#include "common.hpp"
+
+namespace jets {
+namespace {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+enum { ncclSuccess = 0 };
+enum { ncclFloat32 = 7, ncclFloat64 = 8 };
+enum { ncclSum = 0 };
+
+struct Nccl {
+  void* lib = nullptr;
+  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  int (*CommDestroy)(ncclComm_t) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+
+struct Dist {
+  Nccl n;
+  ncclComm_t comm = nullptr;
+  int rank = 0, size = 1;
+  bool ready = false;
+  double* dev_gather = nullptr;  // [size] doubles
+  char* halo_tmp = nullptr;      // receive staging for halo_reduce
+  size_t halo_tmp_bytes = 0;
+};
+Dist& dist() {
+  static Dist d;
+  return d;
+}
+
+void load_nccl() {
+  Nccl& n = dist().n;
+  if (n.lib) return;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  for (const char* nm : names) {
+    n.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (n.lib) break;
+  }
+  JETS_CHECK(n.lib, JETS_ERR_NCCL, "cannot dlopen libnccl.so.2: %s", dlerror());
+#define SYM(field, name)                                                         \
+  n.field = reinterpret_cast<decltype(n.field)>(dlsym(n.lib, name));             \
+  JETS_CHECK(n.field, JETS_ERR_NCCL, "libnccl is missing symbol %s", name)
+  SYM(GetUniqueId, "ncclGetUniqueId");
+  SYM(CommInitRank, "ncclCommInitRank");
+  SYM(CommDestroy, "ncclCommDestroy");
+  SYM(AllGather, "ncclAllGather");
+  SYM(ReduceScatter, "ncclReduceScatter");
+  SYM(AllReduce, "ncclAllReduce");
+  SYM(Send, "ncclSend");
+  SYM(Recv, "ncclRecv");
+  SYM(GroupStart, "ncclGroupStart");
+  SYM(GroupEnd, "ncclGroupEnd");
+  SYM(GetErrorString, "ncclGetErrorString");
+#undef SYM
+}
+
+#define NCCL_TRY(expr)                                                                      \
+  do {                                                                                      \
+    int r__ = (expr);                                                                       \
+    if (r__ != ncclSuccess)                                                                 \
+      JETS_FAIL(JETS_ERR_NCCL, "NCCL error %s at %s:%d", dist().n.GetErrorString(r__), __FILE__, __LINE__); \
+  } while (0)
+
+int nccl_type(int dt) { return dt == JETS_F32 ? ncclFloat32 : ncclFloat64; }
+void need_dist() { JETS_CHECK(dist().ready, JETS_ERR_NCCL, "jets_dist_init() has not been called"); }
+
+// x[0:n] += y[0:n]
+template <typename T>
+__global__ void add_inplace_kernel(T* __restrict__ x, const T* __restrict__ y, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i] = x[i] + y[i];
+}
+void add_inplace(int dt, void* x, const void* y, int64_t n, cudaStream_t s) {
+  if (n <= 0) return;
+  int64_t g = (n + 1023) / 1024;
+  const int64_t cap = (int64_t)ctx().sm_count * 16;
+  if (g > cap) g = cap;
+  if (dt == JETS_F32) add_inplace_kernel<float><<<(unsigned)g, 256, 0, s>>>((float*)x, (const float*)y, n);
+  else add_inplace_kernel<double><<<(unsigned)g, 256, 0, s>>>((double*)x, (const double*)y, n);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
+
+__global__ void sum_in_order_kernel(const double* v, int n, double* out) {
+  double s = 0.0;
+  for (int i = 0; i < n; ++i) s += v[i];
+  *out = s;
+}
+
+int64_t blocks_len(jets_buf x, int first, int n) { return x->blk_off[first + n] - x->blk_off[first]; }
+
+}  // namespace
+}  // namespace jets
+
+using namespace jets;
+
+extern "C" {
+
+int jets_dist_unique_id(char id[128]) {
+  return guard([&] {
+    load_nccl();
+    ncclUniqueId u;
+    NCCL_TRY(dist().n.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+  });
+}
+
+int jets_dist_init(int rank, int nranks, const char id[128]) {
+  return guard([&] {
+    require_ready();
+    load_nccl();
+    Dist& d = dist();
+    JETS_CHECK(!d.ready, JETS_ERR_NCCL, "jets_dist_init called twice");
+    JETS_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, JETS_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    ncclUniqueId u;
+    memcpy(u.internal, id, 128);
+    NCCL_TRY(d.n.CommInitRank(&d.comm, nranks, u, rank));
+    d.rank = rank;
+    d.size = nranks;
+    CUDA_TRY(cudaMalloc(&d.dev_gather, (nranks + 2) * sizeof(double)));
+    d.ready = true;
+  });
+}
+
+int jets_dist_shutdown(void) {
+  return guard([&] {
+    Dist& d = dist();
+    if (!d.ready) return;
+    cudaStreamSynchronize(ctx().stream);
+    d.n.CommDestroy(d.comm);
+    cudaFree(d.dev_gather);
+    if (d.halo_tmp) cudaFree(d.halo_tmp);
+    d.comm = nullptr; d.ready = false; d.size = 1; d.rank = 0;
+    d.halo_tmp = nullptr; d.halo_tmp_bytes = 0;
+  });
+}
+int jets_dist_rank(void) { return dist().rank; }
+int jets_dist_size(void) { return dist().size; }
+
+int jets_dist_sum_scalar(double* inout) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    Context& c = ctx();
+    c.host_scratch[40] = *inout;
+    double* mine = d.dev_gather + d.size;
+    CUDA_TRY(cudaMemcpyAsync(mine, &c.host_scratch[40], sizeof(double), cudaMemcpyHostToDevice, c.stream));
+    NCCL_TRY(d.n.AllGather(mine, d.dev_gather, 1, ncclFloat64, d.comm, c.stream));
+    sum_in_order_kernel<<<1, 1, 0, c.stream>>>(d.dev_gather, d.size, mine + 1);  // rank order: bit-stable
+    count_launch();
+    CUDA_TRY(cudaMemcpyAsync(&c.host_scratch[41], mine + 1, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    *inout = c.host_scratch[41];
+  });
+}
+
+int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    Context& c = ctx();
+    const int nb = x->nblocks();
+    const int ty = nccl_type(x->dtype);
+    const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+    NCCL_TRY(d.n.GroupStart());
+    // my last nlo blocks are the next rank's `lo`; my first nhi blocks are the previous rank's `hi`
+    if (has_next && nlo > 0) NCCL_TRY(d.n.Send(x->block_ptr(nb - nlo), (size_t)blocks_len(x, nb - nlo, nlo), ty, d.rank + 1, d.comm, c.stream));
+    if (has_prev && nhi > 0) NCCL_TRY(d.n.Send(x->block_ptr(0), (size_t)blocks_len(x, 0, nhi), ty, d.rank - 1, d.comm, c.stream));
+    if (has_prev && nlo > 0 && lo) NCCL_TRY(d.n.Recv(lo->ptr(), (size_t)lo->length(), ty, d.rank - 1, d.comm, c.stream));
+    if (has_next && nhi > 0 && hi) NCCL_TRY(d.n.Recv(hi->ptr(), (size_t)hi->length(), ty, d.rank + 1, d.comm, c.stream));
+    NCCL_TRY(d.n.GroupEnd());
+  });
+}
+
+int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    Context& c = ctx();
+    const int nb = x->nblocks();
+    const int ty = nccl_type(x->dtype);
+    const size_t es = dsize(x->dtype);
+    const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+    // lo = my partial contribution to the previous rank's last nlo blocks; hi = to the next rank's
+    // first nhi blocks.  I receive the mirror images and add them, previous rank first.
+    const int64_t n_from_prev = (has_prev && nhi > 0) ? blocks_len(x, 0, nhi) : 0;
+    const int64_t n_from_next = (has_next && nlo > 0) ? blocks_len(x, nb - nlo, nlo) : 0;
+    const size_t need = (size_t)(n_from_prev + n_from_next) * es + 512;
+    if (need > d.halo_tmp_bytes) {
+      if (d.halo_tmp) cudaFree(d.halo_tmp);
+      CUDA_TRY(cudaMalloc(&d.halo_tmp, need));
+      d.halo_tmp_bytes = need;
+    }
+    char* from_prev = d.halo_tmp;
+    char* from_next = d.halo_tmp + (((size_t)n_from_prev * es + 255) & ~(size_t)255);
+    NCCL_TRY(d.n.GroupStart());
+    if (has_prev && nlo > 0 && lo) NCCL_TRY(d.n.Send(lo->ptr(), (size_t)lo->length(), ty, d.rank - 1, d.comm, c.stream));
+    if (has_next && nhi > 0 && hi) NCCL_TRY(d.n.Send(hi->ptr(), (size_t)hi->length(), ty, d.rank + 1, d.comm, c.stream));
+    if (n_from_prev) NCCL_TRY(d.n.Recv(from_prev, (size_t)n_from_prev, ty, d.rank - 1, d.comm, c.stream));
+    if (n_from_next) NCCL_TRY(d.n.Recv(from_next, (size_t)n_from_next, ty, d.rank + 1, d.comm, c.stream));
+    NCCL_TRY(d.n.GroupEnd());
+    if (n_from_prev) add_inplace(x->dtype, x->block_ptr(0), from_prev, n_from_prev, c.stream);
+    if (n_from_next) add_inplace(x->dtype, x->block_ptr(nb - nlo), from_next, n_from_next, c.stream);
+  });
+}
+
+int jets_dist_allgather(jets_buf shard, jets_buf full) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    JETS_CHECK(full->length() == shard->length() * d.size, JETS_ERR_SHAPE, "allgather: full must be nranks x shard");
+    NCCL_TRY(d.n.AllGather(shard->ptr(), full->ptr(), (size_t)shard->length(), nccl_type(shard->dtype), d.comm, ctx().stream));
+  });
+}
+
+int jets_dist_reduce_scatter(jets_buf full, jets_buf shard) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    JETS_CHECK(full->length() == shard->length() * d.size, JETS_ERR_SHAPE, "reduce_scatter: full must be nranks x shard");
+    NCCL_TRY(d.n.ReduceScatter(full->ptr(), shard->ptr(), (size_t)shard->length(), nccl_type(full->dtype), ncclSum, d.comm, ctx().stream));
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,660 @@
+// Lowers an operator tree (Jet) + mode into a short list of kernel launches, cached per handle.
+//
+//   * Every subtree made of elementwise / stencil leaves under JopBlock, JopSum, JopComposite,
+//     JopAdjoint is flattened into ONE fused launch: per output block a list of signed terms,
+//     each an elementwise chain over one input block (src/Jets.jl:524-540, 630-655, 1010-1057
+//     collapse into a table walk; no temporaries, no zero-fill + accumulate passes).
+//   * Dense leaves (fusion barriers) become block-GEMV launches over a table of matrices.
+//   * Anything else is staged through device temporaries, stage by stage, exactly the way the
+//     reference evaluates it (zeros(range(op)) per composite stage, :525-539).
+#include <algorithm>
+#include "common.hpp"
+
+namespace jets {
+
+int fused_nslots(int max_streams);
+uint64_t g_epoch = 1;  // bumped by point! -> cached plans holding stale mo pointers are rebuilt
+
+namespace {
+
+constexpr int kMaxStagesPerTerm = 6;
+constexpr int kMaxStreamsPerTerm = 4;
+constexpr size_t kMaxEntries = 1u << 20;
+
+struct Entry {
+  int r = 0, c = 0;
+  int sign = 1;
+  bool linear = true;
+  std::vector<FStage> chain;  // application order
+};
+using Entries = std::vector<Entry>;
+
+int map_mode_lnview(int mode) { return mode == JETS_MODE_F ? JETS_MODE_DF : mode; }
+int map_mode_adj(int mode) { return mode == JETS_MODE_DFT ? JETS_MODE_DF : JETS_MODE_DFT; }
+
+const Space& out_space(jets_op a, int mode) { return mode == JETS_MODE_DFT ? a->dom : a->rng; }
+const Space& in_space(jets_op a, int mode) { return mode == JETS_MODE_DFT ? a->rng : a->dom; }
+
+FStage mk(int op, int fn = 0, const void* ptr = nullptr, double c0 = 0) {
+  FStage s;
+  s.op = op; s.fn = fn; s.ptr = ptr; s.c0 = c0; s.c1 = 0;
+  return s;
+}
+
+int chain_streams(const std::vector<FStage>& ch) {
+  int n = 1;
+  for (auto& s : ch) n += s.ptr != nullptr;
+  return n;
+}
+
+bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp);
+thread_local size_t g_esz = 8;  // element size of the plan being built
+
+bool has_stencil(const Entry& e) {
+  for (auto& s : e.chain)
+    if (s.op == S_FDIFF || s.op == S_BDIFF || s.op == S_LAP) return true;
+  return false;
+}
+
+// Entries of an operator acting on ONE flat block are re-expressed on the block structure
+// `target` (same total length): an elementwise chain acts block by block, its operand streams
+// shifted by the block offset.  (The reference applies e.g. `a*A`'s scalar stage to a BlockArray
+// through the per-block broadcast, src/Jets.jl:905-911, :1159-1164.)
+bool reblock(Entries& es, const Space& target) {
+  for (auto& e : es)
+    if (e.r != 0 || e.c != 0 || has_stencil(e)) return false;
+  Entries out;
+  int64_t off = 0;
+  for (size_t k = 0; k < target.len.size(); ++k) {
+    for (const Entry& e : es) {
+      Entry x = e;
+      x.r = x.c = (int)k;
+      for (auto& st : x.chain)
+        if (st.ptr) st.ptr = reinterpret_cast<const char*>(st.ptr) + (size_t)off * g_esz;
+      out.push_back(std::move(x));
+    }
+    off += target.len[k];
+  }
+  es.swap(out);
+  return true;
+}
+
+bool is_flat(const Space& s) { return s.len.size() == 1; }
+
+// B is applied first, then A:  result = A after B.
+bool product(const Entries& A, const Entries& B, Entries& out) {
+  for (const Entry& a : A) {
+    int nb = 0;
+    for (const Entry& b : B) nb += (b.r == a.c);
+    if (nb > 1 && !a.linear) return false;  // phi(sum) != sum(phi)
+    if (nb == 0) {
+      if (a.linear) continue;  // A(0) = 0
+      Entry e;
+      e.r = a.r; e.c = 0; e.sign = a.sign; e.linear = false;
+      e.chain.push_back(mk(S_ZERO));
+      e.chain.insert(e.chain.end(), a.chain.begin(), a.chain.end());
+      out.push_back(std::move(e));
+      continue;
+    }
+    for (const Entry& b : B) {
+      if (b.r != a.c) continue;
+      Entry e;
+      e.r = a.r; e.c = b.c;
+      e.linear = a.linear && b.linear;
+      e.chain = b.chain;
+      if (b.sign < 0 && !a.linear) {
+        e.chain.push_back(mk(S_NEG));
+        e.sign = a.sign;
+      } else {
+        e.sign = a.sign * b.sign;
+      }
+      e.chain.insert(e.chain.end(), a.chain.begin(), a.chain.end());
+      if ((int)e.chain.size() > kMaxStagesPerTerm) return false;
+      if (chain_streams(e.chain) > kMaxStreamsPerTerm) return false;
+      out.push_back(std::move(e));
+      if (out.size() > kMaxEntries) return false;
+    }
+  }
+  return true;
+}
+
+// ops given in APPLICATION order (first applied first), all expanded with `mode`.
+bool expand_seq(const std::vector<jets_op>& seq, int mode, Entries& out, Space& isp, Space& osp) {
+  Entries cur;
+  Space cur_in, cur_out;
+  if (!expand(seq[0], mode, cur, cur_in, cur_out)) return false;
+  for (size_t i = 1; i < seq.size(); ++i) {
+    Entries nxt, prod;
+    Space nin, nout;
+    if (!expand(seq[i], mode, nxt, nin, nout)) return false;
+    if (!cur_out.same_layout(nin)) {
+      if (cur_out.total() != nin.total()) return false;
+      if (is_flat(nin) && is_flat(nout) && nin.total() == nout.total()) {
+        if (!reblock(nxt, cur_out)) return false;
+        nin = nout = cur_out;
+      } else if (is_flat(cur_out) && is_flat(cur_in) && cur_in.total() == cur_out.total()) {
+        if (!reblock(cur, nin)) return false;
+        cur_in = cur_out = nin;
+      } else {
+        return false;
+      }
+    }
+    if (!product(nxt, cur, prod)) return false;
+    cur.swap(prod);
+    cur_out = nout;
+  }
+  out.swap(cur);
+  isp = cur_in;
+  osp = cur_out;
+  return true;
+}
+
+std::vector<jets_op> app_order(jets_op a, int mode) {
+  std::vector<jets_op> seq;
+  if (mode == JETS_MODE_DFT) seq.assign(a->kids.begin(), a->kids.end());       // ops[1]' first (:537)
+  else seq.assign(a->kids.rbegin(), a->kids.rend());                          // ops[n] first (:525)
+  return seq;
+}
+
+bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
+  isp = in_space(a, mode);
+  osp = out_space(a, mode);
+  switch (a->kind) {
+    case K_DIAG: {
+      Entry e;
+      e.chain.push_back(mk(S_DIAG, 0, a->w->ptr()));
+      out.push_back(e);
+      return true;
+    }
+    case K_SCALE: {
+      Entry e;
+      e.chain.push_back(mk(S_SCALE, 0, nullptr, a->a));
+      out.push_back(e);
+      return true;
+    }
+    case K_PW: {
+      Entry e;
+      if (mode == JETS_MODE_F) {
+        e.linear = false;
+        e.chain.push_back(mk(S_PW_F, a->fn, nullptr, a->p));
+      } else {
+        JETS_CHECK(a->mo != nullptr, JETS_ERR_NO_POINT,
+                   "Jacobian of a pointwise operator applied before point!/jacobian set mo");
+        e.chain.push_back(mk(S_PW_J, a->fn, a->mo->ptr(), a->p));
+      }
+      out.push_back(e);
+      return true;
+    }
+    case K_STENCIL: {
+      Entry e;
+      if (a->fn == JETS_ST_FDIFF) e.chain.push_back(mk(mode == JETS_MODE_DFT ? S_BDIFF : S_FDIFF));
+      else e.chain.push_back(mk(S_LAP));
+      out.push_back(e);
+      return true;
+    }
+    case K_ZERO: return true;  // contributes nothing (src/Jets.jl:942, skipped at :1022,:1047)
+    case K_DENSE: return false;
+    case K_LNVIEW: return expand(a->kids[0], map_mode_lnview(mode), out, isp, osp);
+    case K_ADJ: return expand(a->kids[0], map_mode_adj(mode), out, isp, osp);
+    case K_COMPOSE: return expand_seq(app_order(a, mode), mode, out, isp, osp);
+    case K_SUM: {
+      bool first = true;
+      for (size_t k = 0; k < a->kids.size(); ++k) {
+        Entries e;
+        Space ki, ko;
+        if (!expand(a->kids[k], mode, e, ki, ko)) return false;
+        if (first) { isp = ki; osp = ko; first = false; }
+        else if (!ki.same_layout(isp) || !ko.same_layout(osp)) {
+          if (is_flat(ki) && is_flat(ko) && isp.same_layout(osp)) {
+            if (!reblock(e, isp)) return false;
+          } else if (is_flat(isp) && is_flat(osp) && ki.same_layout(ko)) {
+            if (!reblock(out, ki)) return false;
+            isp = ki; osp = ko;
+          } else {
+            return false;
+          }
+        }
+        for (auto& x : e) {
+          x.sign *= a->sgn[k];
+          out.push_back(std::move(x));
+        }
+      }
+      return true;
+    }
+    case K_BLOCK: {
+      for (int c = 0; c < a->C; ++c)
+        for (int r = 0; r < a->R; ++r) {
+          Entries e;
+          Space ki, ko;
+          if (!expand(a->kids[r + (size_t)c * a->R], mode, e, ki, ko)) return false;
+          if (!is_flat(ki) || !is_flat(ko)) return false;  // nested block spaces are not supported
+          for (auto& x : e) {
+            if (x.r != 0 || x.c != 0) return false;
+            if (mode == JETS_MODE_DFT) { x.r = c; x.c = r; }
+            else { x.r = r; x.c = c; }
+            out.push_back(std::move(x));
+            if (out.size() > kMaxEntries) return false;
+          }
+        }
+      return true;
+    }
+  }
+  return false;
+}
+
+void halo_of(const Entries& es, int& hl, int& hr) {
+  hl = hr = 0;
+  for (const Entry& e : es) {
+    int l = 0, r = 0;
+    for (auto it = e.chain.rbegin(); it != e.chain.rend(); ++it) {
+      if (it->op == S_FDIFF) r += 1;
+      else if (it->op == S_BDIFF) l += 1;
+      else if (it->op == S_LAP) { l += 1; r += 1; }
+    }
+    hl = std::max(hl, l);
+    hr = std::max(hr, r);
+  }
+}
+
+std::vector<int64_t> offsets_of(const Space& s) {
+  std::vector<int64_t> o(s.len.size() + 1, 0);
+  for (size_t i = 0; i < s.len.size(); ++i) o[i + 1] = o[i] + s.len[i];
+  return o;
+}
+
+// ------------------------------------------------------------------ plan builder ---------
+struct Builder {
+  Plan& plan;
+  int dtype;
+  bool io_ok;     // apply's in/out are library-owned (guarded) and 16B aligned
+  int engine;     // 0 auto, 1 TMA, 2 LDG
+
+  Ref new_tmp(int64_t elems) {
+    const size_t bytes = (size_t)elems * dsize(dtype);
+    char* p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes + 2 * kGuardBytes));
+    CUDA_TRY(cudaMemset(p, 0, bytes + 2 * kGuardBytes));
+    plan.tmps.push_back(p);
+    plan.tmp_bytes.push_back(bytes);
+    Ref r;
+    r.which = 2 + (int)plan.tmps.size() - 1;
+    r.off = 0;
+    return r;
+  }
+  bool ref_ok(const Ref& r) const { return r.which >= 2 || io_ok; }
+
+  void emit_fill0(Ref dst, int64_t len) {
+    Step st;
+    st.kind = ST_FILL0;
+    st.dst = dst;
+    st.fill_len = len;
+    plan.steps.push_back(std::move(st));
+  }
+
+  // Entries use block coordinates of (out_sp, in_sp); dst/src give the flat base offsets.
+  void emit_fused(Entries& es, const Space& out_sp, const Space& in_sp, Ref dst, Ref src, int acc) {
+    int hl, hr;
+    halo_of(es, hl, hr);
+    JETS_CHECK(hl <= 1 && hr <= 1, JETS_ERR_UNSUPPORTED, "internal: halo too wide for fusion");
+    std::stable_sort(es.begin(), es.end(), [](const Entry& x, const Entry& y) {
+      return x.r != y.r ? x.r < y.r : x.c < y.c;
+    });
+    const auto oo = offsets_of(out_sp), io = offsets_of(in_sp);
+    const size_t esz = dsize(dtype);
+    FusedTables t;
+    t.hl = hl; t.hr = hr;
+    const int tile = fused_tile_elems(dtype);
+    bool tma = ref_ok(dst) && ref_ok(src) && (dst.off * esz) % 16 == 0 && (src.off * esz) % 16 == 0;
+    size_t k = 0;
+    int max_terms = 0;
+    for (size_t r = 0; r < out_sp.len.size(); ++r) {
+      FRow row{};
+      row.out_off = dst.off + oo[r];
+      row.len = out_sp.len[r];
+      row.term_begin = (int32_t)t.terms.size();
+      while (k < es.size() && es[k].r == (int)r) {
+        const Entry& e = es[k++];
+        FTerm tm{};
+        tm.in_off = src.off + io[e.c];
+        tm.in_abs = nullptr;
+        tm.stage_begin = (int32_t)t.stages.size();
+        for (const FStage& s : e.chain) {
+          t.stages.push_back(s);
+          if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
+        }
+        tm.stage_end = (int32_t)t.stages.size();
+        tm.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
+        tm.nstreams = chain_streams(e.chain);
+        t.max_streams = std::max(t.max_streams, tm.nstreams);
+        if ((tm.in_off * esz) % 16) tma = false;
+        JETS_CHECK(in_sp.len[e.c] == out_sp.len[r], JETS_ERR_SHAPE,
+                   "elementwise block (%d,%d) maps %lld -> %lld elements", (int)r, e.c,
+                   (long long)in_sp.len[e.c], (long long)out_sp.len[r]);
+        t.terms.push_back(tm);
+      }
+      row.term_end = (int32_t)t.terms.size();
+      row.init = (acc == ACC_SET) ? 0 : 1;
+      row.ntiles = (int32_t)((row.len + tile - 1) / tile);
+      if ((row.out_off * esz) % 16) tma = false;
+      max_terms = std::max(max_terms, row.term_end - row.term_begin);
+      if (row.term_end == row.term_begin && acc != ACC_SET) continue;  // nothing to add
+      if (row.len == 0) continue;
+      t.rows.push_back(row);
+    }
+    if (max_terms > fused_max_terms_tma()) tma = false;
+    if (fused_nslots(t.max_streams) < 2) tma = false;
+    t.tma_ok = tma;
+    bool use_tma = tma;
+    if (engine == 2) use_tma = false;
+    if (engine == 1 && !tma) JETS_FAIL(JETS_ERR_UNSUPPORTED, "TMA engine forced but operands are not aligned/guarded");
+
+    // schedule: rows sorted by chunk count (desc); segments with a constant set of active rows
+    const int K = fused_tiles_per_item();
+    std::vector<int32_t> order(t.rows.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
+    auto nchunks = [&](int32_t i) { return (int64_t)(t.rows[i].ntiles + K - 1) / K; };
+    std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return nchunks(x) > nchunks(y); });
+    std::vector<FSeg> segs;
+    int64_t pos = 0, begin = 0, ntiles = 0;
+    for (auto& r : t.rows) ntiles += r.ntiles;
+    for (int kact = (int)order.size(); kact >= 1; --kact) {
+      const int64_t upper = nchunks(order[kact - 1]);
+      if (upper > pos) {
+        FSeg sg{};
+        sg.tile_begin = begin; sg.pos_begin = pos; sg.nactive = kact;
+        segs.push_back(sg);
+        begin += (upper - pos) * kact;
+        pos = upper;
+      }
+    }
+    Step st;
+    st.kind = ST_FUSED;
+    st.src = src; st.dst = dst; st.acc = acc;
+    DevFused& f = st.fused;
+    f.nrows = (int32_t)t.rows.size();
+    f.nsegs = (int32_t)segs.size();
+    f.ntiles = ntiles;
+    f.nitems = begin;
+    f.hl = hl; f.hr = hr; f.max_streams = t.max_streams;
+    f.tile_elems = tile;
+    f.use_tma = use_tma;
+    if (f.nrows > 0) {
+      auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+      const size_t b0 = 0, b1 = b0 + al(t.stages.size() * sizeof(FStage)),
+                   b2 = b1 + al(t.terms.size() * sizeof(FTerm)), b3 = b2 + al(t.rows.size() * sizeof(FRow)),
+                   b4 = b3 + al(segs.size() * sizeof(FSeg)), b5 = b4 + al(order.size() * sizeof(int32_t));
+      std::vector<char> host(b5, 0);
+      if (!t.stages.empty()) memcpy(host.data() + b0, t.stages.data(), t.stages.size() * sizeof(FStage));
+      if (!t.terms.empty()) memcpy(host.data() + b1, t.terms.data(), t.terms.size() * sizeof(FTerm));
+      memcpy(host.data() + b2, t.rows.data(), t.rows.size() * sizeof(FRow));
+      memcpy(host.data() + b3, segs.data(), segs.size() * sizeof(FSeg));
+      memcpy(host.data() + b4, order.data(), order.size() * sizeof(int32_t));
+      char* blob = nullptr;
+      CUDA_TRY(cudaMalloc(&blob, b5));
+      CUDA_TRY(cudaMemcpy(blob, host.data(), b5, cudaMemcpyHostToDevice));
+      plan.blobs.push_back(blob);
+      f.blob = blob;
+      f.stages = reinterpret_cast<FStage*>(blob + b0);
+      f.terms = reinterpret_cast<FTerm*>(blob + b1);
+      f.rows = reinterpret_cast<FRow*>(blob + b2);
+      f.segs = reinterpret_cast<FSeg*>(blob + b3);
+      f.order = reinterpret_cast<int32_t*>(blob + b4);
+    }
+    plan.engines |= use_tma ? 1 : 2;
+    plan.steps.push_back(std::move(st));
+  }
+
+  // Dense entries sharing one orientation; groups = distinct output blocks.
+  void emit_gemv(std::vector<DBlock>& blocks, int acc) {
+    if (blocks.empty()) return;
+    std::stable_sort(blocks.begin(), blocks.end(),
+                     [](const DBlock& x, const DBlock& y) { return x.out_off < y.out_off; });
+    Step st;
+    st.kind = ST_GEMV;
+    st.acc = acc;
+    std::vector<int32_t> row_ptr{0}, tile_ptr{0};
+    const bool trans = blocks[0].trans != 0;
+    for (size_t i = 0; i < blocks.size(); ++i) {
+      const bool last = i + 1 == blocks.size() || blocks[i + 1].out_off != blocks[i].out_off;
+      if (last) {
+        row_ptr.push_back((int32_t)i + 1);
+        int32_t nt;
+        gemv_tile_count(dtype, trans, trans ? blocks[i].cols : blocks[i].rows, &nt);
+        tile_ptr.push_back(tile_ptr.back() + nt);
+      }
+    }
+    st.n_out_rows = (int32_t)row_ptr.size() - 1;
+    st.gemv_tiles = tile_ptr.back();
+    st.dblocks = blocks;
+    const size_t nb = blocks.size() * sizeof(DBlock);
+    const size_t nb_al = (nb + 255) & ~(size_t)255;
+    std::vector<char> host(nb_al + 2 * row_ptr.size() * sizeof(int32_t));
+    memcpy(host.data(), blocks.data(), nb);
+    memcpy(host.data() + nb_al, row_ptr.data(), row_ptr.size() * sizeof(int32_t));
+    memcpy(host.data() + nb_al + row_ptr.size() * sizeof(int32_t), tile_ptr.data(), tile_ptr.size() * sizeof(int32_t));
+    char* blob = nullptr;
+    CUDA_TRY(cudaMalloc(&blob, host.size()));
+    CUDA_TRY(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+    plan.blobs.push_back(blob);
+    st.d_dblocks = reinterpret_cast<DBlock*>(blob);
+    st.d_row_ptr = reinterpret_cast<int32_t*>(blob + nb_al);
+    plan.engines |= 4;
+    plan.steps.push_back(std::move(st));
+  }
+
+  // Is `a` (possibly under adjoint / linear views) a plain dense leaf?  Returns the leaf and the
+  // effective orientation for `mode`.
+  static jets_op dense_leaf(jets_op a, int mode, bool& trans) {
+    while (true) {
+      if (a->kind == K_LNVIEW) { mode = map_mode_lnview(mode); a = a->kids[0]; }
+      else if (a->kind == K_ADJ) { mode = map_mode_adj(mode); a = a->kids[0]; }
+      else break;
+    }
+    if (a->kind != K_DENSE) return nullptr;
+    trans = (mode == JETS_MODE_DFT);
+    return a;
+  }
+
+  void push_dense(std::vector<DBlock>& n, std::vector<DBlock>& t, jets_op leaf, bool trans,
+                  int64_t out_off, int64_t in_off, int which_src, int which_dst) {
+    (void)which_src; (void)which_dst;
+    for (int64_t k = 0; k < leaf->nrhs; ++k) {
+      DBlock b{};
+      b.A = leaf->w->ptr();
+      b.rows = (int32_t)leaf->rows; b.cols = (int32_t)leaf->cols; b.lda = (int32_t)leaf->rows;
+      b.trans = trans; b.nrhs = 1;
+      b.in_off = in_off + k * (trans ? leaf->rows : leaf->cols);
+      b.out_off = out_off + k * (trans ? leaf->cols : leaf->rows);
+      (trans ? t : n).push_back(b);
+    }
+  }
+
+  static int combine(int acc, int sgn) {  // accumulate mode for a signed term under `acc`
+    const int eff = (acc == ACC_SUB ? -1 : 1) * sgn;
+    return eff > 0 ? ACC_ADD : ACC_SUB;
+  }
+
+  void lower(jets_op a, int mode, Ref dst, Ref src, int acc) {
+    {
+      Entries es;
+      Space isp, osp;
+      int hl = 0, hr = 0;
+      if (expand(a, mode, es, isp, osp)) {
+        halo_of(es, hl, hr);
+        if (hl <= 1 && hr <= 1) {
+          emit_fused(es, osp, isp, dst, src, acc);
+          return;
+        }
+      }
+    }
+    switch (a->kind) {
+      case K_LNVIEW: lower(a->kids[0], map_mode_lnview(mode), dst, src, acc); return;
+      case K_ADJ: lower(a->kids[0], map_mode_adj(mode), dst, src, acc); return;
+      case K_DENSE: {
+        std::vector<DBlock> n, t;
+        push_dense(n, t, a, mode == JETS_MODE_DFT, dst.off, src.off, 0, 0);
+        Step* st;
+        emit_gemv(n.empty() ? t : n, acc);
+        st = &plan.steps.back();
+        st->src = src; st->dst = dst;
+        return;
+      }
+      case K_COMPOSE: {
+        plan.engines |= 16;
+        const std::vector<jets_op> seq = app_order(a, mode);
+        size_t i = 0;
+        Ref cur = src;
+        while (i < seq.size()) {
+          // longest fusible run starting at i
+          size_t best = 0;
+          Entries best_es;
+          Space best_in, best_out;
+          for (size_t j = seq.size(); j > i; --j) {
+            std::vector<jets_op> grp(seq.begin() + i, seq.begin() + j);
+            Entries es;
+            Space gi, go;
+            int hl, hr;
+            if (expand_seq(grp, mode, es, gi, go)) {
+              halo_of(es, hl, hr);
+              if (hl <= 1 && hr <= 1) { best = j; best_es.swap(es); best_in = gi; best_out = go; break; }
+            }
+          }
+          const size_t j = best ? best : i + 1;
+          const bool last = (j == seq.size());
+          const Space& osp = out_space(seq[j - 1], mode);
+          Ref nxt = last ? dst : new_tmp(osp.total());
+          const int nacc = last ? acc : ACC_SET;
+          if (best) emit_fused(best_es, best_out, best_in, nxt, cur, nacc);
+          else lower(seq[i], mode, nxt, cur, nacc);
+          cur = nxt;
+          i = j;
+        }
+        return;
+      }
+      case K_SUM: {
+        plan.engines |= 16;
+        int first = acc;
+        if (acc == ACC_SET) {
+          if (a->sgn[0] > 0) first = ACC_SET;
+          else { emit_fill0(dst, out_space(a, mode).total()); first = ACC_SUB; }
+        } else {
+          first = combine(acc, a->sgn[0]);
+        }
+        for (size_t k = 0; k < a->kids.size(); ++k) {
+          const int m = (k == 0) ? first : combine(acc == ACC_SET ? ACC_ADD : acc, a->sgn[k]);
+          lower(a->kids[k], mode, dst, src, m);
+        }
+        return;
+      }
+      case K_BLOCK: {
+        const bool adj = (mode == JETS_MODE_DFT);
+        const Space& osp = out_space(a, mode);
+        const Space& isp = in_space(a, mode);
+        const auto oo = offsets_of(osp), io = offsets_of(isp);
+        const int nout = (int)osp.len.size();
+        std::vector<DBlock> dn, dt;
+        Entries fes;
+        struct Rest { jets_op op; int o, i; };
+        std::vector<Rest> rest;
+        std::vector<int> covered(nout, 0);
+        for (int c = 0; c < a->C; ++c)
+          for (int r = 0; r < a->R; ++r) {
+            jets_op kid = a->kids[r + (size_t)c * a->R];
+            const int o = adj ? c : r, i = adj ? r : c;
+            bool trans = false;
+            if (jets_op leaf = dense_leaf(kid, mode, trans)) {
+              push_dense(dn, dt, leaf, trans, dst.off + oo[o], src.off + io[i], 0, 0);
+              covered[o] |= trans ? 2 : 1;
+              continue;
+            }
+            Entries es;
+            Space ki, ko;
+            int hl, hr;
+            if (expand(kid, mode, es, ki, ko)) {
+              halo_of(es, hl, hr);
+              bool ok = hl <= 1 && hr <= 1 && is_flat(ki) && is_flat(ko);
+              for (auto& x : es) ok = ok && x.r == 0 && x.c == 0;
+              if (ok) {
+                for (auto& x : es) { x.r = o; x.c = i; fes.push_back(std::move(x)); }
+                continue;
+              }
+            }
+            rest.push_back({kid, o, i});
+          }
+        // Pure dense, one orientation, every output block covered: SET directly (one launch).
+        const bool pure = fes.empty() && rest.empty() && (dn.empty() || dt.empty()) &&
+                          std::all_of(covered.begin(), covered.end(), [](int v) { return v != 0; });
+        int cur = acc;
+        if (pure) {
+          emit_gemv(dn.empty() ? dt : dn, acc);
+          plan.steps.back().src = Ref{src.which, 0};
+          plan.steps.back().dst = Ref{dst.which, 0};
+          return;
+        }
+        plan.engines |= 16;
+        // first the fused part (it can SET: rows without fused terms are zero-filled by it) ...
+        emit_fused(fes, osp, isp, dst, src, acc);
+        cur = (acc == ACC_SET) ? ACC_ADD : acc;
+        // ... then dense tables and whatever is left accumulate on top
+        for (auto* v : {&dn, &dt}) {
+          if (v->empty()) continue;
+          emit_gemv(*v, cur);
+          plan.steps.back().src = Ref{src.which, 0};
+          plan.steps.back().dst = Ref{dst.which, 0};
+        }
+        for (auto& x : rest) {
+          Ref d = dst, s = src;
+          d.off += oo[x.o];
+          s.off += io[x.i];
+          lower(x.op, mode, d, s, cur);
+        }
+        return;
+      }
+      default: JETS_FAIL(JETS_ERR_UNSUPPORTED, "internal: cannot lower operator kind %d", (int)a->kind);
+    }
+  }
+};
+
+}  // namespace
+
+Plan::~Plan() {
+  for (void* p : tmps) cudaFree(p);
+  for (void* p : blobs) cudaFree(p);
+}
+
+std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok, int engine) {
+  auto plan = std::make_shared<Plan>();
+  g_esz = dsize(a->dtype);
+  Builder b{*plan, a->dtype, io_ok, engine};
+  int acc = ACC_SET;
+  if (accumulate) {
+    // quirk Q1 (src/Jets.jl:1001,1024): only a forward block apply with ncol>1 accumulates
+    jets_op t = a;
+    int m = mode;
+    while (t->kind == K_LNVIEW) { m = map_mode_lnview(m); t = t->kids[0]; }
+    if (t->kind == K_BLOCK && t->C > 1 && m != JETS_MODE_DFT) acc = ACC_ADD;
+  }
+  b.lower(a, mode, Ref{1, 0}, Ref{0, 0}, acc);
+  plan->version = g_epoch;
+  return plan;
+}
+
+void run_plan(Plan& p, int dtype, char* in, char* out) {
+  Context& c = ctx();
+  auto base = [&](const Ref& r) -> char* {
+    if (r.which == 0) return in;
+    if (r.which == 1) return out;
+    return reinterpret_cast<char*>(p.tmps[r.which - 2]) + kGuardBytes;
+  };
+  for (Step& st : p.steps) {
+    switch (st.kind) {
+      case ST_FUSED: launch_fused(st.fused, dtype, base(st.src), base(st.dst), c.stream); break;
+      case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;
+      case ST_FILL0:
+        vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);
+        break;
+    }
+  }
+}
+
+}  // namespace jets

@@ -1,0 +1,140 @@
+"""LSQR-style caller of the hot path: every iteration is A*v, A'*u, two norms and
+a handful of BlockArray broadcast updates -- exactly what IterativeSolvers.lsqr does with a Jets
+operator (docs/src/index.md:235-246).  Written only with the public API of this package so that
+it exercises mul!, adjoint mul!, norm and the broadcast updates the way a Jets user would.
+
+``lsqr``         host scalars: two stream synchronisations per iteration (the norms).
+``lsqr_graph``   device scalars + one CUDA graph per iteration: no host round trip at all.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+from . import _lib as L
+from ._lib import check, lib
+from . import core as J
+
+
+def lsqr(A, b, iters=10, x0=None):
+    """Golub-Kahan LSQR (Paige & Saunders 1982) without stopping tests: exactly ``iters``
+    iterations.  Returns (x, history of (alpha, beta))."""
+    x = J.zeros(J.domain(A)) if x0 is None else x0
+    At = J.adjoint(A)
+    u = b.copy()
+    beta = float(J.norm(u))
+    J.lincomb_(u, [(1.0 / beta, u)])
+    v = At * u
+    alpha = float(J.norm(v))
+    J.lincomb_(v, [(1.0 / alpha, v)])
+    w = v.copy()
+    phibar, rhobar = beta, alpha
+    tmp_u = J.zeros(J.range_(A))
+    tmp_v = J.zeros(J.domain(A))
+    hist = []
+    for _ in range(iters):
+        J.mul_(tmp_u, A, v)                                  # u = A v - alpha u
+        J.lincomb_(u, [(1.0, tmp_u), (-alpha, u)])
+        beta = float(J.norm(u))
+        J.lincomb_(u, [(1.0 / beta, u)])
+        J.mul_(tmp_v, At, u)                                 # v = A' u - beta v
+        J.lincomb_(v, [(1.0, tmp_v), (-beta, v)])
+        alpha = float(J.norm(v))
+        J.lincomb_(v, [(1.0 / alpha, v)])
+        rho = (rhobar * rhobar + beta * beta) ** 0.5
+        c, s = rhobar / rho, beta / rho
+        theta = s * alpha
+        rhobar = -c * alpha
+        phi = c * phibar
+        phibar = s * phibar
+        J.lincomb_(x, [(1.0, x), (phi / rho, w)])            # x += (phi/rho) w
+        J.lincomb_(w, [(1.0, v), (-theta / rho, w)])         # w = v - (theta/rho) w
+        hist.append((alpha, beta))
+    return x, hist
+
+
+class _S:
+    """Device scalar (jets_scalar)."""
+
+    def __init__(self, v=0.0):
+        L.ensure_init()
+        self.h = C.c_void_p()
+        check(lib.jets_scalar_create(C.byref(self.h)))
+        if v:
+            self.set(v)
+
+    def set(self, v):
+        check(lib.jets_scalar_set(self.h, float(v)))
+
+    def get(self):
+        r = C.c_double()
+        check(lib.jets_scalar_get(self.h, C.byref(r)))
+        return r.value
+
+    def __del__(self):
+        try:
+            lib.jets_scalar_destroy(self.h)
+        except Exception:
+            pass
+
+
+def _sop(out, op, a, b=None):
+    check(lib.jets_scalar_op(out.h, op.encode(), a.h, b.h if b is not None else None))
+
+
+def _axpby(out, sa, ca, af, x, sb=None, cb=0.0, bf=0, y=None):
+    check(lib.jets_axpby_dev(out._h, sa.h if sa is not None else None, ca, af, x._h,
+                             sb.h if sb is not None else None, cb, bf, y._h if y is not None else None))
+
+
+def lsqr_graph(A, b, iters=10):
+    """Same recurrences with every scalar resident on the device; one iteration is captured once
+    in a CUDA graph and replayed ``iters`` times (no host synchronisation inside the loop)."""
+    x = J.zeros(J.domain(A))
+    At = J.adjoint(A)
+    u = b.copy()
+    beta, alpha, rho, rhobar, phibar, phi, theta, c, s, t1, t2 = (_S() for _ in range(11))
+    check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+    _axpby(u, beta, 0.0, L.COEF_INV, u)
+    v = At * u
+    check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+    _axpby(v, alpha, 0.0, L.COEF_INV, v)
+    w = v.copy()
+    _sop(phibar, "+", beta)      # phibar = beta  (x + 0)
+    _sop(rhobar, "+", alpha)
+    tmp_u = J.zeros(J.range_(A))
+    tmp_v = J.zeros(J.domain(A))
+
+    def body():
+        J.mul_(tmp_u, A, v)
+        _axpby(u, None, 1.0, 0, tmp_u, alpha, 0.0, L.COEF_NEG, u)        # u = A v - alpha u
+        check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+        _axpby(u, beta, 0.0, L.COEF_INV, u)
+        J.mul_(tmp_v, At, u)
+        _axpby(v, None, 1.0, 0, tmp_v, beta, 0.0, L.COEF_NEG, v)         # v = A' u - beta v
+        check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+        _axpby(v, alpha, 0.0, L.COEF_INV, v)
+        _sop(rho, "h", rhobar, beta)
+        _sop(c, "/", rhobar, rho)
+        _sop(s, "/", beta, rho)
+        _sop(theta, "*", s, alpha)
+        _sop(t1, "*", c, alpha)
+        _sop(rhobar, "n", t1)
+        _sop(phi, "*", c, phibar)
+        _sop(phibar, "*", s, phibar)
+        _sop(t1, "/", phi, rho)
+        _sop(t2, "/", theta, rho)
+        _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                        # x += (phi/rho) w
+        _axpby(w, None, 1.0, 0, v, t2, 0.0, L.COEF_NEG, w)               # w = v - (theta/rho) w
+
+    body()  # warm-up builds every plan outside the capture
+    check(lib.jets_graph_begin())
+    try:
+        body()
+    finally:
+        g = C.c_void_p()
+        check(lib.jets_graph_end(C.byref(g)))
+    for _ in range(iters - 1):
+        check(lib.jets_graph_launch(g))
+    J.sync()
+    check(lib.jets_graph_destroy(g))
+    return x, (alpha.get(), beta.get())

@@ -166,6 +166,7 @@ class BlockArray:
     """Vector of independently stored block arrays + their index ranges (:809-812)."""
 
     __array_priority__ = 100
+    __array_ufunc__ = None  # numpy scalars/arrays defer to the reflected operators below
 
     def __init__(self, arrays, idx):
         self.arrays = list(arrays)
@@ -507,6 +508,7 @@ class Jop:
         return adjoint(self)
 
     __array_priority__ = 200
+    __array_ufunc__ = None
 
 
 class JopNl(Jop):
