@@ -181,7 +181,29 @@ struct FRow {        // 40 bytes
   int32_t term_begin, term_end;
   int32_t init;      // 0 zero-init, 1 accumulate onto existing out, 2 leave untouched
   int32_t ntiles;
-  int64_t pad;
+  int32_t group_begin, group_end;  // term groups (one TMA slot each)
+};
+// Compact, kernel-facing description of a term GROUP: consecutive terms of one output row whose
+// operand streams share one TMA slot.  Lives in global memory (read-only, L1/L2 resident): the
+// producer reads ptr/nstreams, the consumers read terms/stages.
+constexpr int kMaxStages = 6;     // per term (longer chains are split by the planner)
+constexpr int kMaxStreams = 4;    // operand streams per slot (= per term group)
+constexpr int kGroupTerms = 4;    // terms of one output tile that share a slot
+constexpr int kGroupStages = 12;  // stage pool of a group
+struct CStage {      // 16 bytes
+  uint8_t op, fn, has_stream, pad0;
+  uint32_t pad1;
+  double c0;
+};
+struct GTerm {       // 8 bytes
+  int16_t stage0, nstages;   // into the group's stage pool
+  int16_t stream0, sign;     // first operand stream of the term inside the slot
+};
+struct GroupRec {    // 272 bytes
+  int64_t ptr[kMaxStreams];  // absolute address, or byte offset from the apply's `in` base (rel_mask bit)
+  int32_t nstreams, nterms, rel_mask, pad;
+  GTerm terms[kGroupTerms];
+  CStage stages[kGroupStages];
 };
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
   int64_t tile_begin;
@@ -194,6 +216,7 @@ struct FusedTables {
   std::vector<FStage> stages;
   std::vector<FTerm> terms;
   std::vector<FRow> rows;
+  std::vector<GroupRec> groups;
   int hl = 0, hr = 0;     // halo (elements) the chains need on the left / right
   int max_streams = 1;
   bool tma_ok = false;    // all streams 16B aligned + guarded
@@ -203,14 +226,17 @@ struct DevFused {   // device copy + launch geometry
   FStage* stages = nullptr;
   FTerm* terms = nullptr;
   FRow* rows = nullptr;
+  GroupRec* groups = nullptr;
   FSeg* segs = nullptr;
   int32_t* order = nullptr;  // rows sorted by ntiles (desc)
   int32_t nrows = 0, nsegs = 0;
   int64_t ntiles = 0;   // real tiles
   int64_t nitems = 0;   // (row, chunk-of-tiles) work items
-  int hl = 0, hr = 0, max_streams = 1;
+  int hl = 0, hr = 0, slot_streams = 1;
+  int S = 1;            // tiles per (super-chunk, row) item
   int tile_elems = 0;
   bool use_tma = false;
+  bool heavy = false;   // chains use transcendental pointwise functions
   void* blob = nullptr;
 };
 
@@ -264,8 +290,7 @@ void run_plan(Plan& p, int dtype, char* in, char* out);
 // kernels_fused.cu
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
 int fused_tile_elems(int dtype);
-int fused_tiles_per_item();
-int fused_max_terms_tma();
+int fused_nslots(int slot_streams);
 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);

@@ -12,17 +12,11 @@ template <typename T> struct VecOf;
 template <> struct VecOf<float>  { using type = float4;  static constexpr int V = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int V = 2; };
 
-// Compact stage descriptor as consumed by the kernels (16 bytes).
-struct CStage {
-  uint8_t op, fn, has_stream, pad0;
-  uint32_t pad1;
-  double c0;
-};
-constexpr int kMaxStages = 6;   // per term (longer chains are split by the planner)
-constexpr int kMaxStreams = 4;  // input + 3 operand streams per term
-
-template <typename T>
+// HEAVY=false instantiations only know x^2 (the transcendental bodies, double-precision pow in
+// particular, are hundreds of instructions and would evict the streaming loop from the I-cache).
+template <typename T, bool HEAVY>
 __device__ __forceinline__ T pw_phi(int fn, T x, T p) {
+  if (!HEAVY) return x * x;
   switch (fn) {
     case JETS_PW_SQUARE: return x * x;
     case JETS_PW_POWER:  return pow(x, p);
@@ -31,8 +25,9 @@ __device__ __forceinline__ T pw_phi(int fn, T x, T p) {
     default:             return tanh(x);
   }
 }
-template <typename T>
+template <typename T, bool HEAVY>
 __device__ __forceinline__ T pw_dphi(int fn, T x, T p) {
+  if (!HEAVY) return T(2) * x;
   switch (fn) {
     case JETS_PW_SQUARE: return T(2) * x;
     case JETS_PW_POWER:  return p * pow(x, p - T(1));
@@ -42,11 +37,19 @@ __device__ __forceinline__ T pw_dphi(int fn, T x, T p) {
   }
 }
 
+__device__ __forceinline__ CStage load_stage(const CStage* p) {
+  // 16-byte uniform load; global tables go through the read-only (L1) path
+  const uint4 r = *reinterpret_cast<const uint4*>(p);
+  CStage s;
+  *reinterpret_cast<uint4*>(&s) = r;
+  return s;
+}
+
 // Evaluates one term on NV windows at once.  val[i][w] holds the chain value at block-local
 // position p0[i] - HL + w.  `ld(k, i, out)` loads the window of operand stream k for vector i.
 // Positions outside [0, len) may hold garbage; every stencil masks them with a select, so
 // garbage never reaches a valid position.
-template <typename T, int HL, int HR, int NV, class Loader>
+template <typename T, int HL, int HR, int NV, bool HEAVY, class Loader>
 __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int nstages,
                                           Loader& ld, const int64_t (&p0)[NV], int64_t len,
                                           T (&val)[NV][HL + VecOf<T>::V + HR]) {
@@ -55,7 +58,7 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
   for (int i = 0; i < NV; ++i) ld(0, i, val[i]);
   int sidx = 1;
   for (int s = 0; s < nstages; ++s) {
-    const CStage st = stages[s];
+    const CStage st = load_stage(stages + s);
     switch (st.op) {
       case S_SCALE: {
         const T c = (T)st.c0;
@@ -79,7 +82,7 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
 #pragma unroll
         for (int i = 0; i < NV; ++i)
 #pragma unroll
-          for (int w = 0; w < W; ++w) val[i][w] = pw_phi<T>(st.fn, val[i][w], p);
+          for (int w = 0; w < W; ++w) val[i][w] = pw_phi<T, HEAVY>(st.fn, val[i][w], p);
       } break;
       case S_PW_J: {
         const T p = (T)st.c0;
@@ -88,7 +91,7 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
           T b[W];
           ld(sidx, i, b);
 #pragma unroll
-          for (int w = 0; w < W; ++w) val[i][w] = pw_dphi<T>(st.fn, b[w], p) * val[i][w];
+          for (int w = 0; w < W; ++w) val[i][w] = pw_dphi<T, HEAVY>(st.fn, b[w], p) * val[i][w];
         }
         ++sidx;
       } break;

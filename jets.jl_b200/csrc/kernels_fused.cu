@@ -7,9 +7,15 @@
 //
 // TMA engine (default): a warp-specialised persistent kernel, one CTA per SM.  A producer warp
 // streams operand tiles HBM -> shared memory with cp.async.bulk (1-D TMA) through a ring of
-// mbarrier-guarded slots; 8 consumer warps interpret the chain on 128-bit vectors read from
-// shared memory (halo elements for stencils come from the same staged tile) and write the
-// output with coalesced 128-bit stores.
+// mbarrier-guarded slots; one slot carries every operand stream of a GROUP of terms of one output
+// tile (up to 4 streams), so a block-tridiagonal row (3 terms, 4 streams) costs one barrier round
+// trip per tile.  16 consumer warps interpret the chains on 128-bit vectors read from shared
+// memory (stencil halo elements come from the same staged tile) and write the output with
+// coalesced 128-bit stores.
+// Tiles are visited in (super-chunk, row, position) order and dealt round-robin to the CTAs: at
+// any instant all SMs stream one contiguous window of a block (DRAM-page friendly, like a plain
+// streaming kernel), while rows that share an input block follow each other closely enough for the
+// shared tile to be an L2 hit.
 // LDG engine (fallback for unaligned / caller-owned memory, and the A/B comparison): same
 // interpreter, operands read with guarded global loads.
 #include "fused_ops.cuh"
@@ -20,44 +26,39 @@ namespace {
 constexpr int kTileBytes = 8192;            // per stream per slot
 constexpr int kPad = 16;                    // halo padding on either side of a staged tile
 constexpr int kBufBytes = kTileBytes + 2 * kPad;
-constexpr int kConsumers = 256;
+constexpr int kConsumerWarps = 16;
+constexpr int kConsumers = kConsumerWarps * 32;
 constexpr int kThreads = kConsumers + 32;   // + producer warp
-constexpr int kVPT = kTileBytes / 16 / kConsumers;  // vectors per consumer thread per tile (2)
 constexpr int kMaxSlots = 16;
-constexpr int kTilesPerItem = 8;            // consecutive tiles of one row share a descriptor
-constexpr int kMaxTermsTMA = 64;            // job-cache capacity (terms per row)
 constexpr int kSmemLimit = 227 * 1024;
+constexpr int kLdgThreads = 256;
+constexpr int kLdgVPT = kTileBytes / 16 / kLdgThreads;
 
 enum : int { F_FIRST = 1, F_LAST = 2, F_END = 4, F_ACC = 8, F_NOTERM = 16 };
 
-struct SlotMeta {                 // written by the producer, read by consumers (smem)
+struct SlotMeta {                 // written by the producer, read by consumers (smem), 48 bytes
   int64_t tile_start;             // block-local element index of the tile
   int64_t len;                    // block length
   char* out_tile;                 // absolute address of out[tile_start]
+  const GroupRec* rec;            // static description of the term group (global, read-only)
   int32_t nvalid;
   int32_t flags;
-  int32_t sign;
-  int32_t nstages;
-  CStage stages[kMaxStages];
 };
-static_assert(sizeof(SlotMeta) == 40 + 16 * kMaxStages, "SlotMeta layout");
 
-struct Job {                      // producer-private cache of one term (smem)
-  const char* ptr[kMaxStreams];
-  int32_t nstreams, nstages, sign, pad;
-  CStage stages[kMaxStages];
-};
+constexpr int kHdrBytes = 256 + kMaxSlots * (int)sizeof(SlotMeta);
+constexpr int kHdrAligned = (kHdrBytes + 127) & ~127;
 
 struct FusedParams {
   const FStage* stages;
   const FTerm* terms;
+  const GroupRec* groups;
   const FRow* rows;
   const FSeg* segs;
   const int32_t* order;
   int32_t nsegs;
   int32_t nslots;
-  int32_t max_streams;
-  int32_t pad;
+  int32_t slot_streams;
+  int32_t S;          // tiles per (super-chunk, row) item
   int64_t nitems;
   const char* in;
   char* out;
@@ -102,8 +103,8 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 // ------------------------------------------------------------------ schedule -------------
-// item -> (row, chunk): items are ordered chunk-major so that all rows touching the same
-// positions of the input run back to back (the shared input tile is then an L2 hit).
+// item -> (row, super-chunk): items are ordered super-chunk-major so that all rows touching the
+// same positions of an input block run back to back (the shared input tile is an L2 hit).
 __device__ __forceinline__ void decode_item(const FusedParams& P, int64_t item, int32_t& row,
                                             int64_t& chunk) {
   int lo = 0, hi = P.nsegs - 1;
@@ -118,15 +119,15 @@ __device__ __forceinline__ void decode_item(const FusedParams& P, int64_t item, 
 }
 
 // ------------------------------------------------------------------ loaders --------------
-template <typename T, int HL, int HR>
+template <typename T, int HL, int HR, int NV>
 struct SmemLoader {
   using Vec = typename VecOf<T>::type;
   static constexpr int V = VecOf<T>::V;
   static constexpr int W = HL + V + HR;
-  const char* slot;  // slot base (stream 0)
-  int e0[kVPT];      // element offset of each owned vector inside the tile
+  const char* base;  // slot base + stream0 of the current term
+  int e0[NV];        // element offset of each owned vector inside the tile
   __device__ __forceinline__ void operator()(int k, int i, T (&out)[W]) const {
-    const char* b = slot + k * kBufBytes + kPad + e0[i] * (int)sizeof(T);
+    const char* b = base + k * kBufBytes + kPad + e0[i] * (int)sizeof(T);
     const Vec v = *reinterpret_cast<const Vec*>(b);
     const T* vs = reinterpret_cast<const T*>(&v);
 #pragma unroll
@@ -138,13 +139,13 @@ struct SmemLoader {
   }
 };
 
-template <typename T, int HL, int HR>
+template <typename T, int HL, int HR, int NV>
 struct GlobalLoader {
   using Vec = typename VecOf<T>::type;
   static constexpr int V = VecOf<T>::V;
   static constexpr int W = HL + V + HR;
   const char* ptr[kMaxStreams];  // block start of each stream
-  int64_t p0[kVPT];
+  int64_t p0[NV];
   int64_t len;
   __device__ __forceinline__ void operator()(int k, int i, T (&out)[W]) const {
     const T* base = reinterpret_cast<const T*>(ptr[k]);
@@ -207,7 +208,7 @@ __device__ __forceinline__ void store_out(char* out_tile, int e0, int nvalid,
 }
 
 // ------------------------------------------------------------------ TMA engine -----------
-template <typename T, int HL, int HR>
+template <typename T, int HL, int HR, bool HEAVY>
 __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const FusedParams P) {
   constexpr int V = VecOf<T>::V;
   constexpr int W = HL + V + HR;
@@ -216,294 +217,268 @@ __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const Fused
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kMaxSlots]
   uint64_t* empty = full + kMaxSlots;                          // [kMaxSlots]
   SlotMeta* meta = reinterpret_cast<SlotMeta*>(smem + 256);    // [kMaxSlots]
-  Job* jobs = reinterpret_cast<Job*>(smem + 256 + kMaxSlots * sizeof(SlotMeta));  // [kMaxTermsTMA]
-  constexpr int kHdr = 256 + kMaxSlots * (int)sizeof(SlotMeta) + kMaxTermsTMA * (int)sizeof(Job);
-  constexpr int kHdrAligned = (kHdr + 127) & ~127;
   unsigned char* slots = smem + kHdrAligned;
   const int nslots = P.nslots;
-  const int slot_bytes = P.max_streams * kBufBytes;
+  const int slot_bytes = P.slot_streams * kBufBytes;
 
   const int tid = threadIdx.x;
   if (tid == 0) {
     for (int s = 0; s < nslots; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], kConsumers / 32);
+      mbar_init(&empty[s], kConsumerWarps);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  // contiguous, balanced range of the (item, tile-in-item) sequence for this CTA
-  const int64_t Q = P.nitems * kTilesPerItem;
-  const int64_t q0 = (Q * blockIdx.x) / gridDim.x;
-  const int64_t q1 = (Q * (blockIdx.x + 1)) / gridDim.x;
-
   if (tid >= kConsumers) {
     // =============================== producer warp ===============================
+    // Tiles q = blockIdx.x, +gridDim.x, ... ; q = item * S + tin.  Lane g of the warp issues the
+    // g-th term group of the current tile (its own slot, its own barrier, its own bulk copies).
     const int lane = tid - kConsumers;
-    uint32_t it = 0;  // slots issued so far
-    int32_t row_id = -1;
+    const int64_t Q = P.nitems * P.S;
+    int slot = 0;            // next slot to fill (ring position) and its use parity
+    uint32_t par = 0;
+    int64_t item = (int64_t)blockIdx.x / P.S;
+    int tin = (int)((int64_t)blockIdx.x - item * P.S);
+    int64_t cur_item = -1;
     int64_t chunk = 0;
+    int32_t row_id = 0;
     FRow row;
-    int nterms = 0;
+    int ngroups = 0;
     const int G = nslots < 32 ? nslots : 32;
-    for (int64_t q = q0; q < q1; ++q) {
-      const int64_t item = q / kTilesPerItem;
-      const int tin = (int)(q % kTilesPerItem);
-      if (row_id < 0 || tin == 0) {
+    for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
+      if (item != cur_item) {
+        cur_item = item;
         decode_item(P, item, row_id, chunk);
         row = P.rows[row_id];
-        nterms = row.term_end - row.term_begin;
-        __syncwarp();
-        for (int t = lane; t < nterms; t += 32) {  // fill the job cache, one term per lane
-          const FTerm tm = P.terms[row.term_begin + t];
-          Job jb;
-          jb.ptr[0] = tm.in_abs ? reinterpret_cast<const char*>(tm.in_abs)
-                                : P.in + tm.in_off * (int64_t)sizeof(T);
-          int k = 1;
-          jb.nstages = tm.stage_end - tm.stage_begin;
-          for (int s = 0; s < jb.nstages; ++s) {
-            const FStage fs = P.stages[tm.stage_begin + s];
-            CStage cs;
-            cs.op = (uint8_t)fs.op; cs.fn = (uint8_t)fs.fn; cs.has_stream = fs.ptr != nullptr;
-            cs.pad0 = 0; cs.pad1 = 0; cs.c0 = fs.c0;
-            jb.stages[s] = cs;
-            if (fs.ptr) jb.ptr[k++] = reinterpret_cast<const char*>(fs.ptr);
-          }
-          for (int s = jb.nstages; s < kMaxStages; ++s) jb.stages[s] = CStage{};
-          for (int kk = k; kk < kMaxStreams; ++kk) jb.ptr[kk] = nullptr;
-          jb.nstreams = k; jb.sign = tm.sign; jb.pad = 0;
-          jobs[t] = jb;
-        }
-        __syncwarp();
+        ngroups = row.group_end - row.group_begin;
       }
-      const int64_t pos = chunk * kTilesPerItem + tin;
-      if (pos >= row.ntiles) continue;  // phantom tile of a ragged last chunk
+      const int64_t pos = chunk * P.S + tin;
+      tin += (int)gridDim.x;
+      while (tin >= P.S) { tin -= P.S; ++item; }
+      if (pos >= row.ntiles) continue;  // phantom tile of a ragged last super-chunk
       const int64_t tile_start = pos * kTileElems;
       const int64_t rem = row.len - tile_start;
       const int nvalid = rem < kTileElems ? (int)rem : kTileElems;
       const uint32_t bytes = (HL ? kPad : 0) + (((uint32_t)nvalid * sizeof(T) + 15u) & ~15u) + (HR ? kPad : 0);
       char* out_tile = P.out + (row.out_off + tile_start) * (int64_t)sizeof(T);
-      const int nissue = nterms > 0 ? nterms : 1;
+      const int nissue = ngroups > 0 ? ngroups : 1;
       for (int g0 = 0; g0 < nissue; g0 += G) {
-        const int t = g0 + lane;
-        if (lane < G && t < nissue) {
-          const uint32_t my = it + lane;
-          const int slot = my % nslots;
-          const uint32_t use = my / nslots;
-          mbar_wait(&empty[slot], (use & 1) ^ 1);
-          SlotMeta& M = meta[slot];
+        const int g = g0 + lane;
+        const int n = (nissue - g0) < G ? (nissue - g0) : G;
+        if (lane < n) {
+          int my = slot + lane;
+          uint32_t mypar = par;
+          if (my >= nslots) { my -= nslots; mypar ^= 1; }
+          const GroupRec* rec = P.groups + row.group_begin + g;
+          int nstreams = 0, rel = 0;
+          if (ngroups > 0) { nstreams = __ldg(&rec->nstreams); rel = __ldg(&rec->rel_mask); }
+          mbar_wait(&empty[my], mypar ^ 1);
+          SlotMeta& M = meta[my];
           M.tile_start = tile_start;
           M.len = row.len;
           M.out_tile = out_tile;
+          M.rec = rec;
           M.nvalid = nvalid;
-          int fl = (t == 0 ? F_FIRST : 0) | (t == nissue - 1 ? F_LAST : 0) | (row.init == 1 ? F_ACC : 0);
-          if (nterms == 0) {
+          const int fl = (g == 0 ? F_FIRST : 0) | (g == nissue - 1 ? F_LAST : 0) | (row.init == 1 ? F_ACC : 0);
+          if (ngroups == 0) {
             M.flags = fl | F_NOTERM;
-            M.sign = 1; M.nstages = 0;
-            mbar_arrive(&full[slot]);
+            mbar_arrive(&full[my]);
           } else {
-            const Job& jb = jobs[t];
             M.flags = fl;
-            M.sign = jb.sign;
-            M.nstages = jb.nstages;
-#pragma unroll
-            for (int s = 0; s < kMaxStages; ++s) M.stages[s] = jb.stages[s];
-            mbar_expect_tx(&full[slot], bytes * jb.nstreams);
-            unsigned char* sb = slots + (size_t)slot * slot_bytes + (HL ? 0 : kPad);
+            mbar_expect_tx(&full[my], bytes * nstreams);
+            unsigned char* sb = slots + (size_t)my * slot_bytes + (HL ? 0 : kPad);
             const int64_t goff = tile_start * (int64_t)sizeof(T) - (HL ? kPad : 0);
-            for (int k = 0; k < jb.nstreams; ++k)
-              bulk_g2s(sb + k * kBufBytes, jb.ptr[k] + goff, bytes, &full[slot]);
+            for (int k = 0; k < nstreams; ++k) {
+              const int64_t pk = __ldg(&rec->ptr[k]);
+              const char* src = ((rel >> k) & 1) ? P.in + pk : reinterpret_cast<const char*>(pk);
+              bulk_g2s(sb + k * kBufBytes, src + goff, bytes, &full[my]);
+            }
           }
         }
-        const int n = (nissue - g0) < G ? (nissue - g0) : G;
-        it += n;
+        slot += n;
+        if (slot >= nslots) { slot -= nslots; par ^= 1; }
         __syncwarp();
       }
     }
     if (lane == 0) {  // end-of-work sentinel
-      const int slot = it % nslots;
-      const uint32_t use = it / nslots;
-      mbar_wait(&empty[slot], (use & 1) ^ 1);
+      mbar_wait(&empty[slot], par ^ 1);
       meta[slot].flags = F_END;
       mbar_arrive(&full[slot]);
     }
   } else {
     // =============================== consumer warps ==============================
-    T acc[kVPT][V];
-    SmemLoader<T, HL, HR> ld;
-#pragma unroll
-    for (int i = 0; i < kVPT; ++i) ld.e0[i] = (i * kConsumers + tid) * V;
-    uint32_t it = 0;
+    T acc[V];
+    SmemLoader<T, HL, HR, 1> ld;
+    ld.e0[0] = tid * V;
+    int slot = 0;
+    uint32_t par = 0;
     while (true) {
-      const int slot = it % nslots;
-      const uint32_t use = it / nslots;
-      mbar_wait(&full[slot], use & 1);
+      mbar_wait(&full[slot], par);
       const SlotMeta& M = meta[slot];
       const int flags = M.flags;
       if (flags & F_END) break;
       const int nvalid = M.nvalid;
       char* out_tile = M.out_tile;
       if (flags & F_FIRST) {
+        if (flags & F_ACC) load_out<T>(out_tile, ld.e0[0], nvalid, acc);
+        else {
 #pragma unroll
-        for (int i = 0; i < kVPT; ++i) {
-          if (flags & F_ACC) load_out<T>(out_tile, ld.e0[i], nvalid, acc[i]);
-          else {
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = T(0);
-          }
+          for (int j = 0; j < V; ++j) acc[j] = T(0);
         }
       }
       if (!(flags & F_NOTERM)) {
-        ld.slot = reinterpret_cast<const char*>(slots + (size_t)slot * slot_bytes);
-        T val[kVPT][W];
-        int64_t p0[kVPT];
+        const GroupRec* __restrict__ rec = M.rec;
+        const int nterms = __ldg(&rec->nterms);
+        const int64_t len = M.len;
+        int64_t p0[1];
+        p0[0] = M.tile_start + ld.e0[0];
+        const char* sbase = reinterpret_cast<const char*>(slots + (size_t)slot * slot_bytes);
+        for (int t = 0; t < nterms; ++t) {
+          const uint2 gtr = __ldg(reinterpret_cast<const uint2*>(&rec->terms[t]));
+          const int stage0 = (int)(int16_t)(gtr.x & 0xffff), nst = (int)(int16_t)(gtr.x >> 16);
+          const int stream0 = (int)(int16_t)(gtr.y & 0xffff), sign = (int)(int16_t)(gtr.y >> 16);
+          ld.base = sbase + stream0 * kBufBytes;
+          T val[1][W];
+          eval_term<T, HL, HR, 1, HEAVY>(rec->stages + stage0, nst, ld, p0, len, val);
+          if (sign >= 0) {
 #pragma unroll
-        for (int i = 0; i < kVPT; ++i) p0[i] = M.tile_start + ld.e0[i];
-        eval_term<T, HL, HR, kVPT>(M.stages, M.nstages, ld, p0, M.len, val);
-        if (M.sign >= 0) {
+            for (int j = 0; j < V; ++j) acc[j] = acc[j] + val[0][HL + j];
+          } else {
 #pragma unroll
-          for (int i = 0; i < kVPT; ++i)
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[i][HL + j];
-        } else {
-#pragma unroll
-          for (int i = 0; i < kVPT; ++i)
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[i][HL + j];
+            for (int j = 0; j < V; ++j) acc[j] = acc[j] - val[0][HL + j];
+          }
         }
       }
       __syncwarp();
       if ((tid & 31) == 0) mbar_arrive(&empty[slot]);  // slot may be refilled
-      if (flags & F_LAST) {
-#pragma unroll
-        for (int i = 0; i < kVPT; ++i) store_out<T>(out_tile, ld.e0[i], nvalid, acc[i]);
-      }
-      ++it;
+      if (flags & F_LAST) store_out<T>(out_tile, ld.e0[0], nvalid, acc);
+      if (++slot == nslots) { slot = 0; par ^= 1; }
     }
   }
 }
 
 // ------------------------------------------------------------------ LDG engine -----------
-template <typename T, int HL, int HR>
-__global__ void __launch_bounds__(kConsumers) jets_fused_ldg_kernel(const FusedParams P) {
+template <typename T, int HL, int HR, bool HEAVY>
+__global__ void __launch_bounds__(kLdgThreads) jets_fused_ldg_kernel(const FusedParams P) {
   constexpr int V = VecOf<T>::V;
   constexpr int W = HL + V + HR;
   constexpr int kTileElems = kTileBytes / (int)sizeof(T);
   const int tid = threadIdx.x;
-  for (int64_t item = blockIdx.x; item < P.nitems; item += gridDim.x) {
-    int32_t row_id;
-    int64_t chunk;
-    decode_item(P, item, row_id, chunk);
-    const FRow row = P.rows[row_id];
+  const int64_t Q = P.nitems * P.S;
+  int64_t cur_item = -1;
+  int64_t chunk = 0;
+  int32_t row_id = 0;
+  FRow row;
+  for (int64_t q = blockIdx.x; q < Q; q += gridDim.x) {
+    const int64_t item = q / P.S;
+    const int tin = (int)(q - item * P.S);
+    if (item != cur_item) {
+      cur_item = item;
+      decode_item(P, item, row_id, chunk);
+      row = P.rows[row_id];
+    }
+    const int64_t pos = chunk * P.S + tin;
+    if (pos >= row.ntiles) continue;
     const int nterms = row.term_end - row.term_begin;
-    for (int tin = 0; tin < kTilesPerItem; ++tin) {
-      const int64_t pos = chunk * kTilesPerItem + tin;
-      if (pos >= row.ntiles) break;
-      const int64_t tile_start = pos * kTileElems;
-      const int64_t rem = row.len - tile_start;
-      const int nvalid = rem < kTileElems ? (int)rem : kTileElems;
-      char* out_tile = P.out + (row.out_off + tile_start) * (int64_t)sizeof(T);
-      T acc[kVPT][V];
-      GlobalLoader<T, HL, HR> ld;
-      ld.len = row.len;
-      int e0[kVPT];
+    const int64_t tile_start = pos * kTileElems;
+    const int64_t rem = row.len - tile_start;
+    const int nvalid = rem < kTileElems ? (int)rem : kTileElems;
+    char* out_tile = P.out + (row.out_off + tile_start) * (int64_t)sizeof(T);
+    T acc[kLdgVPT][V];
+    GlobalLoader<T, HL, HR, kLdgVPT> ld;
+    ld.len = row.len;
+    int e0[kLdgVPT];
 #pragma unroll
-      for (int i = 0; i < kVPT; ++i) {
-        e0[i] = (i * kConsumers + tid) * V;
-        ld.p0[i] = tile_start + e0[i];
-        if (row.init == 1) load_out<T>(out_tile, e0[i], nvalid, acc[i]);
-        else {
+    for (int i = 0; i < kLdgVPT; ++i) {
+      e0[i] = (i * kLdgThreads + tid) * V;
+      ld.p0[i] = tile_start + e0[i];
+      if (row.init == 1) load_out<T>(out_tile, e0[i], nvalid, acc[i]);
+      else {
 #pragma unroll
-          for (int j = 0; j < V; ++j) acc[i][j] = T(0);
-        }
+        for (int j = 0; j < V; ++j) acc[i][j] = T(0);
       }
-      for (int t = 0; t < nterms; ++t) {
-        const FTerm tm = P.terms[row.term_begin + t];
-        CStage cs[kMaxStages];
-        ld.ptr[0] = tm.in_abs ? reinterpret_cast<const char*>(tm.in_abs)
-                              : P.in + tm.in_off * (int64_t)sizeof(T);
-        int k = 1;
-        const int ns = tm.stage_end - tm.stage_begin;
+    }
+    for (int t = 0; t < nterms; ++t) {
+      const FTerm tm = P.terms[row.term_begin + t];
+      CStage cs[kMaxStages];
+      ld.ptr[0] = tm.in_abs ? reinterpret_cast<const char*>(tm.in_abs)
+                            : P.in + tm.in_off * (int64_t)sizeof(T);
+      int k = 1;
+      const int ns = tm.stage_end - tm.stage_begin;
 #pragma unroll
-        for (int s = 0; s < kMaxStages; ++s) {
-          if (s < ns) {
-            const FStage fs = P.stages[tm.stage_begin + s];
-            cs[s].op = (uint8_t)fs.op; cs[s].fn = (uint8_t)fs.fn; cs[s].c0 = fs.c0;
-            cs[s].has_stream = fs.ptr != nullptr;
-            if (fs.ptr) {
+      for (int s = 0; s < kMaxStages; ++s) {
+        if (s < ns) {
+          const FStage fs = P.stages[tm.stage_begin + s];
+          cs[s].op = (uint8_t)fs.op; cs[s].fn = (uint8_t)fs.fn; cs[s].c0 = fs.c0;
+          cs[s].has_stream = fs.ptr != nullptr;
+          if (fs.ptr) {
 #pragma unroll
-              for (int kk = 1; kk < kMaxStreams; ++kk)
-                if (kk == k) ld.ptr[kk] = reinterpret_cast<const char*>(fs.ptr);
-              ++k;
-            }
+            for (int kk = 1; kk < kMaxStreams; ++kk)
+              if (kk == k) ld.ptr[kk] = reinterpret_cast<const char*>(fs.ptr);
+            ++k;
           }
         }
-        T val[kVPT][W];
-        eval_term<T, HL, HR, kVPT>(cs, ns, ld, ld.p0, row.len, val);
-        if (tm.sign >= 0) {
-#pragma unroll
-          for (int i = 0; i < kVPT; ++i)
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[i][HL + j];
-        } else {
-#pragma unroll
-          for (int i = 0; i < kVPT; ++i)
-#pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[i][HL + j];
-        }
       }
+      T val[kLdgVPT][W];
+      eval_term<T, HL, HR, kLdgVPT, HEAVY>(cs, ns, ld, ld.p0, row.len, val);
+      if (tm.sign >= 0) {
 #pragma unroll
-      for (int i = 0; i < kVPT; ++i) store_out<T>(out_tile, e0[i], nvalid, acc[i]);
+        for (int i = 0; i < kLdgVPT; ++i)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[i][HL + j];
+      } else {
+#pragma unroll
+        for (int i = 0; i < kLdgVPT; ++i)
+#pragma unroll
+          for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[i][HL + j];
+      }
     }
+#pragma unroll
+    for (int i = 0; i < kLdgVPT; ++i) store_out<T>(out_tile, e0[i], nvalid, acc[i]);
   }
 }
 
-template <typename T, int HL, int HR>
+template <typename T, int HL, int HR, bool HEAVY>
 void launch_one(const DevFused& f, const FusedParams& P, cudaStream_t s) {
   const int sms = ctx().sm_count;
+  const int64_t Q = P.nitems * P.S;
   if (f.use_tma) {
-    constexpr int kHdr = 256 + kMaxSlots * (int)sizeof(SlotMeta) + kMaxTermsTMA * (int)sizeof(Job);
-    constexpr int kHdrAligned = (kHdr + 127) & ~127;
-    const size_t smem = kHdrAligned + (size_t)P.nslots * P.max_streams * kBufBytes;
+    const size_t smem = kHdrAligned + (size_t)P.nslots * P.slot_streams * kBufBytes;
     static bool attr_set = false;
     if (!attr_set) {
-      CUDA_TRY(cudaFuncSetAttribute(jets_fused_tma_kernel<T, HL, HR>,
+      CUDA_TRY(cudaFuncSetAttribute(jets_fused_tma_kernel<T, HL, HR, HEAVY>,
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
       attr_set = true;
     }
     int64_t grid = sms;
-    const int64_t Q = f.ntiles;  // real tiles
     if (grid > Q) grid = Q > 0 ? Q : 1;
-    jets_fused_tma_kernel<T, HL, HR><<<(unsigned)grid, kThreads, smem, s>>>(P);
+    jets_fused_tma_kernel<T, HL, HR, HEAVY><<<(unsigned)grid, kThreads, smem, s>>>(P);
   } else {
     int64_t grid = (int64_t)sms * 8;
-    if (grid > P.nitems) grid = P.nitems > 0 ? P.nitems : 1;
-    jets_fused_ldg_kernel<T, HL, HR><<<(unsigned)grid, kConsumers, 0, s>>>(P);
+    if (grid > Q) grid = Q > 0 ? Q : 1;
+    jets_fused_ldg_kernel<T, HL, HR, HEAVY><<<(unsigned)grid, kLdgThreads, 0, s>>>(P);
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }
 
-template <typename T>
+template <typename T, bool HEAVY>
 void launch_halo(const DevFused& f, const FusedParams& P, cudaStream_t s) {
-  if (f.hl == 0 && f.hr == 0) launch_one<T, 0, 0>(f, P, s);
-  else if (f.hl == 0 && f.hr == 1) launch_one<T, 0, 1>(f, P, s);
-  else if (f.hl == 1 && f.hr == 0) launch_one<T, 1, 0>(f, P, s);
-  else if (f.hl == 1 && f.hr == 1) launch_one<T, 1, 1>(f, P, s);
+  if (f.hl == 0 && f.hr == 0) launch_one<T, 0, 0, HEAVY>(f, P, s);
+  else if (f.hl == 0 && f.hr == 1) launch_one<T, 0, 1, HEAVY>(f, P, s);
+  else if (f.hl == 1 && f.hr == 0) launch_one<T, 1, 0, HEAVY>(f, P, s);
+  else if (f.hl == 1 && f.hr == 1) launch_one<T, 1, 1, HEAVY>(f, P, s);
   else JETS_FAIL(JETS_ERR_UNSUPPORTED, "fused halo (%d,%d) not instantiated", f.hl, f.hr);
 }
 
 }  // namespace
 
 int fused_tile_elems(int dtype) { return kTileBytes / (int)dsize(dtype); }
-int fused_tiles_per_item() { return kTilesPerItem; }
-int fused_max_terms_tma() { return kMaxTermsTMA; }
 
-int fused_nslots(int max_streams) {
-  constexpr int kHdr = 256 + kMaxSlots * (int)sizeof(SlotMeta) + kMaxTermsTMA * (int)sizeof(Job);
-  constexpr int kHdrAligned = (kHdr + 127) & ~127;
-  int n = (kSmemLimit - kHdrAligned) / (max_streams * kBufBytes);
+int fused_nslots(int slot_streams) {
+  int n = (kSmemLimit - kHdrAligned) / (slot_streams * kBufBytes);
   if (n > kMaxSlots) n = kMaxSlots;
   return n;
 }
@@ -511,11 +486,15 @@ int fused_nslots(int max_streams) {
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s) {
   if (f.nrows == 0 || f.ntiles == 0) return;
   FusedParams P;
-  P.stages = f.stages; P.terms = f.terms; P.rows = f.rows; P.segs = f.segs; P.order = f.order;
-  P.nsegs = f.nsegs; P.nslots = fused_nslots(f.max_streams); P.max_streams = f.max_streams;
-  P.pad = 0; P.nitems = f.nitems; P.in = in; P.out = out;
-  if (dtype == JETS_F32) launch_halo<float>(f, P, s);
-  else launch_halo<double>(f, P, s);
+  P.stages = f.stages; P.terms = f.terms; P.groups = f.groups; P.rows = f.rows; P.segs = f.segs;
+  P.order = f.order;
+  P.nsegs = f.nsegs; P.nslots = fused_nslots(f.slot_streams); P.slot_streams = f.slot_streams;
+  P.S = f.S; P.nitems = f.nitems; P.in = in; P.out = out;
+  if (dtype == JETS_F32) {
+    if (f.heavy) launch_halo<float, true>(f, P, s); else launch_halo<float, false>(f, P, s);
+  } else {
+    if (f.heavy) launch_halo<double, true>(f, P, s); else launch_halo<double, false>(f, P, s);
+  }
 }
 
 }  // namespace jets

@@ -12,7 +12,6 @@
 
 namespace jets {
 
-int fused_nslots(int max_streams);
 uint64_t g_epoch = 1;  // bumped by point! -> cached plans holding stale mo pointers are rebuilt
 
 namespace {
@@ -306,12 +305,24 @@ struct Builder {
     const int tile = fused_tile_elems(dtype);
     bool tma = ref_ok(dst) && ref_ok(src) && (dst.off * esz) % 16 == 0 && (src.off * esz) % 16 == 0;
     size_t k = 0;
-    int max_terms = 0;
+    bool heavy = false;
+    constexpr int kSlotStreams = 4, kGroupTermsMax = 4, kGroupStagesMax = 12;
     for (size_t r = 0; r < out_sp.len.size(); ++r) {
       FRow row{};
       row.out_off = dst.off + oo[r];
       row.len = out_sp.len[r];
       row.term_begin = (int32_t)t.terms.size();
+      row.group_begin = (int32_t)t.groups.size();
+      GroupRec grp{};
+      int g_terms = 0, g_stages = 0;
+      auto close_group = [&]() {
+        if (g_terms == 0) return;
+        grp.nterms = g_terms;
+        t.max_streams = std::max(t.max_streams, (int)grp.nstreams);
+        t.groups.push_back(grp);
+        grp = GroupRec{};
+        g_terms = g_stages = 0;
+      };
       while (k < es.size() && es[k].r == (int)r) {
         const Entry& e = es[k++];
         FTerm tm{};
@@ -321,35 +332,57 @@ struct Builder {
         for (const FStage& s : e.chain) {
           t.stages.push_back(s);
           if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
+          if ((s.op == S_PW_F || s.op == S_PW_J) && s.fn != JETS_PW_SQUARE) heavy = true;
         }
         tm.stage_end = (int32_t)t.stages.size();
         tm.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
         tm.nstreams = chain_streams(e.chain);
-        t.max_streams = std::max(t.max_streams, tm.nstreams);
         if ((tm.in_off * esz) % 16) tma = false;
         JETS_CHECK(in_sp.len[e.c] == out_sp.len[r], JETS_ERR_SHAPE,
                    "elementwise block (%d,%d) maps %lld -> %lld elements", (int)r, e.c,
                    (long long)in_sp.len[e.c], (long long)out_sp.len[r]);
         t.terms.push_back(tm);
+        // close the current group when this term does not fit into its slot any more
+        if (g_terms > 0 && (grp.nstreams + tm.nstreams > kSlotStreams || g_terms + 1 > kGroupTermsMax ||
+                            g_stages + (int)e.chain.size() > kGroupStagesMax))
+          close_group();
+        GTerm gt{};
+        gt.stage0 = (int16_t)g_stages;
+        gt.nstages = (int16_t)e.chain.size();
+        gt.stream0 = (int16_t)grp.nstreams;
+        gt.sign = (int16_t)tm.sign;
+        grp.terms[g_terms++] = gt;
+        grp.ptr[grp.nstreams] = (int64_t)(tm.in_off * (int64_t)esz);   // relative to the apply's `in`
+        grp.rel_mask |= 1 << grp.nstreams;
+        grp.nstreams++;
+        for (const FStage& s : e.chain) {
+          CStage cs{};
+          cs.op = (uint8_t)s.op; cs.fn = (uint8_t)s.fn; cs.has_stream = s.ptr != nullptr; cs.c0 = s.c0;
+          grp.stages[g_stages++] = cs;
+          if (s.ptr) grp.ptr[grp.nstreams++] = (int64_t)reinterpret_cast<uintptr_t>(s.ptr);
+        }
       }
       row.term_end = (int32_t)t.terms.size();
+      close_group();
+      row.group_end = (int32_t)t.groups.size();
       row.init = (acc == ACC_SET) ? 0 : 1;
       row.ntiles = (int32_t)((row.len + tile - 1) / tile);
       if ((row.out_off * esz) % 16) tma = false;
-      max_terms = std::max(max_terms, row.term_end - row.term_begin);
       if (row.term_end == row.term_begin && acc != ACC_SET) continue;  // nothing to add
       if (row.len == 0) continue;
       t.rows.push_back(row);
     }
-    if (max_terms > fused_max_terms_tma()) tma = false;
     if (fused_nslots(t.max_streams) < 2) tma = false;
     t.tma_ok = tma;
     bool use_tma = tma;
     if (engine == 2) use_tma = false;
     if (engine == 1 && !tma) JETS_FAIL(JETS_ERR_UNSUPPORTED, "TMA engine forced but operands are not aligned/guarded");
 
-    // schedule: rows sorted by chunk count (desc); segments with a constant set of active rows
-    const int K = fused_tiles_per_item();
+    // schedule: tiles are visited in (super-chunk of S tiles, row, tile) order and dealt round-robin
+    // to the CTAs.  Rows sorted by super-chunk count (desc); one segment per constant set of active rows.
+    int64_t max_tiles = 1;
+    for (auto& r : t.rows) max_tiles = std::max<int64_t>(max_tiles, r.ntiles);
+    const int K = (int)std::min<int64_t>(max_tiles, 4 * (int64_t)ctx().sm_count);
     std::vector<int32_t> order(t.rows.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int32_t)i;
     auto nchunks = [&](int32_t i) { return (int64_t)(t.rows[i].ntiles + K - 1) / K; };
@@ -375,20 +408,24 @@ struct Builder {
     f.nsegs = (int32_t)segs.size();
     f.ntiles = ntiles;
     f.nitems = begin;
-    f.hl = hl; f.hr = hr; f.max_streams = t.max_streams;
+    f.hl = hl; f.hr = hr; f.slot_streams = t.max_streams;
+    f.S = K;
+    f.heavy = heavy;
     f.tile_elems = tile;
     f.use_tma = use_tma;
     if (f.nrows > 0) {
       auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
       const size_t b0 = 0, b1 = b0 + al(t.stages.size() * sizeof(FStage)),
                    b2 = b1 + al(t.terms.size() * sizeof(FTerm)), b3 = b2 + al(t.rows.size() * sizeof(FRow)),
-                   b4 = b3 + al(segs.size() * sizeof(FSeg)), b5 = b4 + al(order.size() * sizeof(int32_t));
+                   b4 = b3 + al(segs.size() * sizeof(FSeg)), b5x = b4 + al(order.size() * sizeof(int32_t)),
+                   b5 = b5x + al(t.groups.size() * sizeof(GroupRec));
       std::vector<char> host(b5, 0);
       if (!t.stages.empty()) memcpy(host.data() + b0, t.stages.data(), t.stages.size() * sizeof(FStage));
       if (!t.terms.empty()) memcpy(host.data() + b1, t.terms.data(), t.terms.size() * sizeof(FTerm));
       memcpy(host.data() + b2, t.rows.data(), t.rows.size() * sizeof(FRow));
       memcpy(host.data() + b3, segs.data(), segs.size() * sizeof(FSeg));
       memcpy(host.data() + b4, order.data(), order.size() * sizeof(int32_t));
+      if (!t.groups.empty()) memcpy(host.data() + b5x, t.groups.data(), t.groups.size() * sizeof(GroupRec));
       char* blob = nullptr;
       CUDA_TRY(cudaMalloc(&blob, b5));
       CUDA_TRY(cudaMemcpy(blob, host.data(), b5, cudaMemcpyHostToDevice));
@@ -399,6 +436,7 @@ struct Builder {
       f.rows = reinterpret_cast<FRow*>(blob + b2);
       f.segs = reinterpret_cast<FSeg*>(blob + b3);
       f.order = reinterpret_cast<int32_t*>(blob + b4);
+      f.groups = reinterpret_cast<GroupRec*>(blob + b5x);
     }
     plan.engines |= use_tma ? 1 : 2;
     plan.steps.push_back(std::move(st));

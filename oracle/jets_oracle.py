@@ -194,6 +194,9 @@ class BlockArray:
         return self.arrays[j].reshape(-1, order="F")[k]
 
     def __setitem__(self, i, v):
+        if i is Ellipsis:  # ``x .= v``
+            self.assign(v) if isinstance(v, (BlockArray, np.ndarray)) else fill_(self, v)
+            return
         j, k = self._find(i)
         flat = self.arrays[j].reshape(-1, order="F")
         flat[k] = v
