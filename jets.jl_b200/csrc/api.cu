@@ -1,6 +1,7 @@
 // C ABI of libjets_b200.so (include/jets_b200.h): context, device storage, operator trees,
 // linearization, apply, reductions.  No exceptions leave this file.
 #include <cstdarg>
+#include <cstdlib>
 #include <cmath>
 #include <algorithm>
 #include "common.hpp"
@@ -258,6 +259,8 @@ int jets_init(int device) {
     CUDA_TRY(cudaMallocHost(&c.host_scratch, 64 * sizeof(double)));
     c.dev_scratch_elems = (size_t)c.sm_count * 8 + 64;
     CUDA_TRY(cudaMalloc(&c.dev_scratch, (c.dev_scratch_elems + 64) * sizeof(double)));
+    if (const char* v = getenv("JETS_B200_FAST_VARIANT")) c.fast_variant = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_FAST")) c.no_fast = atoi(v);
     c.ready = true;
   });
 }

@@ -59,6 +59,8 @@ struct Context {
   bool own_stream = false;
   int64_t launches = 0;
   int fused_engine = 0;  // 0 auto, 1 TMA, 2 LDG
+  int fast_variant = -1; // JETS_B200_FAST_VARIANT (-1 = chosen per plan): consumer shape of the fast TMA kernel
+  int no_fast = 0;       // JETS_B200_NO_FAST=1: always use the interpreter kernel
   double* host_scratch = nullptr;  // pinned, 64 doubles
   double* dev_scratch = nullptr;   // device partials for reductions
   size_t dev_scratch_elems = 0;
@@ -195,9 +197,26 @@ struct CStage {      // 16 bytes
   uint32_t pad1;
   double c0;
 };
+// Chains the consumer evaluates with straight-line, compile-time-specialised code instead of the
+// stage interpreter (same IEEE operations in the same order, so results are bit-identical).
+enum Pattern : int {
+  PAT_GENERIC = 0,
+  PAT_COPY,           // no stage (identity)
+  PAT_DIAG,           // w .* x                      (JopBlock of diagonal JopLn, config 1)
+  PAT_FDIFF, PAT_BDIFF, PAT_LAP,   // bare stencils
+  PAT_SCALE,          // c .* x
+  PAT_J2_FDIFF_DIAG,  // w .* S(2 mo .* x)           (config 2 forward: D ∘ S ∘ J)
+  PAT_DIAG_BDIFF_J2,  // 2 mo .* S'(w .* x)          (config 2 adjoint)
+  PAT_LAP_SCALE, PAT_FDIFF_SCALE, PAT_BDIFF_SCALE,   // c .* S(x)   (config 4: B - c*S)
+  PAT_J2,             // 2 mo .* x                   (Jacobian of x^2)
+  PAT_SQUARE          // x .* x
+};
 struct GTerm {       // 8 bytes
-  int16_t stage0, nstages;   // into the group's stage pool
-  int16_t stream0, sign;     // first operand stream of the term inside the slot
+  uint8_t stage0, nstages;   // into the group's stage pool
+  uint8_t stream0;           // first operand stream of the term inside the slot
+  uint8_t pattern;           // Pattern
+  int8_t sign;
+  uint8_t pad[3];
 };
 struct GroupRec {    // 272 bytes
   int64_t ptr[kMaxStreams];  // absolute address, or byte offset from the apply's `in` base (rel_mask bit)
@@ -237,6 +256,8 @@ struct DevFused {   // device copy + launch geometry
   int tile_elems = 0;
   bool use_tma = false;
   bool heavy = false;   // chains use transcendental pointwise functions
+  bool fast = false;    // every chain has a straight-line fast path -> jets_fused_fast_kernel
+  int variant = 0;      // fast-kernel shape: 0 = 16 warps x 1 vec, 1 = 8 x 2, 2 = 16 x 2 (16 KB tiles)
   void* blob = nullptr;
 };
 
@@ -291,6 +312,9 @@ void run_plan(Plan& p, int dtype, char* in, char* out);
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
 int fused_tile_elems(int dtype);
 int fused_nslots(int slot_streams);
+int fast_tile_bytes(int variant);
+int fast_nslots(int variant, int slot_streams);
+void launch_fused_fast(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);

@@ -151,3 +151,138 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
 }
 
 }  // namespace jets
+
+namespace jets {
+
+// ------------------------------------------------------------------ fast paths -----------
+// Straight-line evaluation of the common chains on one 128-bit vector, reading the staged tile
+// directly.  `b0` points at this thread's first element of the term's first stream; stream k of the
+// term lives `k * stride` bytes further.  `first`: the vector starts at the block's first element;
+// `last`: index (relative to the vector) of the block's last element, so element j has a right
+// neighbour inside the block iff j < last.  Operation order is the interpreter's, bit for bit.
+template <typename T>
+struct FastIO {
+  using Vec = typename VecOf<T>::type;
+  static constexpr int V = VecOf<T>::V;
+  const char* b0;
+  int stride;
+  __device__ __forceinline__ void vec(int k, T (&x)[V]) const {
+    const Vec v = *reinterpret_cast<const Vec*>(b0 + k * stride);
+    const T* vs = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) x[j] = vs[j];
+  }
+  __device__ __forceinline__ T at(int k, int j) const {  // element j (may be -1 or V: halo)
+    return *reinterpret_cast<const T*>(b0 + k * stride + j * (int)sizeof(T));
+  }
+};
+
+template <typename T>
+__device__ __forceinline__ void st_fdiff(const T (&x)[VecOf<T>::V], T xr, int last, T (&o)[VecOf<T>::V]) {
+  constexpr int V = VecOf<T>::V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const T nx = (j + 1 < V) ? x[(j + 1 < V) ? j + 1 : j] : xr;
+    o[j] = (j < last) ? (nx - x[j]) : T(0);
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st_bdiff(const T (&x)[VecOf<T>::V], T xl, bool first, int last, T (&o)[VecOf<T>::V]) {
+  constexpr int V = VecOf<T>::V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const T pv = (j > 0) ? x[(j > 0) ? j - 1 : 0] : xl;
+    const T l = (j > 0 || !first) ? pv : T(0);
+    const T r = (j < last) ? x[j] : T(0);
+    o[j] = l - r;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st_lap(const T (&x)[VecOf<T>::V], T xl, T xr, bool first, int last, T (&o)[VecOf<T>::V]) {
+  constexpr int V = VecOf<T>::V;
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    const T pv = (j > 0) ? x[(j > 0) ? j - 1 : 0] : xl;
+    const T nx = (j + 1 < V) ? x[(j + 1 < V) ? j + 1 : j] : xr;
+    const T l = (j > 0 || !first) ? pv : T(0);
+    const T r = (j < last) ? nx : T(0);
+    o[j] = (l - T(2) * x[j]) + r;
+  }
+}
+
+// Returns false when `pattern` has no fast path (the caller falls back to the interpreter).
+template <typename T>
+__device__ __forceinline__ bool eval_fast(int pattern, const FastIO<T>& io, const CStage* stages,
+                                          bool first, int last, T (&o)[VecOf<T>::V]) {
+  constexpr int V = VecOf<T>::V;
+  T x[V];
+  switch (pattern) {
+    case PAT_COPY: io.vec(0, o); return true;
+    case PAT_DIAG: {
+      T w[V];
+      io.vec(0, x); io.vec(1, w);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = w[j] * x[j];
+      return true;
+    }
+    case PAT_FDIFF: io.vec(0, x); st_fdiff<T>(x, io.at(0, V), last, o); return true;
+    case PAT_BDIFF: io.vec(0, x); st_bdiff<T>(x, io.at(0, -1), first, last, o); return true;
+    case PAT_LAP: io.vec(0, x); st_lap<T>(x, io.at(0, -1), io.at(0, V), first, last, o); return true;
+    case PAT_SCALE: {
+      const T c = (T)load_stage(stages).c0;
+      io.vec(0, x);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = c * x[j];
+      return true;
+    }
+    case PAT_LAP_SCALE: case PAT_FDIFF_SCALE: case PAT_BDIFF_SCALE: {
+      const T c = (T)load_stage(stages + 1).c0;
+      T s[V];
+      io.vec(0, x);
+      if (pattern == PAT_LAP_SCALE) st_lap<T>(x, io.at(0, -1), io.at(0, V), first, last, s);
+      else if (pattern == PAT_FDIFF_SCALE) st_fdiff<T>(x, io.at(0, V), last, s);
+      else st_bdiff<T>(x, io.at(0, -1), first, last, s);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = c * s[j];
+      return true;
+    }
+    case PAT_J2: {
+      T m[V];
+      io.vec(0, x); io.vec(1, m);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = (T(2) * m[j]) * x[j];
+      return true;
+    }
+    case PAT_SQUARE: {
+      io.vec(0, x);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = x[j] * x[j];
+      return true;
+    }
+    case PAT_J2_FDIFF_DIAG: {  // streams: x, mo, w
+      T m[V], w[V], y[V], s[V];
+      io.vec(0, x); io.vec(1, m); io.vec(2, w);
+#pragma unroll
+      for (int j = 0; j < V; ++j) y[j] = (T(2) * m[j]) * x[j];
+      const T yr = (T(2) * io.at(1, V)) * io.at(0, V);
+      st_fdiff<T>(y, yr, last, s);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = w[j] * s[j];
+      return true;
+    }
+    case PAT_DIAG_BDIFF_J2: {  // streams: x, w, mo
+      T w[V], m[V], y[V], s[V];
+      io.vec(0, x); io.vec(1, w); io.vec(2, m);
+#pragma unroll
+      for (int j = 0; j < V; ++j) y[j] = w[j] * x[j];
+      const T yl = io.at(1, -1) * io.at(0, -1);
+      st_bdiff<T>(y, yl, first, last, s);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = (T(2) * m[j]) * s[j];
+      return true;
+    }
+    default: return false;
+  }
+}
+
+}  // namespace jets

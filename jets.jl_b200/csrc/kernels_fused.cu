@@ -43,6 +43,9 @@ struct SlotMeta {                 // written by the producer, read by consumers 
   const GroupRec* rec;            // static description of the term group (global, read-only)
   int32_t nvalid;
   int32_t flags;
+  int32_t nterms;
+  int32_t pad;
+  GTerm terms[kGroupTerms];       // copied from rec so the consumers never wait on global memory
 };
 
 constexpr int kHdrBytes = 256 + kMaxSlots * (int)sizeof(SlotMeta);
@@ -272,8 +275,14 @@ __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const Fused
           uint32_t mypar = par;
           if (my >= nslots) { my -= nslots; mypar ^= 1; }
           const GroupRec* rec = P.groups + row.group_begin + g;
-          int nstreams = 0, rel = 0;
-          if (ngroups > 0) { nstreams = __ldg(&rec->nstreams); rel = __ldg(&rec->rel_mask); }
+          int nstreams = 0, rel = 0, nterms = 0;
+          uint4 t01 = make_uint4(0, 0, 0, 0), t23 = make_uint4(0, 0, 0, 0);
+          if (ngroups > 0) {
+            const int4 hd = __ldg(reinterpret_cast<const int4*>(&rec->nstreams));
+            nstreams = hd.x; nterms = hd.y; rel = hd.z;
+            t01 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[0]));
+            t23 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[2]));
+          }
           mbar_wait(&empty[my], mypar ^ 1);
           SlotMeta& M = meta[my];
           M.tile_start = tile_start;
@@ -281,6 +290,9 @@ __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const Fused
           M.out_tile = out_tile;
           M.rec = rec;
           M.nvalid = nvalid;
+          M.nterms = nterms;
+          *reinterpret_cast<uint4*>(&M.terms[0]) = t01;
+          *reinterpret_cast<uint4*>(&M.terms[2]) = t23;
           const int fl = (g == 0 ? F_FIRST : 0) | (g == nissue - 1 ? F_LAST : 0) | (row.init == 1 ? F_ACC : 0);
           if (ngroups == 0) {
             M.flags = fl | F_NOTERM;
@@ -330,24 +342,33 @@ __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const Fused
       }
       if (!(flags & F_NOTERM)) {
         const GroupRec* __restrict__ rec = M.rec;
-        const int nterms = __ldg(&rec->nterms);
+        const int nterms = M.nterms;
         const int64_t len = M.len;
         int64_t p0[1];
         p0[0] = M.tile_start + ld.e0[0];
+        const bool first = (p0[0] == 0);
+        const int64_t rl = len - 1 - p0[0];
+        const int last = rl > V ? V : (rl < -1 ? -1 : (int)rl);
         const char* sbase = reinterpret_cast<const char*>(slots + (size_t)slot * slot_bytes);
         for (int t = 0; t < nterms; ++t) {
-          const uint2 gtr = __ldg(reinterpret_cast<const uint2*>(&rec->terms[t]));
-          const int stage0 = (int)(int16_t)(gtr.x & 0xffff), nst = (int)(int16_t)(gtr.x >> 16);
-          const int stream0 = (int)(int16_t)(gtr.y & 0xffff), sign = (int)(int16_t)(gtr.y >> 16);
-          ld.base = sbase + stream0 * kBufBytes;
-          T val[1][W];
-          eval_term<T, HL, HR, 1, HEAVY>(rec->stages + stage0, nst, ld, p0, len, val);
-          if (sign >= 0) {
+          const GTerm gt = M.terms[t];
+          T val[V];
+          FastIO<T> io;
+          io.b0 = sbase + gt.stream0 * kBufBytes + kPad + ld.e0[0] * (int)sizeof(T);
+          io.stride = kBufBytes;
+          if (!eval_fast<T>(gt.pattern, io, rec->stages + gt.stage0, first, last, val)) {
+            ld.base = sbase + gt.stream0 * kBufBytes;
+            T wv[1][W];
+            eval_term<T, HL, HR, 1, HEAVY>(rec->stages + gt.stage0, gt.nstages, ld, p0, len, wv);
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[j] = acc[j] + val[0][HL + j];
+            for (int j = 0; j < V; ++j) val[j] = wv[0][HL + j];
+          }
+          if (gt.sign >= 0) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[j] = acc[j] + val[j];
           } else {
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[j] = acc[j] - val[0][HL + j];
+            for (int j = 0; j < V; ++j) acc[j] = acc[j] - val[j];
           }
         }
       }

@@ -255,6 +255,31 @@ void halo_of(const Entries& es, int& hl, int& hr) {
   }
 }
 
+// Which straight-line fast path (if any) evaluates this chain.
+int classify(const std::vector<FStage>& ch) {
+  auto is = [&](size_t i, int op) { return i < ch.size() && ch[i].op == op; };
+  auto j2 = [&](size_t i) { return is(i, S_PW_J) && ch[i].fn == JETS_PW_SQUARE; };
+  const size_t n = ch.size();
+  if (n == 0) return PAT_COPY;
+  if (n == 1) {
+    if (is(0, S_DIAG)) return PAT_DIAG;
+    if (is(0, S_FDIFF)) return PAT_FDIFF;
+    if (is(0, S_BDIFF)) return PAT_BDIFF;
+    if (is(0, S_LAP)) return PAT_LAP;
+    if (is(0, S_SCALE)) return PAT_SCALE;
+    if (j2(0)) return PAT_J2;
+    if (is(0, S_PW_F) && ch[0].fn == JETS_PW_SQUARE) return PAT_SQUARE;
+  }
+  if (n == 2 && is(1, S_SCALE)) {
+    if (is(0, S_LAP)) return PAT_LAP_SCALE;
+    if (is(0, S_FDIFF)) return PAT_FDIFF_SCALE;
+    if (is(0, S_BDIFF)) return PAT_BDIFF_SCALE;
+  }
+  if (n == 3 && j2(0) && is(1, S_FDIFF) && is(2, S_DIAG)) return PAT_J2_FDIFF_DIAG;
+  if (n == 3 && is(0, S_DIAG) && is(1, S_BDIFF) && j2(2)) return PAT_DIAG_BDIFF_J2;
+  return PAT_GENERIC;
+}
+
 std::vector<int64_t> offsets_of(const Space& s) {
   std::vector<int64_t> o(s.len.size() + 1, 0);
   for (size_t i = 0; i < s.len.size(); ++i) o[i + 1] = o[i] + s.len[i];
@@ -302,8 +327,39 @@ struct Builder {
     const size_t esz = dsize(dtype);
     FusedTables t;
     t.hl = hl; t.hr = hr;
-    const int tile = fused_tile_elems(dtype);
+    // Pre-pass: can the TMA engines be used at all (every stream 16B aligned in guarded memory),
+    // does every chain have a straight-line fast path, and how many terms does a row sum?
     bool tma = ref_ok(dst) && ref_ok(src) && (dst.off * esz) % 16 == 0 && (src.off * esz) % 16 == 0;
+    bool all_fast = !ctx().no_fast && engine != 2;
+    int max_row_terms = 0, max_term_streams = 1;
+    {
+      int run = 0, prev_r = -1;
+      for (const Entry& e : es) {
+        if (classify(e.chain) == PAT_GENERIC) all_fast = false;
+        for (const FStage& s : e.chain)
+          if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
+        if (((src.off + io[e.c]) * esz) % 16 || ((dst.off + oo[e.r]) * esz) % 16) tma = false;
+        run = (e.r == prev_r) ? run + 1 : 1;
+        prev_r = e.r;
+        max_row_terms = std::max(max_row_terms, run);
+        max_term_streams = std::max(max_term_streams, chain_streams(e.chain));
+      }
+      for (size_t r = 0; r < out_sp.len.size(); ++r)
+        if (((dst.off + oo[r]) * esz) % 16) tma = false;
+    }
+    if (engine == 2) tma = false;
+    all_fast = all_fast && tma;
+    // Fast-kernel shape (measured on B200, profiles/README.md): 16 consumer warps x 2 vectors per
+    // thread (16 KB tiles) amortises the per-slot work best -- 81% of HBM peak on config 5, 98% on
+    // config 2 vs 53% / 87% with 8 KB tiles.  Blocks shorter than a few tiles keep 8 KB tiles.
+    int variant = ctx().fast_variant;
+    (void)max_row_terms; (void)max_term_streams;
+    if (variant < 0 || variant > 2) {
+      int64_t longest = 0;
+      for (auto l : out_sp.len) longest = std::max(longest, l);
+      variant = (longest * (int64_t)esz >= 4 * 16384) ? 2 : 0;
+    }
+    const int tile = all_fast ? fast_tile_bytes(variant) / (int)esz : fused_tile_elems(dtype);
     size_t k = 0;
     bool heavy = false;
     constexpr int kSlotStreams = 4, kGroupTermsMax = 4, kGroupStagesMax = 12;
@@ -347,10 +403,11 @@ struct Builder {
                             g_stages + (int)e.chain.size() > kGroupStagesMax))
           close_group();
         GTerm gt{};
-        gt.stage0 = (int16_t)g_stages;
-        gt.nstages = (int16_t)e.chain.size();
-        gt.stream0 = (int16_t)grp.nstreams;
-        gt.sign = (int16_t)tm.sign;
+        gt.stage0 = (uint8_t)g_stages;
+        gt.nstages = (uint8_t)e.chain.size();
+        gt.stream0 = (uint8_t)grp.nstreams;
+        gt.sign = (int8_t)tm.sign;
+        gt.pattern = (uint8_t)classify(e.chain);
         grp.terms[g_terms++] = gt;
         grp.ptr[grp.nstreams] = (int64_t)(tm.in_off * (int64_t)esz);   // relative to the apply's `in`
         grp.rel_mask |= 1 << grp.nstreams;
@@ -372,7 +429,7 @@ struct Builder {
       if (row.len == 0) continue;
       t.rows.push_back(row);
     }
-    if (fused_nslots(t.max_streams) < 2) tma = false;
+    if ((all_fast ? fast_nslots(variant, t.max_streams) : fused_nslots(t.max_streams)) < 2) tma = false;
     t.tma_ok = tma;
     bool use_tma = tma;
     if (engine == 2) use_tma = false;
@@ -411,6 +468,8 @@ struct Builder {
     f.hl = hl; f.hr = hr; f.slot_streams = t.max_streams;
     f.S = K;
     f.heavy = heavy;
+    f.fast = all_fast && use_tma;
+    f.variant = variant;
     f.tile_elems = tile;
     f.use_tma = use_tma;
     if (f.nrows > 0) {
@@ -686,7 +745,10 @@ void run_plan(Plan& p, int dtype, char* in, char* out) {
   };
   for (Step& st : p.steps) {
     switch (st.kind) {
-      case ST_FUSED: launch_fused(st.fused, dtype, base(st.src), base(st.dst), c.stream); break;
+      case ST_FUSED:
+        if (st.fused.fast) launch_fused_fast(st.fused, dtype, base(st.src), base(st.dst), c.stream);
+        else launch_fused(st.fused, dtype, base(st.src), base(st.dst), c.stream);
+        break;
       case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;
       case ST_FILL0:
         vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);
