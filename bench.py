@@ -168,45 +168,31 @@ def build_c5(B, rank, world, blk):
     import numpy as np
     import ctypes as C
     T = np.float32
-    rl = NBLK // world
-    r0 = rank * rl
+    D = B.dist
+    part = D.RowPartition(NBLK, world, rank, halo=1)
+    rl, r0 = part.nloc, part.r0
     sp = B.JetSpace(T, blk)
     Wsp = B.JetBSpace([sp] * rl)
     W = B.zeros(Wsp)
+    # counter-based RNG keyed by the GLOBAL element index: every partition draws the same operator
     B.check(B.lib.jets_buf_rand(W._h, SEED_W, C.c_uint64(r0 * blk), 0))
-    Z = B.JopZeroBlock(sp, sp)
     Sup = B.JopStencil(T, blk, "fdiff")
     Slo = B.JopStencil(T, blk, "lap")
-    rows = []
-    for i in range(rl):
-        row = []
-        for j in range(rl + 2):
-            c = r0 - 1 + j
-            if c < 0 or c >= NBLK:
-                row.append(Z)
-            elif j == i + 1:
-                row.append(B.JopDiagonal(B.getblock(W, i + 1)))
-            elif j == i + 2:
-                row.append(Sup)
-            elif j == i:
-                row.append(Slo)
-            else:
-                row.append(Z)
-        rows.append(row)
-    A = B.blockop(rows)
-    xext = B.zeros(B.domain(A))      # rl+2 blocks
-    own = C.c_void_p()
-    B.check(B.lib.jets_buf_view(xext._h, 1, rl, C.byref(own)))
-    x_own = B.DeviceArray(own, Wsp, owner=xext)
+    Z = B.JopZeroBlock(sp, sp)
+
+    def make_block(r, c):
+        if r == c:
+            return B.JopDiagonal(B.getblock(W, r - r0 + 1))
+        return Sup if c == r + 1 else Slo
+    A = D.build_local_operator(B, part, make_block, lambda: Z)
+    comm = D.LibComm(B, part)
+    xext = B.zeros(B.domain(A))      # rl+2 blocks: [lo halo | own | hi halo]
+    x_own = comm.own(xext)
     B.check(B.lib.jets_buf_rand(x_own._h, SEED_M, C.c_uint64(r0 * blk), 0))
     d = B.zeros(B.range_(A))
     mext = B.zeros(B.domain(A))
-    own2 = C.c_void_p()
-    B.check(B.lib.jets_buf_view(mext._h, 1, rl, C.byref(own2)))
-    m_own = B.DeviceArray(own2, Wsp, owner=mext)
-    return dict(A=A, At=B.adjoint(A), xext=xext, x_own=x_own, d=d, mext=mext, m_own=m_own, W=W, rl=rl,
-                lo_x=B.getblock(xext, 1), hi_x=B.getblock(xext, rl + 2),
-                lo_m=B.getblock(mext, 1), hi_m=B.getblock(mext, rl + 2))
+    return dict(A=A, At=B.adjoint(A), xext=xext, x_own=x_own, d=d, mext=mext, m_own=comm.own(mext), W=W, rl=rl,
+                part=part, comm=comm)
 
 
 def run_ours(args):
@@ -226,28 +212,21 @@ def run_ours(args):
     B.check(B.lib.jets_stream_set(C.c_void_p(stream.cuda_stream)))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        ident = C.create_string_buffer(128)
-        if rank == 0:
-            B.check(B.lib.jets_dist_unique_id(ident))
-        t = torch.frombuffer(bytearray(ident.raw), dtype=torch.uint8).cuda()
-        dist.broadcast(t, 0)
-        ident = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
-        B.check(B.lib.jets_dist_init(rank, world, ident))
+        B.dist.init_nccl_from_torch(B, dist, torch, rank, world)
     blk = int(BLK * args.scale)
     blk -= blk % 4
     S = build_c5(B, rank, world, blk)
     A, At, rl = S["A"], S["At"], S["rl"]
+    part, comm = S["part"], S["comm"]
     lib = B.lib
 
     def fwd():
-        if world > 1:
-            B.check(lib.jets_dist_halo_exchange(S["x_own"]._h, 1, S["lo_x"]._h, 1, S["hi_x"]._h))
-        B.mul_(S["d"], A, S["xext"])
+        B.dist.forward(B, part, comm, A, S["xext"], S["d"])
 
     def adj():
+        comm_m = comm
         B.mul_(S["mext"], At, S["d"])
-        if world > 1:
-            B.check(lib.jets_dist_halo_reduce(S["m_own"]._h, 1, S["lo_m"]._h, 1, S["hi_m"]._h))
+        comm_m.halo_reduce(S["mext"], part.halo, part.nloc)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,27 +239,24 @@ def run_ours(args):
         adj()
     barrier()
     # parity at full size through size-independent properties: <A m, d> == <m, A' d> over all ranks
-    dpt = None
-    if True:
-        y = B.rand(B.range_(A), seed=77 + rank)
-        tmp = B.zeros(B.domain(A))
-        fwd()
-        lhs = float(B.dot(S["d"], y))
-        B.mul_(tmp, At, y)
-        if world > 1:
-            own = C.c_void_p()
-            B.check(lib.jets_buf_view(tmp._h, 1, rl, C.byref(own)))
-            t_own = B.DeviceArray(own, S["x_own"].space, owner=tmp)
-            B.check(lib.jets_dist_halo_reduce(t_own._h, 1, B.getblock(tmp, 1)._h, 1, B.getblock(tmp, rl + 2)._h))
-            rhs = float(B.dot(S["x_own"], t_own))
-            v1, v2 = C.c_double(lhs), C.c_double(rhs)
-            B.check(lib.jets_dist_sum_scalar(C.byref(v1)))
-            B.check(lib.jets_dist_sum_scalar(C.byref(v2)))
-            lhs, rhs = v1.value, v2.value
-        else:
-            rhs = float(B.dot(S["xext"], tmp))
-        dpt = abs(lhs - rhs) / abs(lhs + rhs)
-        del y, tmp
+    def ddot(x, y):  # f64 dot over all ranks, partials summed in rank order (bit-stable)
+        r = C.c_double()
+        B.check(lib.jets_dot(x._h, y._h, C.byref(r)))
+        return comm.sum_scalar(r.value)
+
+    y = B.zeros(B.range_(A))
+    B.check(lib.jets_buf_rand(y._h, 77, C.c_uint64(part.r0 * blk), 0))
+    tmp = B.zeros(B.domain(A))
+    fwd()
+    lhs = ddot(S["d"], y)
+    B.mul_(tmp, At, y)
+    comm.halo_reduce(tmp, part.halo, part.nloc)
+    rhs = ddot(S["x_own"], comm.own(tmp))
+    dpt = abs(lhs - rhs) / abs(lhs + rhs)
+    adj()
+    # partition-independent checksums of the two results (compare across --gpus N runs)
+    checksum = {"dot(A*m, y)": lhs, "|A'*A*m|^2": ddot(S["m_own"], S["m_own"])}
+    del y, tmp
     barrier()
 
     sampler = ClockSampler(local) if rank == 0 else None
@@ -363,7 +339,7 @@ def run_ours(args):
                 "what": "pinned host m -> H2D -> d=A*m -> m'=A'*d -> D2H m' through jets_buf_upload/jets_apply/jets_buf_download"},
         "gpu_launches": int(ln.item()),
         "clocks": clocks,
-        "parity": {"dot_product_test_rel": dpt, "tolerance": 1e-5},
+        "parity": {"dot_product_test_rel": dpt, "tolerance": 1e-5, "checksum": checksum},
         "engine": B.plan_info(A),
     }
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -9,3 +9,4 @@ from ._lib import JetsError, init, lib, LIB_PATH, SIGNATURES  # noqa: F401
 from .core import *  # noqa: F401,F403
 from .core import (DeviceArray, JetSpace, JetBSpace, JopNl, JopLn, JopAdjoint, Jop)  # noqa: F401
 from . import solvers  # noqa: F401
+from . import dist  # noqa: F401

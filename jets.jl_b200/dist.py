@@ -1,0 +1,155 @@
+"""Block-row partition of a JopBlock across GPUs (one process per GPU) -- SURVEY §8e.
+
+The reference has no distributed path (Jets.jl is single-process; DistributedJets.jl is a separate
+package), so this is the build's own design: rank g owns a contiguous range of block rows, the
+matching range blocks of the result and the matching domain blocks.  For a block-banded operator
+(bandwidth b: op[r,c] == JopZeroBlock for |r-c| > b) the forward apply needs only b halo blocks
+from each neighbour (``jets_dist_halo_exchange``, NCCL send/recv over NVLink) instead of an
+all-gather of the whole domain, and the adjoint sends its partial contributions to the b blocks
+it does not own back to their owners, which add them in rank order (``jets_dist_halo_reduce``;
+deterministic).  Dense block structure uses ``jets_dist_allgather`` / ``jets_dist_reduce_scatter``.
+
+Everything here is host-side bookkeeping: pure functions of (nblk, world, rank) plus two
+communication strategies with the same interface -- ``LibComm`` (libjets_b200 + NCCL, device
+buffers) and any object with ``halo_exchange`` / ``halo_reduce`` / ``sum_scalar`` (the CPU tests
+drive the very same partition logic over torch.distributed gloo).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class RowPartition:
+    """Contiguous block-row ownership: rank g owns rows [r0, r1) of `nblk`."""
+    nblk: int
+    world: int
+    rank: int
+    halo: int = 1  # bandwidth of the block-banded operator
+
+    def __post_init__(self):
+        if self.nblk % self.world:
+            raise ValueError(f"{self.nblk} block rows do not split evenly over {self.world} ranks")
+        if self.nblk // self.world < self.halo:
+            raise ValueError("fewer local block rows than the halo width")
+
+    @property
+    def nloc(self):
+        return self.nblk // self.world
+
+    @property
+    def r0(self):
+        return self.rank * self.nloc
+
+    @property
+    def r1(self):
+        return self.r0 + self.nloc
+
+    @property
+    def next_cols(self):
+        """Number of block columns of the halo-extended local domain [lo halo | own | hi halo]."""
+        return self.nloc + 2 * self.halo
+
+    def global_col(self, j):
+        """Global block column of extended local column j, or None outside the operator."""
+        c = self.r0 - self.halo + j
+        return c if 0 <= c < self.nblk else None
+
+    def local_block_map(self):
+        """[[(r, c) or None]]: the global block behind every entry of the nloc x next_cols local
+        operator (None = outside the band or outside the operator -> JopZeroBlock)."""
+        rows = []
+        for i in range(self.nloc):
+            r = self.r0 + i
+            row = []
+            for j in range(self.next_cols):
+                c = self.global_col(j)
+                row.append((r, c) if c is not None and abs(r - c) <= self.halo else None)
+            rows.append(row)
+        return rows
+
+    @property
+    def has_prev(self):
+        return self.rank > 0
+
+    @property
+    def has_next(self):
+        return self.rank + 1 < self.world
+
+
+def build_local_operator(K, part: RowPartition, make_block, zero_block):
+    """Local rows of the global operator as a K.blockop over the halo-extended domain.
+    ``make_block(r, c)`` builds the global block (r, c); ``zero_block()`` a JopZeroBlock."""
+    Z = zero_block()
+    rows = [[Z if rc is None else make_block(*rc) for rc in row] for row in part.local_block_map()]
+    return K.blockop(rows)
+
+
+def forward(K, part: RowPartition, comm, A_loc, x_ext, d_loc):
+    """d_loc = (A x)[own rows]: gather the halo blocks of x, then one local fused apply."""
+    h, n = part.halo, part.nloc
+    comm.halo_exchange(x_ext, h, n)
+    return K.mul_(d_loc, A_loc, x_ext)
+
+
+def adjoint(K, part: RowPartition, comm, A_loc, m_ext, d_loc):
+    """m_ext[own] = (A' d)[own columns]: one local fused adjoint apply produces partial sums for the
+    halo columns too; they are sent to their owners and added in rank order."""
+    h, n = part.halo, part.nloc
+    K.mul_(m_ext, K.adjoint(A_loc), d_loc)
+    comm.halo_reduce(m_ext, h, n)
+    return m_ext
+
+
+class LibComm:
+    """NCCL inside libjets_b200.so (device buffers).  ``x_ext`` is a DeviceArray with
+    nloc + 2*halo blocks."""
+
+    def __init__(self, B, part: RowPartition):
+        self.B, self.part = B, part
+        self._views = {}
+
+    def _view(self, x, first, n):
+        key = (id(x), first, n)
+        v = self._views.get(key)
+        if v is None:
+            h = C.c_void_p()
+            self.B.check(self.B.lib.jets_buf_view(x._h, first, n, C.byref(h)))
+            sp = self.B.JetBSpace(x.space.spaces[first:first + n])
+            v = self._views[key] = self.B.DeviceArray(h, sp, owner=x)
+        return v
+
+    def halo_exchange(self, x_ext, h, n):
+        if self.part.world == 1:
+            return
+        own, lo, hi = self._view(x_ext, h, n), self._view(x_ext, 0, h), self._view(x_ext, h + n, h)
+        self.B.check(self.B.lib.jets_dist_halo_exchange(own._h, h, lo._h, h, hi._h))
+
+    def halo_reduce(self, m_ext, h, n):
+        if self.part.world == 1:
+            return
+        own, lo, hi = self._view(m_ext, h, n), self._view(m_ext, 0, h), self._view(m_ext, h + n, h)
+        self.B.check(self.B.lib.jets_dist_halo_reduce(own._h, h, lo._h, h, hi._h))
+
+    def own(self, x_ext):
+        return self._view(x_ext, self.part.halo, self.part.nloc)
+
+    def sum_scalar(self, v):
+        if self.part.world == 1:
+            return float(v)
+        r = C.c_double(float(v))
+        self.B.check(self.B.lib.jets_dist_sum_scalar(C.byref(r)))
+        return r.value
+
+
+def init_nccl_from_torch(B, dist_mod, torch_mod, rank, world):
+    """Create the library's NCCL communicator: rank 0 makes the ncclUniqueId, torch.distributed
+    (already initialised by the launcher) broadcasts its 128 bytes."""
+    ident = C.create_string_buffer(128)
+    if rank == 0:
+        B.check(B.lib.jets_dist_unique_id(ident))
+    t = torch_mod.frombuffer(bytearray(ident.raw), dtype=torch_mod.uint8).cuda()
+    dist_mod.broadcast(t, 0)
+    ident = C.create_string_buffer(bytes(t.cpu().numpy().tobytes()), 128)
+    B.check(B.lib.jets_dist_init(rank, world, ident))
