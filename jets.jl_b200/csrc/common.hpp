@@ -273,7 +273,7 @@ struct DBlock {
   int32_t pad;
 };
 
-enum StepKind : int { ST_FUSED, ST_GEMV, ST_FILL0 };
+enum StepKind : int { ST_FUSED, ST_GEMV, ST_FILL0, ST_GEMM_TC };
 enum AccMode : int { ACC_SET = 0, ACC_ADD = 1, ACC_SUB = 2 };
 
 struct Ref {           // where a step reads / writes: 0 = apply's `in`, 1 = apply's `out`, >=2 tmp
@@ -292,6 +292,15 @@ struct Step {
   int64_t gemv_tiles = 0;
   int acc = ACC_SET;
   int64_t fill_len = 0;
+  // ST_GEMM_TC (kernels_gemm_tc.cu): pre-split right-hand sides, tensor maps, tile tables
+  int32_t tc_np = 0, tc_nsegs = 0;
+  int64_t tc_kp = 0;
+  void* tc_xs = nullptr;
+  void* tc_maps = nullptr;
+  void* tc_segs = nullptr;
+  int32_t* tc_tile_ptr = nullptr;
+  int32_t* tc_koff = nullptr;
+  alignas(64) unsigned char tc_xmap[128] = {};
 };
 
 struct Plan {
@@ -319,6 +328,11 @@ void launch_fused_fast(const DevFused& f, int dtype, const char* in, char* out, 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);
 void gemv_tile_count(int dtype, bool trans, int32_t out_len, int32_t* ntiles);
+
+// kernels_gemm_tc.cu
+bool gemm_tc_eligible(int dtype, const std::vector<DBlock>& blocks);
+void gemm_tc_prepare(Step& st, Plan& plan);
+void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s);
 
 // kernels_vec.cu
 void vec_fill(int dtype, void* p, int64_t n, double a, cudaStream_t s);

@@ -1,0 +1,563 @@
+// Dense block primitive applied to MANY right-hand sides: D = A X and M = A' Y for a whole table
+// of column-major Float32 matrix blocks on the 5th-generation tensor cores
+// (replaces the per-column stdlib mul! the reference would run for a matrix of right-hand sides:
+// _matmul_df!/_df'! src/Jets.jl:573-574 and the JetBlock_df!/df'! accumulation :1024,:1049).
+//
+// Precision: kind::tf32 keeps 11 significant bits, far short of the 1e-5 the path promises, so
+// every product is evaluated as the classic three-term split
+//     a*x ~= a_hi*x_hi + a_hi*x_lo + a_lo*x_hi,   a_hi = a & ~0x1fff,  a_lo = tf32(a - a_hi)
+// (all four operands exactly representable in tf32, so the tensor core sees exact inputs; the
+// dropped a_lo*x_lo term is 2^-22 relative).  The tensor core TRUNCATES when it adds into the f32
+// accumulator (measured: 1.5e-5 relative after 768 accumulates), so the main term a_hi*x_hi gets
+// its own accumulator columns (one truncation per 8-deep k-step), the two 2^-11-sized correction
+// terms share a second set, and both are folded into per-thread f32 registers with
+// round-to-nearest adds every kDrainStages k-stages: the result does not depend on the length
+// of the reduction.
+//
+// The kernel is HBM-bound by design (32 flop/B on the matrix stream), so it is built around the
+// matrix bytes: one CTA per SM, persistent over 128-row output tiles, no split-K, no atomics.
+//   warp 8      A producer: per 32-deep k-stage four 32x32 TMA boxes of the matrix block
+//               (cp.async.bulk.tensor, evict-first), an 8-deep ring = 128 KB in flight per SM
+//   warp 9      X producer: one box of the pre-split right-hand sides [x_hi | x_lo] per stage
+//               (evict-last: every tile re-reads them from L2), a 4-deep ring
+//   warps 4-7   read the landed A tile ONCE from shared memory, one matrix row per thread, split it
+//               and write a_hi / a_lo straight into TENSOR MEMORY (tcgen05.st): the MMA takes its A
+//               operand from TMEM, so shared memory carries the matrix bytes exactly twice
+//               (TMA write + this read) instead of ~8x with hi/lo copies in shared memory
+//   warp 10     issues tcgen05.mma.kind::tf32 (A from TMEM, X from shared memory through a K-major
+//               128B-swizzle descriptor), commits ring slots and accumulator chunks to mbarriers
+//   warps 0-3   epilogue: tcgen05.ld the accumulator chunk, add into registers, store the tile
+// Both orientations read the matrix from its one column-major layout: A*X stages [k][32 rows]
+// boxes and each thread gathers its row with conflict-free 4-byte loads; A'*Y stages [col][32 k]
+// boxes (128B swizzle) and each thread reads its own 128-byte row.
+#include <cuda.h>
+#include <algorithm>
+#include <map>
+#include "common.hpp"
+
+namespace jets {
+namespace {
+
+constexpr int BM = 128;            // output rows per tile (= TMEM lanes)
+constexpr int BK = 32;             // k per stage
+constexpr int kAStages = 8;        // matrix ring (HBM latency)
+constexpr int kXStages = 4;        // right-hand-side ring == TMEM operand ring
+constexpr int kABytes = BM * BK * 4;           // 16 KB
+constexpr int kXBytes = 128 * BK * 4;          // 2*NP rows of 128 B, NP <= 64
+constexpr int kDrainStages = 8;    // TMEM accumulation length (256 k) before folding into registers
+constexpr int kThreads = 352;      // 11 warps
+constexpr int kTmemCols = 512;     // [0,256): 2 accumulator buffers x (main | correction) x 64; [256,512): 4 A slots x (hi | lo) x 32
+constexpr int kBufCols = 128;
+constexpr int kASlotCol = 256;
+constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kXStages * kXBytes + 512;
+
+struct TcParams {
+  const DBlock* blocks;
+  const int32_t* row_ptr;
+  const int32_t* tile_ptr;
+  const int32_t* koff;        // per block: first k of its input block inside the split buffer
+  const CUtensorMap* amaps;   // per block
+  int32_t ngroups, ntiles;
+  int32_t np;                 // padded right-hand-side count (multiple of 16, <= 64)
+  int32_t nrhs, n0;           // right-hand sides handled by this launch: [n0, n0+nrhs)
+  int32_t trans, acc;
+  float* out;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_2d(uint32_t dst, const void* map, int c0, int c1, uint32_t bar, uint64_t policy) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, %3}], [%4], %5;"
+      ::"r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar), "l"(policy) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, A: 128 lanes x 8 columns of tf32, B: N x 8 through a shared-memory descriptor
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]),
+        "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]),
+        "r"(v[30]), "r"(v[31]) : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 UMMA), K-major 128B swizzle: start>>4 [0,14), LBO>>4 [16,30)
+// (unused for swizzled K-major), SBO>>4 [32,46) = 1024 B between 8-row groups, version=1 [46,48),
+// layout SWIZZLE_128B=2 [61,64).
+__device__ __forceinline__ uint64_t make_desc_k128(uint32_t saddr) {
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// Instruction descriptor: D=f32 [4,6)=1, A=tf32 [7,10)=2, B=tf32 [10,13)=2, both K-major, N>>3 [17,23), M>>4 [24,29).
+__device__ __forceinline__ uint32_t make_idesc(int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
+__device__ __forceinline__ int find_group(const int32_t* tile_ptr, int ngroups, int tile) {
+  int lo = 0, hi = ngroups - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if (tile_ptr[mid] <= tile) lo = mid; else hi = mid - 1;
+  }
+  return lo;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) {
+  extern __shared__ unsigned char smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms need 1024-byte alignment
+  unsigned char* sbase = smem_raw + (base - raw);
+  const uint32_t a0 = base, x0 = base + kAStages * kABytes;
+  const uint32_t bars = x0 + kXStages * kXBytes;
+  const uint32_t a_full0 = bars, a_empty0 = bars + 64, x_full0 = bars + 128, t_ready0 = bars + 160, mma_done0 = bars + 192,
+                 acc_full0 = bars + 224, acc_empty0 = bars + 240;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAStages * kABytes + kXStages * kXBytes + 256);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(a_full0 + 8 * s, 1);
+      mbar_init(a_empty0 + 8 * s, 4);
+    }
+    for (int s = 0; s < kXStages; ++s) {
+      mbar_init(x_full0 + 8 * s, 1);
+      mbar_init(t_ready0 + 8 * s, 4);
+      mbar_init(mma_done0 + 8 * s, 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(acc_full0 + 8 * b, 1);
+      mbar_init(acc_empty0 + 8 * b, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 10) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+  const int np = P.np;
+
+  if (warp == 8) {
+    // =============================== A producer =================================
+    if (lane == 0) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int g = find_group(P.tile_ptr, P.ngroups, tile);
+        const int m0 = (tile - P.tile_ptr[g]) * BM;
+        for (int e = P.row_ptr[g]; e < P.row_ptr[g + 1]; ++e) {
+          const DBlock b = P.blocks[e];
+          const int kdim = P.trans ? b.rows : b.cols;
+          const int nk = (kdim + BK - 1) / BK;
+          const CUtensorMap* amap = P.amaps + e;
+          for (int kc = 0; kc < nk; ++kc, ++it) {
+            const int s = it % kAStages;
+            mbar_wait(a_empty0 + 8 * s, ((it / kAStages) & 1) ^ 1);
+            const uint32_t st = a0 + s * kABytes;
+            mbar_expect_tx(a_full0 + 8 * s, kABytes);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              // tensor map dims: (row, col) -- forward: rows are the tile's M, cols the k-stage;
+              // adjoint: rows are the k-stage, cols the tile's M
+              const int c_row = P.trans ? kc * BK : m0 + 32 * q;
+              const int c_col = P.trans ? m0 + 32 * q : kc * BK;
+              tma_2d(st + q * 4096, amap, c_row, c_col, a_full0 + 8 * s, pol);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // =============================== X producer =================================
+    if (lane == 0) {
+      uint64_t pol;
+      asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+      const uint32_t xbytes = (uint32_t)(2 * np) * BK * 4;
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int g = find_group(P.tile_ptr, P.ngroups, tile);
+        for (int e = P.row_ptr[g]; e < P.row_ptr[g + 1]; ++e) {
+          const DBlock b = P.blocks[e];
+          const int kdim = P.trans ? b.rows : b.cols;
+          const int nk = (kdim + BK - 1) / BK;
+          const int koff = P.koff[e];
+          for (int kc = 0; kc < nk; ++kc, ++it) {
+            const int s = it % kXStages;
+            mbar_wait(mma_done0 + 8 * s, ((it / kXStages) & 1) ^ 1);
+            mbar_expect_tx(x_full0 + 8 * s, xbytes);
+            tma_2d(x0 + s * kXBytes, &xmap, koff + kc * BK, 0, x_full0 + 8 * s, pol);
+          }
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== MMA issuer =================================
+    const uint32_t idesc_main = make_idesc(2 * np);   // a_hi x [x_hi | x_lo]
+    const uint32_t idesc_corr = make_idesc(np);       // a_lo x x_hi
+    uint32_t it = 0, cn = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      const int g = find_group(P.tile_ptr, P.ngroups, tile);
+      for (int e = P.row_ptr[g]; e < P.row_ptr[g + 1]; ++e) {
+        const DBlock b = P.blocks[e];
+        const int kdim = P.trans ? b.rows : b.cols;
+        const int nk = (kdim + BK - 1) / BK;
+        for (int c0 = 0; c0 < nk; c0 += kDrainStages, ++cn) {
+          const int c1 = min(nk, c0 + kDrainStages);
+          const int buf = cn & 1;
+          mbar_wait(acc_empty0 + 8 * buf, ((cn >> 1) & 1) ^ 1);
+          // columns [0,np): a_hi*x_hi (the main term, ONE truncating accumulate per k-step);
+          // columns [np,2np): a_hi*x_lo + a_lo*x_hi (2^-11 smaller, so its rounding does not matter)
+          const uint32_t d_tmem = tmem_base + buf * kBufCols;
+          for (int kc = c0; kc < c1; ++kc, ++it) {
+            const int s = it % kXStages;
+            const uint32_t ph = (it / kXStages) & 1;
+            mbar_wait(x_full0 + 8 * s, ph);
+            mbar_wait(t_ready0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (lane == 0) {
+              const uint32_t xs = x0 + s * kXBytes;
+              const uint32_t a_hi = tmem_base + kASlotCol + s * 64, a_lo = a_hi + 32;
+#pragma unroll
+              for (int ks = 0; ks < BK / 8; ++ks) {
+                const uint64_t x_all = make_desc_k128(xs + ks * 32);   // a k-step advances 32 bytes inside the 128-byte row
+                umma_tf32_ts(d_tmem, a_hi + ks * 8, x_all, idesc_main, (kc > c0 || ks > 0) ? 1u : 0u);
+                umma_tf32_ts(d_tmem + np, a_lo + ks * 8, x_all, idesc_corr, 1u);
+              }
+              umma_commit(mma_done0 + 8 * s);                      // X slot and TMEM operand slot are free once the MMAs retire
+              if (kc + 1 == c1) umma_commit(acc_full0 + 8 * buf);  // accumulator chunk complete
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // =============================== split A into TMEM (warps 4-7) ==============
+    const int q = warp - 4;                 // TMEM lane quarter == 32-row box of the tile
+    const int r = q * 32 + lane;            // this thread's tile row
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      const int g = find_group(P.tile_ptr, P.ngroups, tile);
+      for (int e = P.row_ptr[g]; e < P.row_ptr[g + 1]; ++e) {
+        const int kdim = P.trans ? P.blocks[e].rows : P.blocks[e].cols;
+        const int nk = (kdim + BK - 1) / BK;
+        for (int kc = 0; kc < nk; ++kc, ++it) {
+          const int sa = it % kAStages, st = it % kXStages;
+          mbar_wait(a_full0 + 8 * sa, (it / kAStages) & 1);
+          uint32_t hi[32], lo[32];
+          const unsigned char* tile_p = sbase + (size_t)sa * kABytes;
+          if (P.trans) {
+            // [col][32 k], 128B swizzle: 16-byte chunk c of row r sits at chunk (c ^ (r & 7))
+            const uint4* row = reinterpret_cast<const uint4*>(tile_p + r * 128);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 v = row[c ^ (r & 7)];
+              hi[4 * c + 0] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
+            }
+          } else {
+            // [k][32 rows] per 32-row box, no swizzle: the warp reads one 128-byte line per k
+            const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_p + q * 4096) + lane;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) hi[k] = col[k * 32];
+          }
+#pragma unroll
+          for (int k = 0; k < 32; ++k) {
+            const uint32_t a = hi[k];
+            hi[k] = a & 0xFFFFE000u;
+            lo[k] = __float_as_uint(__uint_as_float(a) - __uint_as_float(hi[k])) & 0xFFFFE000u;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(a_empty0 + 8 * sa);            // the shared-memory slot can be refilled
+          mbar_wait(mma_done0 + 8 * st, ((it / kXStages) & 1) ^ 1);  // TMEM operand slot free (MMAs of it-4 retired)
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem_base + lane_addr + kASlotCol + st * 64;
+          tmem_st32(taddr, hi);
+          tmem_st32(taddr + 32, lo);
+          asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(t_ready0 + 8 * st);
+        }
+      }
+    }
+  } else {
+    // =============================== epilogue (warps 0-3) =======================
+    float acc[64];
+    uint32_t cn = 0;
+    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+      const int g = find_group(P.tile_ptr, P.ngroups, tile);
+      const int m0 = (tile - P.tile_ptr[g]) * BM;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) acc[c] = 0.f;
+      int64_t out_off = 0;
+      int mdim = 0;
+      for (int e = P.row_ptr[g]; e < P.row_ptr[g + 1]; ++e) {
+        const DBlock b = P.blocks[e];
+        out_off = b.out_off;
+        mdim = P.trans ? b.cols : b.rows;
+        const int kdim = P.trans ? b.rows : b.cols;
+        const int nk = (kdim + BK - 1) / BK;
+        for (int c0 = 0; c0 < nk; c0 += kDrainStages, ++cn) {
+          const int buf = cn & 1;
+          mbar_wait(acc_full0 + 8 * buf, (cn >> 1) & 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t taddr = tmem_base + lane_base + buf * kBufCols;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (q * 16 < np) {
+              uint32_t v[16], w[16];
+              tmem_ld16(taddr + q * 16, v);
+              tmem_ld16(taddr + np + q * 16, w);
+              asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+              for (int c = 0; c < 16; ++c) acc[q * 16 + c] += __uint_as_float(v[c]) + __uint_as_float(w[c]);
+            }
+          }
+          asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(acc_empty0 + 8 * buf);
+        }
+      }
+      // store the tile: row i of the block, right-hand side n -> out[out_off + i + n*mdim]
+      const int i = m0 + warp * 32 + lane;
+      if (i < mdim) {
+        float* o = P.out + out_off + i + (int64_t)P.n0 * mdim;
+#pragma unroll
+        for (int n = 0; n < 64; ++n) {
+          if (n < P.nrhs) {
+            float* p = o + (int64_t)n * mdim;
+            if (P.acc == ACC_SET) *p = acc[n];
+            else if (P.acc == ACC_ADD) *p = *p + acc[n];
+            else *p = *p - acc[n];
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 10) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(kTmemCols) : "memory");
+  }
+}
+
+// Right-hand sides -> the split buffer: xs[n][koff + k] = hi(x[k + n*kdim]), xs[np + n][...] = lo.
+struct SplitSeg { int64_t in_off; int32_t kdim, koff; };
+__global__ void split_rhs_kernel(const float* __restrict__ in, float* __restrict__ xs, const SplitSeg* __restrict__ segs,
+                                 int nsegs, int64_t kp, int np, int nrhs, int n0, int nrhs_total) {
+  const int seg = blockIdx.y;
+  const SplitSeg sg = segs[seg];
+  const int64_t total = (int64_t)sg.kdim * nrhs;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int n = (int)(idx / sg.kdim);
+    const int k = (int)(idx - (int64_t)n * sg.kdim);
+    const float x = in[sg.in_off + k + (int64_t)(n0 + n) * sg.kdim];
+    const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
+    const uint32_t l = __float_as_uint(x - __uint_as_float(h)) & 0xFFFFE000u;
+    xs[(int64_t)n * kp + sg.koff + k] = __uint_as_float(h);
+    xs[(int64_t)(np + n) * kp + sg.koff + k] = __uint_as_float(l);
+  }
+  (void)nsegs; (void)nrhs_total;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    CUDA_TRY(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    JETS_CHECK(p && q == cudaDriverEntryPointSuccess, JETS_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+void encode_2d(CUtensorMap* m, const void* ptr, uint64_t inner, uint64_t outer, uint64_t stride_bytes, uint32_t box_inner,
+               uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+  const cuuint64_t dims[2] = {inner, outer};
+  const cuuint64_t strides[1] = {stride_bytes};
+  const cuuint32_t box[2] = {box_inner, box_outer};
+  const cuuint32_t es[2] = {1, 1};
+  const CUresult r = encode_fn()(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  JETS_CHECK(r == CUDA_SUCCESS, JETS_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): ptr=%p dims=%llu x %llu stride=%llu", (int)r, ptr,
+             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)stride_bytes);
+}
+
+}  // namespace
+
+// Can this table of dense blocks run on the tensor-core path?
+bool gemm_tc_eligible(int dtype, const std::vector<DBlock>& blocks) {
+  if (dtype != JETS_F32 || blocks.empty()) return false;
+  if (getenv("JETS_B200_NO_TC")) return false;
+  for (const DBlock& b : blocks) {
+    if (b.nrhs < 2 || b.nrhs != blocks[0].nrhs) return false;
+    if ((reinterpret_cast<uintptr_t>(b.A) & 15) || (b.lda % 4)) return false;  // TMA: 16-byte base and row pitch
+  }
+  return true;
+}
+
+// Builds the device tables of a tensor-core GEMM step (blocks sorted by out_off, block-level offsets).
+void gemm_tc_prepare(Step& st, Plan& plan) {
+  const std::vector<DBlock>& blocks = st.dblocks;
+  const bool trans = blocks[0].trans != 0;
+  const int nrhs = blocks[0].nrhs;
+  const int ngrp = std::min(nrhs, 64);
+  const int np = (ngrp + 15) & ~15;
+  std::vector<int32_t> row_ptr{0}, tile_ptr{0}, koff(blocks.size());
+  std::map<int64_t, int32_t> seg_of;      // in_off -> koff
+  std::vector<SplitSeg> segs;
+  int64_t kp = 0;
+  for (size_t i = 0; i < blocks.size(); ++i) {
+    const DBlock& b = blocks[i];
+    const int kdim = trans ? b.rows : b.cols;
+    auto it = seg_of.find(b.in_off);
+    if (it == seg_of.end()) {
+      JETS_CHECK(kp + kdim + BK < (1LL << 31), JETS_ERR_UNSUPPORTED, "dense block table too large for the tensor-core path");
+      it = seg_of.emplace(b.in_off, (int32_t)kp).first;
+      segs.push_back(SplitSeg{b.in_off, kdim, (int32_t)kp});
+      kp += ((int64_t)kdim + BK - 1) / BK * BK;   // zero padding up to the next k-stage
+    }
+    koff[i] = it->second;
+    const bool last = i + 1 == blocks.size() || blocks[i + 1].out_off != b.out_off;
+    if (last) {
+      row_ptr.push_back((int32_t)i + 1);
+      const int mdim = trans ? b.cols : b.rows;
+      tile_ptr.push_back(tile_ptr.back() + (mdim + BM - 1) / BM);
+    }
+  }
+  st.n_out_rows = (int32_t)row_ptr.size() - 1;
+  st.gemv_tiles = tile_ptr.back();
+  st.tc_np = np;
+  st.tc_kp = kp;
+  st.tc_nsegs = (int32_t)segs.size();
+  // split buffer (zero-filled once: the padding is never written afterwards)
+  const size_t xs_bytes = (size_t)2 * np * kp * sizeof(float);
+  char* xs = nullptr;
+  CUDA_TRY(cudaMalloc(&xs, xs_bytes));
+  CUDA_TRY(cudaMemset(xs, 0, xs_bytes));
+  plan.blobs.push_back(xs);
+  st.tc_xs = xs;
+  encode_2d(reinterpret_cast<CUtensorMap*>(st.tc_xmap), xs, (uint64_t)kp, (uint64_t)2 * np, (uint64_t)kp * 4, BK, 2 * np);
+  // per-block matrix maps: dims (rows, cols), row pitch lda
+  std::vector<CUtensorMap> maps(blocks.size());
+  for (size_t i = 0; i < blocks.size(); ++i)
+    encode_2d(&maps[i], blocks[i].A, (uint64_t)blocks[i].rows, (uint64_t)blocks[i].cols, (uint64_t)blocks[i].lda * 4, 32, 32,
+              trans ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+  auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_maps = 0, o_blocks = o_maps + al(maps.size() * sizeof(CUtensorMap)),
+               o_row = o_blocks + al(blocks.size() * sizeof(DBlock)), o_tile = o_row + al(row_ptr.size() * 4),
+               o_koff = o_tile + al(tile_ptr.size() * 4), o_segs = o_koff + al(koff.size() * 4),
+               total = o_segs + al(segs.size() * sizeof(SplitSeg));
+  std::vector<char> host(total, 0);
+  memcpy(host.data() + o_maps, maps.data(), maps.size() * sizeof(CUtensorMap));
+  memcpy(host.data() + o_blocks, blocks.data(), blocks.size() * sizeof(DBlock));
+  memcpy(host.data() + o_row, row_ptr.data(), row_ptr.size() * 4);
+  memcpy(host.data() + o_tile, tile_ptr.data(), tile_ptr.size() * 4);
+  memcpy(host.data() + o_koff, koff.data(), koff.size() * 4);
+  memcpy(host.data() + o_segs, segs.data(), segs.size() * sizeof(SplitSeg));
+  char* blob = nullptr;
+  CUDA_TRY(cudaMalloc(&blob, total));
+  CUDA_TRY(cudaMemcpy(blob, host.data(), total, cudaMemcpyHostToDevice));
+  plan.blobs.push_back(blob);
+  st.tc_maps = blob + o_maps;
+  st.d_dblocks = reinterpret_cast<DBlock*>(blob + o_blocks);
+  st.d_row_ptr = reinterpret_cast<int32_t*>(blob + o_row);
+  st.tc_tile_ptr = reinterpret_cast<int32_t*>(blob + o_tile);
+  st.tc_koff = reinterpret_cast<int32_t*>(blob + o_koff);
+  st.tc_segs = blob + o_segs;
+}
+
+void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
+  if (st.n_out_rows == 0 || st.gemv_tiles == 0) return;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(jets_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    attr_set = true;
+  }
+  const int nrhs_total = st.dblocks[0].nrhs;
+  int maxk = 1;
+  for (const DBlock& b : st.dblocks) maxk = std::max(maxk, st.dblocks[0].trans ? b.rows : b.cols);
+  for (int n0 = 0; n0 < nrhs_total; n0 += 64) {
+    const int nrhs = std::min(64, nrhs_total - n0);
+    {
+      const int64_t work = (int64_t)maxk * nrhs;
+      dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 64), (unsigned)st.tc_nsegs);
+      split_rhs_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(st.tc_xs),
+                                            reinterpret_cast<const SplitSeg*>(st.tc_segs), st.tc_nsegs, st.tc_kp, st.tc_np, nrhs, n0,
+                                            nrhs_total);
+      CUDA_TRY(cudaGetLastError());
+      count_launch();
+    }
+    TcParams P;
+    P.blocks = st.d_dblocks;
+    P.row_ptr = st.d_row_ptr;
+    P.tile_ptr = st.tc_tile_ptr;
+    P.koff = st.tc_koff;
+    P.amaps = reinterpret_cast<const CUtensorMap*>(st.tc_maps);
+    P.ngroups = st.n_out_rows;
+    P.ntiles = (int32_t)st.gemv_tiles;
+    P.np = st.tc_np;
+    P.nrhs = nrhs;
+    P.n0 = n0;
+    P.trans = st.dblocks[0].trans;
+    P.acc = st.acc;
+    P.out = reinterpret_cast<float*>(out);
+    const int grid = (int)std::min<int64_t>(st.gemv_tiles, ctx().sm_count);
+    CUtensorMap xmap;
+    memcpy(&xmap, st.tc_xmap, sizeof(xmap));
+    jets_gemm_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(P, xmap);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
+}
+
+}  // namespace jets

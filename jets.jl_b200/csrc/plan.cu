@@ -552,9 +552,28 @@ struct Builder {
     return a;
   }
 
-  void push_dense(std::vector<DBlock>& n, std::vector<DBlock>& t, jets_op leaf, bool trans,
-                  int64_t out_off, int64_t in_off, int which_src, int which_dst) {
-    (void)which_src; (void)which_dst;
+  // Dense tables of one apply: single-vector GEMV entries (n: A*x, t: A'*x) and, for leaves with
+  // several right-hand sides that qualify for the tensor-core path, block-level entries (tn / tt).
+  struct DenseTables {
+    std::vector<DBlock> n, t, tn, tt;
+    bool empty() const { return n.empty() && t.empty() && tn.empty() && tt.empty(); }
+    int kinds() const { return !n.empty() + !t.empty() + !tn.empty() + !tt.empty(); }
+  };
+
+  void push_dense(DenseTables& D, jets_op leaf, bool trans, int64_t out_off, int64_t in_off) {
+    if (leaf->nrhs >= 2) {
+      DBlock b{};
+      b.A = leaf->w->ptr();
+      b.rows = (int32_t)leaf->rows; b.cols = (int32_t)leaf->cols; b.lda = (int32_t)leaf->rows;
+      b.trans = trans; b.nrhs = (int32_t)leaf->nrhs;
+      b.in_off = in_off; b.out_off = out_off;
+      std::vector<DBlock>& v = trans ? D.tt : D.tn;
+      std::vector<DBlock> probe{b};
+      if (gemm_tc_eligible(dtype, probe) && (v.empty() || v[0].nrhs == b.nrhs)) {
+        v.push_back(b);
+        return;
+      }
+    }
     for (int64_t k = 0; k < leaf->nrhs; ++k) {
       DBlock b{};
       b.A = leaf->w->ptr();
@@ -562,7 +581,40 @@ struct Builder {
       b.trans = trans; b.nrhs = 1;
       b.in_off = in_off + k * (trans ? leaf->rows : leaf->cols);
       b.out_off = out_off + k * (trans ? leaf->cols : leaf->rows);
-      (trans ? t : n).push_back(b);
+      (trans ? D.t : D.n).push_back(b);
+    }
+  }
+
+  // Tensor-core GEMM over a table of block-level dense entries (all one orientation, same nrhs).
+  void emit_gemm_tc(std::vector<DBlock>& blocks, int acc, Ref src, Ref dst) {
+    if (blocks.empty()) return;
+    std::stable_sort(blocks.begin(), blocks.end(),
+                     [](const DBlock& x, const DBlock& y) { return x.out_off < y.out_off; });
+    Step st;
+    st.kind = ST_GEMM_TC;
+    st.acc = acc;
+    st.src = src; st.dst = dst;
+    st.dblocks = blocks;
+    gemm_tc_prepare(st, plan);
+    plan.engines |= 8;
+    plan.steps.push_back(std::move(st));
+  }
+
+  // Emits every table of D (first one with `acc`, the rest accumulating on top).
+  void emit_dense(DenseTables& D, int acc, Ref src, Ref dst) {
+    int cur = acc;
+    auto next = [&]() { cur = (acc == ACC_SET) ? ACC_ADD : acc; };
+    for (auto* v : {&D.n, &D.t}) {
+      if (v->empty()) continue;
+      emit_gemv(*v, cur);
+      plan.steps.back().src = Ref{src.which, 0};
+      plan.steps.back().dst = Ref{dst.which, 0};
+      next();
+    }
+    for (auto* v : {&D.tn, &D.tt}) {
+      if (v->empty()) continue;
+      emit_gemm_tc(*v, cur, Ref{src.which, 0}, Ref{dst.which, 0});
+      next();
     }
   }
 
@@ -588,12 +640,9 @@ struct Builder {
       case K_LNVIEW: lower(a->kids[0], map_mode_lnview(mode), dst, src, acc); return;
       case K_ADJ: lower(a->kids[0], map_mode_adj(mode), dst, src, acc); return;
       case K_DENSE: {
-        std::vector<DBlock> n, t;
-        push_dense(n, t, a, mode == JETS_MODE_DFT, dst.off, src.off, 0, 0);
-        Step* st;
-        emit_gemv(n.empty() ? t : n, acc);
-        st = &plan.steps.back();
-        st->src = src; st->dst = dst;
+        DenseTables D;
+        push_dense(D, a, mode == JETS_MODE_DFT, dst.off, src.off);
+        emit_dense(D, acc, src, dst);
         return;
       }
       case K_COMPOSE: {
@@ -649,7 +698,7 @@ struct Builder {
         const Space& isp = in_space(a, mode);
         const auto oo = offsets_of(osp), io = offsets_of(isp);
         const int nout = (int)osp.len.size();
-        std::vector<DBlock> dn, dt;
+        DenseTables D;
         Entries fes;
         struct Rest { jets_op op; int o, i; };
         std::vector<Rest> rest;
@@ -660,8 +709,8 @@ struct Builder {
             const int o = adj ? c : r, i = adj ? r : c;
             bool trans = false;
             if (jets_op leaf = dense_leaf(kid, mode, trans)) {
-              push_dense(dn, dt, leaf, trans, dst.off + oo[o], src.off + io[i], 0, 0);
-              covered[o] |= trans ? 2 : 1;
+              push_dense(D, leaf, trans, dst.off + oo[o], src.off + io[i]);
+              covered[o] |= 1;
               continue;
             }
             Entries es;
@@ -678,14 +727,12 @@ struct Builder {
             }
             rest.push_back({kid, o, i});
           }
-        // Pure dense, one orientation, every output block covered: SET directly (one launch).
-        const bool pure = fes.empty() && rest.empty() && (dn.empty() || dt.empty()) &&
+        // Pure dense, one table, every output block covered: SET directly (one launch).
+        const bool pure = fes.empty() && rest.empty() && D.kinds() == 1 &&
                           std::all_of(covered.begin(), covered.end(), [](int v) { return v != 0; });
         int cur = acc;
         if (pure) {
-          emit_gemv(dn.empty() ? dt : dn, acc);
-          plan.steps.back().src = Ref{src.which, 0};
-          plan.steps.back().dst = Ref{dst.which, 0};
+          emit_dense(D, acc, src, dst);
           return;
         }
         plan.engines |= 16;
@@ -693,12 +740,7 @@ struct Builder {
         emit_fused(fes, osp, isp, dst, src, acc);
         cur = (acc == ACC_SET) ? ACC_ADD : acc;
         // ... then dense tables and whatever is left accumulate on top
-        for (auto* v : {&dn, &dt}) {
-          if (v->empty()) continue;
-          emit_gemv(*v, cur);
-          plan.steps.back().src = Ref{src.which, 0};
-          plan.steps.back().dst = Ref{dst.which, 0};
-        }
+        emit_dense(D, cur, src, dst);
         for (auto& x : rest) {
           Ref d = dst, s = src;
           d.off += oo[x.o];
@@ -750,6 +792,7 @@ void run_plan(Plan& p, int dtype, char* in, char* out) {
         else launch_fused(st.fused, dtype, base(st.src), base(st.dst), c.stream);
         break;
       case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;
+      case ST_GEMM_TC: launch_gemm_tc(st, base(st.src), base(st.dst), c.stream); break;
       case ST_FILL0:
         vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);
         break;

@@ -532,6 +532,64 @@ def test_dense_multi_rhs(O, D):
     assert_close(x.to_host(), A.astype(np.float64).T @ y.to_host().astype(np.float64), T)
 
 
+@pytest.mark.parametrize("shape", [(1, 1, 128, 64, 16), (1, 1, 96, 64, 8), (1, 1, 300, 200, 5), (2, 3, 256, 128, 64),
+                                   (3, 2, 100, 76, 33), (1, 2, 1031, 516, 2), (2, 2, 2048, 2048, 64), (1, 1, 64, 4096, 70)])
+def test_dense_multi_rhs_tcgen05(O, D, shape):
+    """Dense blocks applied to several right-hand sides run on the tcgen05/TMEM path (split-TF32,
+    three MMAs per product) and must still meet the Float32 tolerance in both orientations, including
+    ragged tiles (rows/cols not multiples of the 128x32 tile), padded right-hand-side counts and more
+    than 64 right-hand sides (two launches)."""
+    nr, nc, rows, cols, nrhs = shape
+    T = np.float32
+    B = D.B
+    g = np.random.default_rng(160 + rows + nrhs)
+    Bm = [[(g.random((rows, cols)) - 0.3).astype(T) for _ in range(nc)] for _ in range(nr)]
+    X = [(g.random((cols, nrhs)) - 0.5).astype(T) for _ in range(nc)]
+    Y = [(g.random((rows, nrhs)) - 0.5).astype(T) for _ in range(nr)]
+    A = B.blockop([[B.JopDense(Bm[r][c], nrhs=nrhs) for c in range(nc)] for r in range(nr)])
+    x = B.to_device(np.concatenate([v.reshape(-1, order="F") for v in X]), B.domain(A))
+    y = B.to_device(np.concatenate([v.reshape(-1, order="F") for v in Y]), B.range_(A))
+    f = (A * x).to_host()
+    t = (B.adjoint(A) * y).to_host()
+    # TMA needs a 16-byte row pitch: a column-major block with rows % 4 != 0 falls back to one GEMV per column
+    assert B.plan_info(A)["engines"] == (["tcgen05"] if rows % 4 == 0 else ["gemv"]), B.plan_info(A)
+    f = [f[r * rows * nrhs:(r + 1) * rows * nrhs].reshape((rows, nrhs), order="F") for r in range(nr)]
+    t = [t[c * cols * nrhs:(c + 1) * cols * nrhs].reshape((cols, nrhs), order="F") for c in range(nc)]
+    # The data is signed, so single outputs can cancel to ~0: the elementwise criterion is the componentwise
+    # bound |err_i| <= tol * sum_k |a_ik||x_k| (what "1e-5 relative" means for an inner product), plus the
+    # norm-wise relative error Julia's isapprox uses.
+    def check(got, terms):
+        ref = sum(a @ b for a, b in terms)
+        scale = sum(np.abs(a) @ np.abs(b) for a, b in terms)
+        assert np.linalg.norm(got - ref) <= TOL[np.dtype(T)] * np.linalg.norm(ref)
+        assert np.all(np.abs(got - ref) <= TOL[np.dtype(T)] * scale), float(np.max(np.abs(got - ref) / scale))
+    for r in range(nr):
+        check(f[r], [(Bm[r][c].astype(np.float64), X[c].astype(np.float64)) for c in range(nc)])
+    for c in range(nc):
+        check(t[c], [(Bm[r][c].astype(np.float64).T, Y[r].astype(np.float64)) for r in range(nr)])
+    lhs, rhs = B.dot_product_test(A, x, y)
+    big = float(np.abs(np.concatenate([v.ravel() for v in Y])).sum()) * max(float(np.abs(b).max()) for row in Bm for b in row)
+    assert abs(lhs - rhs) <= TOL[np.dtype(T)] * max(abs(lhs), abs(rhs), 1e-3 * big)
+
+
+def test_dense_multi_rhs_accumulates_with_other_terms(O, D):
+    """A block row mixing a tensor-core dense block with a diagonal block: the fused launch SETs the row,
+    the GEMM accumulates on top (plan = fused + tcgen05)."""
+    T = np.float32
+    B = D.B
+    g = np.random.default_rng(171)
+    n, nrhs = 256, 16
+    Am = g.random((n, n)).astype(T)
+    w = g.random(n * nrhs).astype(T)
+    x = g.random(2 * n * nrhs).astype(T)
+    A = B.blockop([[B.JopDense(Am, nrhs=nrhs), B.JopDiagonal(B.to_device(w, B.JetSpace(T, n, nrhs)))]])
+    y = (A * B.to_device(x, B.domain(A))).to_host()
+    X0 = x[:n * nrhs].reshape((n, nrhs), order="F").astype(np.float64)
+    ref = (Am.astype(np.float64) @ X0).reshape(-1, order="F") + w.astype(np.float64) * x[n * nrhs:]
+    assert_close(y, ref, T)
+    assert "tcgen05" in B.plan_info(A)["engines"]
+
+
 # ------------------------------------------------------------------ engines, edge cases -----
 @pytest.mark.parametrize("T", [np.float32, np.float64])
 def test_tma_and_ldg_engines_agree_bitwise(D, T):
