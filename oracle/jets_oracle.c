@@ -15,6 +15,9 @@
  * mode 0 "faithful": single thread, the reference's passes and temporaries (Jets has no threading).
  * mode 1 "threaded": the same arithmetic in the same order, fused per output element and spread over
  *                    all host cores with OpenMP -- the strongest CPU version of this path.
+ * mode 2 "faithful-threaded": the reference's passes and temporaries (mode 0), every elementwise
+ *                    pass spread over all host cores -- what Jets would do if Julia's broadcast
+ *                    were multithreaded.
  * Compiled with -ffp-contract=off: one rounding per operation, like Julia's broadcast, so both
  * modes and the numpy oracle agree bit for bit.
  */
@@ -43,18 +46,22 @@ int jets_ref_num_threads(void) {
 
 #define DEFINE(T, SUF)                                                                              \
   /* leaf applied to a whole block: out = op(in) (adj: op'(in)) */                                  \
-  static void leaf_apply_##SUF(const jets_ref_leaf* op, int adj, T* out, const T* in, int64_t n) {  \
+  static void leaf_apply_##SUF(const jets_ref_leaf* op, int adj, T* out, const T* in, int64_t n,   \
+                               int par) {                                                          \
     const T* w = (const T*)op->state;                                                               \
     int64_t i;                                                                                      \
     switch (op->kind) {                                                                             \
       case LEAF_DIAG:                                                                               \
+        _Pragma("omp parallel for schedule(static) if(par)")                                        \
         for (i = 0; i < n; ++i) out[i] = w[i] * in[i];                                              \
         break;                                                                                      \
       case LEAF_FDIFF:                                                                              \
         if (!adj) {                                                                                 \
-          for (i = 0; i + 1 < n; ++i) out[i] = in[i + 1] - in[i];                                   \
+          _Pragma("omp parallel for schedule(static) if(par)")                                      \
+          for (i = 0; i < n - 1; ++i) out[i] = in[i + 1] - in[i];                                   \
           out[n - 1] = 0;                                                                           \
         } else {                                                                                    \
+          _Pragma("omp parallel for schedule(static) if(par)")                                      \
           for (i = 0; i < n; ++i) {                                                                 \
             const T l = i >= 1 ? in[i - 1] : (T)0;                                                  \
             const T r = i + 1 < n ? in[i] : (T)0;                                                   \
@@ -63,6 +70,7 @@ int jets_ref_num_threads(void) {
         }                                                                                           \
         break;                                                                                      \
       case LEAF_LAP:                                                                                \
+        _Pragma("omp parallel for schedule(static) if(par)")                                        \
         for (i = 0; i < n; ++i) {                                                                   \
           const T l = i >= 1 ? in[i - 1] : (T)0;                                                    \
           const T r = i + 1 < n ? in[i + 1] : (T)0;                                                 \
@@ -109,7 +117,8 @@ int jets_ref_num_threads(void) {
     for (o = 0; o < NO; ++o) { ooff[o + 1] = ooff[o] + olen[o]; if (olen[o] > maxlen) maxlen = olen[o]; } \
     ioff[0] = 0;                                                                                    \
     for (k = 0; k < NI; ++k) ioff[k + 1] = ioff[k] + ilen[k];                                       \
-    if (mode == 0) {                                                                                \
+    if (mode == 0 || mode == 2) {                                                                   \
+      const int par = (mode == 2);                                                                  \
       /* zeros(range(A)) of `A*m` (:399); fresh temporary like zeros(range(ops[1,1])) (:1012-1014) */ \
       T* tmp = (T*)calloc((size_t)(maxlen > 0 ? maxlen : 1), sizeof(T));                            \
       memset(out, 0, (size_t)ooff[NO] * sizeof(T));                                                 \
@@ -122,10 +131,11 @@ int jets_ref_num_threads(void) {
           const jets_ref_leaf* op = adj ? &ops[k + (size_t)o * R] : &ops[o + (size_t)k * R];        \
           if (op->kind == LEAF_ZERO) continue; /* iszero skip (:1022,:1047) */                      \
           if (NI > 1) {                                                                             \
-            leaf_apply_##SUF(op, adj, tmp, in + ioff[k], n);                                        \
+            leaf_apply_##SUF(op, adj, tmp, in + ioff[k], n, par);                                   \
+            _Pragma("omp parallel for schedule(static) if(par)")                                    \
             for (i = 0; i < n; ++i) _o[i] = _o[i] + tmp[i]; /* _d .+= dtmp (:1024,:1049) */         \
           } else {                                                                                  \
-            leaf_apply_##SUF(op, adj, _o, in + ioff[k], n);                                         \
+            leaf_apply_##SUF(op, adj, _o, in + ioff[k], n, par);                                    \
           }                                                                                         \
         }                                                                                           \
       }                                                                                             \

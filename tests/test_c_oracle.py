@@ -1,4 +1,4 @@
-"""The C restatement (CPU baseline) must agree bit for bit with the numpy oracle in both modes."""
+"""The C restatement (CPU baseline) must agree bit for bit with the numpy oracle in every mode."""
 import numpy as np
 import pytest
 
@@ -7,7 +7,7 @@ from oracle import jets_oracle as J
 
 
 @pytest.mark.parametrize("T", [np.float32, np.float64])
-@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1, 2])
 def test_block_tridiagonal_matches_numpy_oracle(T, mode):
     g = np.random.default_rng(0)
     nb, n = 5, 4099
