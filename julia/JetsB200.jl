@@ -1,0 +1,219 @@
+# JetsB200.jl -- the reference-side binding for libjets_b200.so.
+#
+# STATUS: UNEXECUTED.  Julia is not installed in the build image, so this file has never been
+# parsed or run; it is the stub a Jets.jl maintainer would add (see INTEGRATION.md) and is kept
+# deliberately thin so that it can be checked by inspection against include/jets_b200.h.
+# Every `ccall` below names one entry point of that header; nothing else crosses the boundary.
+#
+# What it provides, in Jets' own vocabulary (src/Jets.jl line numbers of v1.4.1):
+#   * B200Array{T} <: AbstractVector{T}   -- device storage for JetSpace / JetBSpace vectors
+#     (flat buffer + block offset table; `getblock` is a view).           :105-108, :809-924
+#   * B200 leaf constructors returning ordinary JopLn / JopNl whose closures ccall the
+#     library: JopDiagonalB200, JopPointwiseB200, JopStencilB200, JopDenseB200.
+#   * `LinearAlgebra.mul!` methods for JopLn/JopNl/JopAdjoint whose tree is all-B200: the WHOLE
+#     tree (block / sum / composite / adjoint) is handed to ONE `jets_apply`.  :390-392
+#   * device methods for dot / norm / fill! / extrema / broadcast-axpy.   :834-911
+module JetsB200
+
+using Jets, LinearAlgebra
+
+const LIB = get(ENV, "JETS_B200_LIB", "libjets_b200")
+
+struct JetsB200Error <: Exception
+    code::Cint
+    msg::String
+end
+function check(code::Cint)
+    code == 0 && return nothing
+    throw(JetsB200Error(code, unsafe_string(ccall((:jets_last_error, LIB), Cstring, ()))))
+end
+
+init(device::Integer = 0) = check(ccall((:jets_init, LIB), Cint, (Cint,), device))
+dtype_code(::Type{Float32}) = Cint(0)
+dtype_code(::Type{Float64}) = Cint(1)
+
+# ------------------------------------------------------------------ device storage --------
+mutable struct B200Array{T} <: AbstractVector{T}
+    h::Ptr{Cvoid}                 # jets_buf
+    blocklengths::Vector{Int64}
+    function B200Array{T}(h::Ptr{Cvoid}, bl::Vector{Int64}) where {T}
+        x = new{T}(h, bl)
+        finalizer(x -> ccall((:jets_buf_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), x)
+        x
+    end
+end
+Base.size(x::B200Array) = (sum(x.blocklengths),)
+
+# zeros(R) / Array(R) for JetSpace and JetBSpace                      src/Jets.jl:105-108, :922-924
+blocklengths(R::Jets.JetSpace) = Int64[length(R)]
+blocklengths(R::Jets.JetBSpace) = Int64[length(Jets.space(R, i)) for i in 1:Jets.nblocks(R)]
+function b200zeros(R::Jets.JetAbstractSpace{T}) where {T}
+    bl = blocklengths(R)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_buf_create, LIB), Cint, (Cint, Int32, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+                dtype_code(T), length(bl), bl, h))
+    B200Array{T}(h[], bl)
+end
+# host <-> device: setblock!/getblock!/convert(Array,x)               src/Jets.jl:862-868, :915-916
+function Base.copyto!(x::B200Array{T}, a::Array{T}) where {T}
+    check(ccall((:jets_buf_upload, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{T}, Int64), x.h, -1, a, length(a)))
+    x
+end
+function Base.Array(x::B200Array{T}) where {T}
+    a = Vector{T}(undef, length(x))
+    check(ccall((:jets_buf_download, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{T}, Int64), x.h, -1, a, length(a)))
+    a
+end
+function Jets.getblock(x::B200Array{T}, i::Integer) where {T}              # a view, :914
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_buf_view, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{Ptr{Cvoid}}), x.h, i - 1, 1, h))
+    B200Array{T}(h[], [x.blocklengths[i]])
+end
+function Jets.setblock!(x::B200Array{T}, i::Integer, a::Array{T}) where {T} # :916
+    check(ccall((:jets_buf_upload, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{T}, Int64), x.h, i - 1, a, length(a)))
+end
+
+# reductions and updates                                               src/Jets.jl:834-911
+function LinearAlgebra.dot(x::B200Array{T}, y::B200Array{T}) where {T}
+    r = Ref{Cdouble}(0)
+    check(ccall((:jets_dot, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}), x.h, y.h, r))
+    T(r[])
+end
+function LinearAlgebra.norm(x::B200Array{T}, p::Real = 2) where {T}
+    r = Ref{Cdouble}(0)
+    check(ccall((:jets_norm, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cdouble}), x.h, p, r))
+    T(r[])
+end
+Base.fill!(x::B200Array, a) = (check(ccall((:jets_buf_fill, LIB), Cint, (Ptr{Cvoid}, Cdouble), x.h, a)); x)
+function Base.extrema(x::B200Array{T}) where {T}
+    mn = Ref{Cdouble}(0); mx = Ref{Cdouble}(0)
+    check(ccall((:jets_extrema, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), x.h, mn, mx))
+    (T(mn[]), T(mx[]))
+end
+# out .= a.*x .+ b.*y  (the axpy-class broadcasts of CG/LSQR; :905-911)
+function axpby!(out::B200Array, a::Real, x::B200Array, b::Real, y::B200Array)
+    c = Cdouble[a, b]; hs = Ptr{Cvoid}[x.h, y.h]
+    check(ccall((:jets_lincomb, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Cdouble}, Ptr{Ptr{Cvoid}}), out.h, 2, c, hs))
+    out
+end
+
+# ------------------------------------------------------------------ operators --------------
+# The jets_op handle lives in the Jet's state NamedTuple (`s.b200`), so Jets' own combinators
+# (∘, +, -, @blockop, adjoint, jacobian) keep working unchanged; `handle(A)` maps a Jets tree onto
+# a library tree once and caches it.
+mutable struct OpHandle
+    h::Ptr{Cvoid}
+    function OpHandle(h)
+        x = new(h)
+        finalizer(x -> ccall((:jets_op_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), x)
+        x
+    end
+end
+# The closures exist so that a B200 leaf is a legal Jet; they are only reached when a B200 leaf is
+# mixed with CPU operators (then each leaf is one jets_apply on its own).
+function leaf_apply!(out::B200Array, h::OpHandle, mode::Integer, in::B200Array)
+    check(ccall((:jets_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint), h.h, mode, out.h, in.h, 0))
+    out
+end
+
+# JopLn(df! = d .= w.*m)  -- fixture JopFoo, test/runtests.jl:3-8
+function JopDiagonalB200(w::B200Array{T}) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_diag, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), w.h, h))
+    oh = OpHandle(h[])
+    sp = JetSpace(T, length(w))
+    JopLn(dom = sp, rng = sp, s = (b200 = oh, w = w),
+          df! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 1, m),
+          df′! = (m, d; b200, kw...) -> leaf_apply!(m, b200, 2, d))
+end
+# JopNl(f! = phi(m), df! = phi'(mo).*dm) -- fixture JopBar, test/runtests.jl:20-25
+function JopPointwiseB200(::Type{T}, n::Integer, fn::Integer = 0, p::Real = 0) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_pointwise, LIB), Cint, (Cint, Int64, Cint, Cdouble, Ptr{Ptr{Cvoid}}), dtype_code(T), n, fn, p, h))
+    oh = OpHandle(h[])
+    sp = JetSpace(T, n)
+    JopNl(dom = sp, rng = sp, s = (b200 = oh,),
+          f! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 0, m),
+          df! = (d, m; mₒ, b200, kw...) -> leaf_apply!(d, b200, 1, m),
+          df′! = (m, d; mₒ, b200, kw...) -> leaf_apply!(m, b200, 2, d),
+          upstate! = (mₒ, s) -> check(ccall((:jets_op_set_point, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s.b200.h, mₒ.h)))
+end
+function JopStencilB200(::Type{T}, n::Integer, kind::Integer = 0) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_stencil, LIB), Cint, (Cint, Int64, Cint, Ptr{Ptr{Cvoid}}), dtype_code(T), n, kind, h))
+    oh = OpHandle(h[])
+    sp = JetSpace(T, n)
+    JopLn(dom = sp, rng = sp, s = (b200 = oh,),
+          df! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 1, m),
+          df′! = (m, d; b200, kw...) -> leaf_apply!(m, b200, 2, d))
+end
+# Matrix as operator (src/Jets.jl:325-326, :573-576); A is a B200Array holding rows*cols column-major
+function JopDenseB200(A::B200Array{T}, rows::Integer, cols::Integer; nrhs::Integer = 1) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_dense, LIB), Cint, (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Ptr{Cvoid}}), A.h, rows, cols, nrhs, h))
+    oh = OpHandle(h[])
+    dom = nrhs == 1 ? JetSpace(T, cols) : JetSpace(T, cols, nrhs)
+    rng = nrhs == 1 ? JetSpace(T, rows) : JetSpace(T, rows, nrhs)
+    JopLn(dom = dom, rng = rng, s = (b200 = oh, A = A),
+          df! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 1, m),
+          df′! = (m, d; b200, kw...) -> leaf_apply!(m, b200, 2, d))
+end
+
+# ---- tree -> handle (built once per Jet, cached in a WeakKeyDict) ---------------------------
+const TREE = WeakKeyDict{Any,OpHandle}()
+isb200(j::Jets.Jet) = haskey(state(j), :b200) ||
+    (haskey(state(j), :ops) && all(op -> isb200(jet(op)), state(j).ops))
+
+function handle(A::Jets.Jop)
+    A isa Jets.JopAdjoint && return unary(:jets_op_adjoint, handle(A.op))
+    j = jet(A)
+    base = get!(TREE, j) do
+        s = state(j)
+        if haskey(s, :b200)
+            s.b200
+        elseif j.f! === Jets.JetComposite_f!                               # :522-576
+            nary(:jets_op_compose, [handle(op) for op in s.ops])
+        elseif j.f! === Jets.JetSum_f!                                     # :628-708
+            hs = [handle(op) for op in s.ops]; sg = Int32[sgn == (+) ? 1 : -1 for sgn in s.sgns]
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:jets_op_sum, LIB), Cint, (Int32, Ptr{Ptr{Cvoid}}, Ptr{Int32}, Ptr{Ptr{Cvoid}}),
+                        length(hs), [x.h for x in hs], sg, h))
+            OpHandle(h[])
+        elseif j.f! === Jets.JetBlock_f!                                   # :926-1057, column-major like Julia
+            hs = [handle(op) for op in s.ops]                              # Matrix{Jop} iterates column-major
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(ccall((:jets_op_block, LIB), Cint, (Int32, Int32, Ptr{Ptr{Cvoid}}, Cint, Ptr{Ptr{Cvoid}}),
+                        size(s.ops, 1), size(s.ops, 2), [x.h for x in hs], s.dom isa Jets.JetBSpace && size(s.ops, 2) == 1, h))
+            OpHandle(h[])
+        else
+            error("not a B200 operator tree")
+        end
+    end
+    # a JopLn over a nonlinear jet applies df! (the linear view), :209-224
+    (A isa Jets.JopLn && !islinear(base)) ? unary(:jets_op_as_linear, base) : base
+end
+islinear(h::OpHandle) = ccall((:jets_op_is_linear, LIB), Cint, (Ptr{Cvoid},), h.h) == 1
+function unary(f::Symbol, a::OpHandle)
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    code = f === :jets_op_adjoint ?
+        ccall((:jets_op_adjoint, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), a.h, h) :
+        ccall((:jets_op_as_linear, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), a.h, h)
+    check(code)
+    OpHandle(h[])
+end
+function nary(::Symbol, hs::Vector{OpHandle})
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_compose, LIB), Cint, (Int32, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}), length(hs), [x.h for x in hs], h))
+    OpHandle(h[])
+end
+
+# ---- mul! overrides: the whole tree in ONE call (src/Jets.jl:390-392) -------------------------
+const MODE_F, MODE_DF, MODE_DFT = Cint(0), Cint(1), Cint(2)
+apply!(d::B200Array, A::Jets.Jop, m::B200Array, mode::Cint) =
+    (check(ccall((:jets_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint), handle(A).h, mode, d.h, m.h, 0)); d)
+LinearAlgebra.mul!(d::B200Array, A::Jets.JopNl, m::B200Array) = apply!(d, A, m, MODE_F)
+LinearAlgebra.mul!(d::B200Array, A::Jets.JopLn, m::B200Array) = apply!(d, A, m, MODE_DF)
+LinearAlgebra.mul!(m::B200Array, A::Jets.JopAdjoint, d::B200Array) = apply!(m, A.op, d, MODE_DFT)
+Base.:*(A::Jets.Jop, m::B200Array) = mul!(b200zeros(range(A)), A, m)       # :399
+
+end # module
