@@ -211,9 +211,11 @@ int jets_op_jacobian(jets_op a, jets_buf mo, jets_op* out);
  * reference whenever `out` came from zeros(range(A)), i.e. for every `A*m` (:399).              */
 int jets_apply(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate);
 /* Which engine the last plan for (op,mode) used: bit0 TMA-fused, bit1 LDG-fused, bit2 dense
- * GEMV, bit3 tcgen05 GEMM, bit4 staged through HBM temporaries.                                 */
+ * GEMV, bit3 tcgen05 GEMM, bit4 staged through HBM temporaries, bit5 TMA-fused with the
+ * shared-memory input-tile cache (rows sharing an input block fetch it once).                   */
 int jets_op_plan_info(jets_op a, int mode, int32_t* engines, int32_t* nlaunches);
-/* Force an engine for A/B measurements: 0 auto, 1 TMA-fused, 2 LDG-fused.                       */
+/* Force an engine for A/B measurements: 0 auto, 1 TMA-fused, 2 LDG-fused, 3 TMA-fused without
+ * the input-tile cache.                                                                         */
 int jets_set_fused_engine(int which);
 
 /* --------------------------------------------------------- multi-GPU (one process per GPU) --- */

@@ -23,6 +23,7 @@ SOURCES = {
     "plan.cu": [],
     "kernels_fused.cu": ["-fmad=false"],
     "kernels_fused_fast.cu": ["-fmad=false"],
+    "kernels_fused_bundle.cu": ["-fmad=false"],
     "kernels_vec.cu": ["-fmad=false"],
     "kernels_dense.cu": [],
     "kernels_gemm_tc.cu": [],

@@ -855,7 +855,7 @@ def plan_info(A, mode=None):
     e, n = C.c_int32(), C.c_int32()
     check(lib.jets_op_plan_info(A._h.h, A._mode if mode is None else mode, C.byref(e), C.byref(n)))
     names = [nm for bit, nm in ((1, "tma"), (2, "ldg"), (4, "gemv"), (8, "tcgen05"), (16, "staged")) if e.value & bit]
-    return {"engines": names, "launches": n.value}
+    return {"engines": names, "launches": n.value, "input_cache": bool(e.value & 32)}
 
 
 def launch_count():
@@ -863,4 +863,4 @@ def launch_count():
 
 
 def set_fused_engine(which):
-    check(lib.jets_set_fused_engine({"auto": 0, "tma": 1, "ldg": 2}.get(which, which)))
+    check(lib.jets_set_fused_engine({"auto": 0, "tma": 1, "ldg": 2, "tma_nocache": 3}.get(which, which)))

@@ -261,6 +261,10 @@ int jets_init(int device) {
     CUDA_TRY(cudaMalloc(&c.dev_scratch, (c.dev_scratch_elems + 64) * sizeof(double)));
     if (const char* v = getenv("JETS_B200_FAST_VARIANT")) c.fast_variant = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_FAST")) c.no_fast = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_BUNDLE")) c.no_bundle = atoi(v);
+    if (const char* v = getenv("JETS_B200_BUNDLE_NX")) c.bundle_nx = atoi(v);
+    if (const char* v = getenv("JETS_B200_BUNDLE_NS")) c.bundle_ns = atoi(v);
+    if (const char* v = getenv("JETS_B200_BUNDLE_BMAX")) c.bundle_bmax = atoi(v);
     c.ready = true;
   });
 }
@@ -294,7 +298,7 @@ int64_t jets_launch_count(void) { return ctx().launches; }
 int jets_device_sm_count(void) { return ctx().sm_count; }
 int jets_set_fused_engine(int which) {
   return guard([&] {
-    JETS_CHECK(which >= 0 && which <= 2, JETS_ERR_INVALID, "engine must be 0,1,2");
+    JETS_CHECK(which >= 0 && which <= 3, JETS_ERR_INVALID, "engine must be 0,1,2,3");
     ctx().fused_engine = which;
   });
 }

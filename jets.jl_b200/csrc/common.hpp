@@ -2,6 +2,7 @@
 // Nothing here is part of the ABI (include/jets_b200.h is).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstddef>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -61,6 +62,10 @@ struct Context {
   int fused_engine = 0;  // 0 auto, 1 TMA, 2 LDG
   int fast_variant = -1; // JETS_B200_FAST_VARIANT (-1 = chosen per plan): consumer shape of the fast TMA kernel
   int no_fast = 0;       // JETS_B200_NO_FAST=1: always use the interpreter kernel
+  int no_bundle = 0;     // JETS_B200_NO_BUNDLE=1: fast kernel without the shared-memory input-tile cache
+  int bundle_nx = 0;     // JETS_B200_BUNDLE_NX / _NS / _BMAX: override the planner's ring sizes (tuning)
+  int bundle_ns = 0;
+  int bundle_bmax = 0;
   double* host_scratch = nullptr;  // pinned, 64 doubles
   double* dev_scratch = nullptr;   // device partials for reductions
   size_t dev_scratch_elems = 0;
@@ -224,6 +229,39 @@ struct GroupRec {    // 272 bytes
   GTerm terms[kGroupTerms];
   CStage stages[kGroupStages];
 };
+// ---- bundle engine (kernels_fused_bundle.cu): rows that share input blocks are walked by ONE CTA
+// at the same tile position, and every input tile lives in a shared-memory ring ("x ring") from
+// its first to its last use, so a block-tridiagonal row costs 2 tile loads instead of 4.
+enum : int { XF_LOAD = 1, XF_RELEASE = 2 };
+enum : int { BG_ROW_FIRST = 1, BG_ROW_LAST = 2, BG_ACC = 4 };
+struct BTerm {       // 8 bytes
+  uint8_t stage0, nstages;   // into the group's stage pool
+  uint8_t sstream0;          // first STATE stream of the term inside the state slot
+  uint8_t pattern;           // Pattern
+  int8_t sign;
+  uint8_t xflags;            // bit0 XF_LOAD (first use of the input tile), bit1 XF_RELEASE (last use),
+                             // bit2 = (xrel / NX) & 1, bits 4-7 = xrel % NX  (filled in once NX is final)
+  uint16_t xrel;             // allocation index of the input tile inside the unit (x ring slot = (base+xrel) % NX)
+};
+struct BGroupRec {   // 320 bytes
+  int64_t xptr[kGroupTerms];   // input block of each term: byte offset from the apply's `in` (xrel_mask bit) or absolute
+  int64_t sptr[kMaxStreams];   // state streams (absolute addresses)
+  int32_t nsstreams, nterms, xrel_mask, flags;   // flags: BG_*   (16B aligned: fetched with one 128-bit load)
+  BTerm terms[kGroupTerms];    // 16B aligned
+  CStage stages[kGroupStages]; // 16B aligned
+  int64_t out_off;             // element offset of the output row relative to the apply's `out`
+  int64_t pad;
+};
+static_assert(offsetof(BGroupRec, nsstreams) % 16 == 0 && offsetof(BGroupRec, terms) % 16 == 0 &&
+              offsetof(BGroupRec, stages) % 16 == 0, "BGroupRec alignment");
+static_assert(sizeof(BGroupRec) == 320, "BGroupRec layout");
+struct BundleRec {   // 32 bytes: consecutive output rows of equal length walked by one CTA per tile position
+  int64_t unit_begin;          // first (bundle, position) unit of this bundle in the launch-wide enumeration
+  int64_t len;                 // row length (elements)
+  int32_t group_begin, ngroups;
+  int32_t nx, pad;             // x-ring allocations per unit
+};
+
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
   int64_t tile_begin;
   int64_t pos_begin;
@@ -258,6 +296,12 @@ struct DevFused {   // device copy + launch geometry
   bool heavy = false;   // chains use transcendental pointwise functions
   bool fast = false;    // every chain has a straight-line fast path -> jets_fused_fast_kernel
   int variant = 0;      // fast-kernel shape: 0 = 16 warps x 1 vec, 1 = 8 x 2, 2 = 16 x 2 (16 KB tiles)
+  // bundle engine
+  bool bundle = false;
+  BGroupRec* bgroups = nullptr;
+  BundleRec* bundles = nullptr;
+  int32_t nbundles = 0, NX = 0, NS = 0, G = 1, sstreams = 0;
+  int64_t nunits = 0;
   void* blob = nullptr;
 };
 
@@ -324,6 +368,10 @@ int fused_nslots(int slot_streams);
 int fast_tile_bytes(int variant);
 int fast_nslots(int variant, int slot_streams);
 void launch_fused_fast(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
+// kernels_fused_bundle.cu
+int bundle_buf_bytes(int variant);
+int bundle_smem_budget();
+void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);

@@ -177,6 +177,27 @@ struct FastIO {
   }
 };
 
+// Bundle engine: stream 0 (the term's input block) lives in the x ring, the state streams (k >= 1)
+// in the state slot, `stride` bytes apart.
+template <typename T>
+struct FastIO2 {
+  using Vec = typename VecOf<T>::type;
+  static constexpr int V = VecOf<T>::V;
+  const char* bin;   // this thread's vector of the input tile
+  const char* bst;   // this thread's vector of the term's first state stream
+  int stride;
+  __device__ __forceinline__ const char* base(int k) const { return k == 0 ? bin : bst + (k - 1) * stride; }
+  __device__ __forceinline__ void vec(int k, T (&x)[V]) const {
+    const Vec v = *reinterpret_cast<const Vec*>(base(k));
+    const T* vs = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int j = 0; j < V; ++j) x[j] = vs[j];
+  }
+  __device__ __forceinline__ T at(int k, int j) const {
+    return *reinterpret_cast<const T*>(base(k) + j * (int)sizeof(T));
+  }
+};
+
 template <typename T>
 __device__ __forceinline__ void st_fdiff(const T (&x)[VecOf<T>::V], T xr, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
@@ -211,8 +232,8 @@ __device__ __forceinline__ void st_lap(const T (&x)[VecOf<T>::V], T xl, T xr, bo
 }
 
 // Returns false when `pattern` has no fast path (the caller falls back to the interpreter).
-template <typename T>
-__device__ __forceinline__ bool eval_fast(int pattern, const FastIO<T>& io, const CStage* stages,
+template <typename T, class IO>
+__device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStage* stages,
                                           bool first, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
   T x[V];

@@ -1,0 +1,380 @@
+// Bundle engine: the fused block apply with a shared-memory INPUT-TILE CACHE.
+//
+// jets_fused_fast_kernel streams every operand of every term through shared memory once per
+// term, so a block-tridiagonal row d_r = w_r.*x_r + S1(x_{r+1}) + S2(x_{r-1}) pulls 4 tiles out
+// of L2 for 3 algorithmic streams, and a 4x4 JopBlock of diagonals pulls each x block 4 times.
+// The re-reads hit L2, but the L2->SM fabric (not DRAM) then bounds the kernel (measured: 0.78
+// and 0.64 of HBM peak, profiles/r01_*).  Here one CTA walks a BUNDLE of consecutive output rows
+// at the same tile position and keeps every input tile in a ring of shared-memory buffers (the
+// "x ring") from its first to its last use: JetBlock_df!'s `_m = getblock(m, jblock)`
+// (src/Jets.jl:1019) is fetched once per tile no matter how many rows read it, exactly as the
+// adjoint's `_d` (:1044).  Operator state (diagonals, linearization points) streams through a
+// second ring of slots, one slot per term group, as before.
+//
+//   producer warp   per (bundle, position) unit, per term group: waits for the state slot, waits
+//                   for the x-ring buffers its first-use terms allocate (ring order; the planner
+//                   guarantees the previous occupant's last use lies in an earlier group), posts
+//                   ONE expect_tx on the slot's `full` mbarrier covering state + new input tiles
+//                   and issues the cp.async.bulk copies.  Up to G lanes issue groups in parallel;
+//                   the planner picks G so that no lane ever waits on a group of its own batch.
+//   16 consumer warps  wait on the slot's `full` barrier only; evaluate the straight-line chains
+//                   (fused_ops.cuh, same IEEE operations as the interpreter -> bit-identical),
+//                   accumulate the row's terms in registers left to right, release the state slot
+//                   and the x buffers whose last use this group was, store the row tile once.
+// Tiles have a run-time length (<= the template's capacity) chosen by the planner so that the
+// number of units is a multiple of the grid: no ragged last wave.
+#include "fused_ops.cuh"
+
+namespace jets {
+namespace {
+
+constexpr int kPad = 16;
+constexpr int kMaxRing = 16;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr int kHdr = 3 * 128 + kMaxRing * 80;          // sfull | sempty | xempty | slot metadata
+constexpr int kHdrAligned = (kHdr + 127) & ~127;
+
+enum : int { F_FIRST = 1, F_LAST = 2, F_END = 4, F_ACC = 8, F_BLK0 = 32, F_BLKEND = 64 };
+
+struct BMeta {                    // 80 bytes, 16B aligned
+  char* out_tile;                 // absolute address of out[tile_start]
+  const BGroupRec* rec;
+  int32_t nvalid, flags, nterms, xrelease;   // xrelease: bit s -> arrive on xempty[s] after this group
+  BTerm terms[kGroupTerms];       // xrel replaced by the ring slot
+  int64_t pad2[2];
+};
+static_assert(sizeof(BMeta) == 80, "BMeta layout");
+
+struct BundleParams {
+  const BGroupRec* groups;
+  const BundleRec* bundles;
+  int32_t nbundles, NX, NS, sstreams, G, tile_elems;
+  int64_t nunits;
+  const char* in;
+  char* out;
+  int32_t hl, hr;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                   "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <typename T, int CW, int VPT>
+__global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(const BundleParams P) {
+  using Vec = typename VecOf<T>::type;
+  constexpr int V = VecOf<T>::V;
+  constexpr int kConsumers = CW * 32;
+  constexpr int kTileBytes = kConsumers * 16 * VPT;
+  constexpr int kBufBytes = kTileBytes + 2 * kPad;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const uint32_t sm0 = smem_u32(smem);
+  const uint32_t sfull0 = sm0, sempty0 = sm0 + 128, xempty0 = sm0 + 256;
+  BMeta* meta = reinterpret_cast<BMeta*>(smem + 384);
+  const int NX = P.NX, NS = P.NS;
+  const uint32_t xring0 = sm0 + kHdrAligned;
+  const uint32_t sring0 = xring0 + (uint32_t)NX * kBufBytes;
+  const uint32_t slot_bytes = (uint32_t)P.sstreams * kBufBytes;
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(sfull0 + 8 * s, 1);
+      mbar_init(sempty0 + 8 * s, CW);
+      mbar_init(xempty0 + 8 * s, CW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (tid >= kConsumers) {
+    // =============================== producer warp ===============================
+    const int lane = tid - kConsumers;
+    const uint32_t lpad = P.hl ? kPad : 0, rpad = P.hr ? kPad : 0;
+    const int64_t te = P.tile_elems;
+    const int G = P.G;
+    int slot = 0;
+    uint32_t par = 0;
+    uint32_t xbase = 0;            // x-ring allocations made by this CTA so far
+    int b = 0;
+    BundleRec B = P.bundles[0];
+    int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
+
+    // One lane issues one term group of unit `q` into state slot `my`.
+    auto issue = [&](const BGroupRec* rec, int64_t q, uint32_t xb, int my, uint32_t mypar) {
+      const int4 hd = __ldg(reinterpret_cast<const int4*>(&rec->nsstreams));  // nsstreams nterms xrel_mask flags
+      const uint4 t01 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[0]));
+      const uint4 t23 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[2]));
+      const int64_t out_off = __ldg(&rec->out_off);
+      const int64_t tile_start = (q - B.unit_begin) * te;
+      const int64_t rem = B.len - tile_start;
+      const int nvalid = rem < te ? (int)rem : (int)te;
+      const uint32_t bytes = lpad + (((uint32_t)nvalid * sizeof(T) + 15u) & ~15u) + rpad;
+      const int64_t goff = tile_start * (int64_t)sizeof(T) - lpad;
+      const int nss = hd.x, nterms = hd.y, xrel_mask = hd.z, gflags = hd.w;
+      BTerm tt[kGroupTerms];
+      *reinterpret_cast<uint4*>(&tt[0]) = t01;
+      *reinterpret_cast<uint4*>(&tt[2]) = t23;
+      // ring position of the unit's first allocation (one division per group, none per term)
+      const uint32_t xb_use = xb / (uint32_t)NX;
+      const uint32_t xb_mod = xb - xb_use * (uint32_t)NX;
+      mbar_wait(sempty0 + 8 * my, mypar ^ 1);
+      uint32_t total = bytes * (uint32_t)nss;
+      int xrelease = 0;
+#pragma unroll
+      for (int t = 0; t < kGroupTerms; ++t) {
+        if (t < nterms) {
+          // allocation index inside the unit = xdiv * NX + xmod (split by the planner)
+          uint32_t xs = xb_mod + (uint32_t)(tt[t].xflags >> 4);
+          uint32_t use = xb_use + ((tt[t].xflags >> 2) & 1u);
+          if (xs >= (uint32_t)NX) { xs -= (uint32_t)NX; ++use; }
+          if (tt[t].xflags & XF_LOAD) {
+            mbar_wait(xempty0 + 8 * xs, (use & 1) ^ 1);
+            total += bytes;
+          }
+          if (tt[t].xflags & XF_RELEASE) xrelease |= 1 << xs;
+          tt[t].xrel = (uint16_t)xs;
+        }
+      }
+      BMeta& M = meta[my];
+      M.out_tile = P.out + (out_off + tile_start) * (int64_t)sizeof(T);
+      M.rec = rec;
+      const int fl = (tile_start == 0 ? F_BLK0 : 0) | (rem <= te ? F_BLKEND : 0) |
+                     ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
+                     ((gflags & BG_ACC) ? F_ACC : 0);
+      *reinterpret_cast<int4*>(&M.nvalid) = make_int4(nvalid, fl, nterms, xrelease);
+      *reinterpret_cast<uint4*>(&M.terms[0]) = *reinterpret_cast<uint4*>(&tt[0]);
+      *reinterpret_cast<uint4*>(&M.terms[2]) = *reinterpret_cast<uint4*>(&tt[2]);
+      if (total == 0) {
+        mbar_arrive(sfull0 + 8 * my);
+        return;
+      }
+      mbar_expect_tx(sfull0 + 8 * my, total);
+#pragma unroll
+      for (int t = 0; t < kGroupTerms; ++t) {
+        if (t < nterms && (tt[t].xflags & XF_LOAD)) {
+          const int64_t px = __ldg(&rec->xptr[t]);
+          const char* src = ((xrel_mask >> t) & 1) ? P.in + px : reinterpret_cast<const char*>(px);
+          bulk_g2s(xring0 + tt[t].xrel * kBufBytes + (kPad - lpad), src + goff, bytes, sfull0 + 8 * my);
+        }
+      }
+      const uint32_t sb = sring0 + my * slot_bytes + (kPad - lpad);
+      for (int k = 0; k < nss; ++k) {
+        const char* src = reinterpret_cast<const char*>(__ldg(&rec->sptr[k]));
+        bulk_g2s(sb + k * kBufBytes, src + goff, bytes, sfull0 + 8 * my);
+      }
+    };
+
+    for (int64_t q = blockIdx.x; q < P.nunits;) {
+      if (q >= unit_end) {  // next bundle (units are enumerated bundle-major; q only grows)
+        int lo = b, hi = P.nbundles - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(&P.bundles[mid].unit_begin) <= q) lo = mid; else hi = mid - 1;
+        }
+        b = lo;
+        B = P.bundles[b];
+        unit_end = B.unit_begin + (B.len + te - 1) / te;
+      }
+      // Short bundles: several units of the bundle are issued side by side, one lane per group, as
+      // long as the batch needs no x buffer that one of its own groups has to release first.
+      int U = 1;
+      if (2 * B.ngroups <= G) {
+        U = G / B.ngroups;
+        if (B.nx > 0 && U > NX / B.nx) U = NX / B.nx;
+        const int64_t mine = (unit_end - 1 - q) / gridDim.x + 1;   // units of this bundle this CTA still owns
+        if (U > mine) U = (int)mine;
+        if (U < 1) U = 1;
+      }
+      if (U > 1) {
+        const int n = U * B.ngroups;
+        if (lane < n) {
+          const int u = lane / B.ngroups, g = lane - u * B.ngroups;
+          int my = slot + lane;
+          uint32_t mypar = par;
+          if (my >= NS) { my -= NS; mypar ^= 1; }
+          issue(P.groups + B.group_begin + g, q + (int64_t)u * gridDim.x, xbase + (uint32_t)(u * B.nx), my, mypar);
+        }
+        slot += n;
+        if (slot >= NS) { slot -= NS; par ^= 1; }
+        __syncwarp();
+      } else {
+        for (int g0 = 0; g0 < B.ngroups; g0 += G) {
+          const int n = (B.ngroups - g0) < G ? (B.ngroups - g0) : G;
+          if (lane < n) {
+            int my = slot + lane;
+            uint32_t mypar = par;
+            if (my >= NS) { my -= NS; mypar ^= 1; }
+            issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar);
+          }
+          slot += n;
+          if (slot >= NS) { slot -= NS; par ^= 1; }
+          __syncwarp();
+        }
+      }
+      xbase += (uint32_t)(U * B.nx);
+      q += (int64_t)U * gridDim.x;
+    }
+    if (lane == 0) {  // end-of-work sentinel
+      mbar_wait(sempty0 + 8 * slot, par ^ 1);
+      meta[slot].flags = F_END;
+      mbar_arrive(sfull0 + 8 * slot);
+    }
+  } else {
+    // =============================== consumer warps ==============================
+    T acc[VPT][V];
+    int slot = 0;
+    uint32_t par = 0;
+    const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
+    const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
+    while (true) {
+      mbar_wait(sfull0 + 8 * slot, par);
+      const BMeta& M = meta[slot];
+      const int flags = M.flags;
+      if (flags & F_END) break;
+      const int nvalid = M.nvalid;
+      const int nterms = M.nterms;
+      const int xrelease = M.xrelease;
+      T* out_tile = reinterpret_cast<T*>(M.out_tile);
+      const CStage* stages = M.rec->stages;
+      if (flags & F_FIRST) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int e0 = (i * kConsumers + tid) * V;
+          if (flags & F_ACC) {
+            if (e0 + V <= nvalid) {
+              const Vec v = *reinterpret_cast<const Vec*>(out_tile + e0);
+              const T* vs = reinterpret_cast<const T*>(&v);
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[i][j] = vs[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[i][j] = (e0 + j < nvalid) ? out_tile[e0 + j] : T(0);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[i][j] = T(0);
+          }
+        }
+      }
+      for (int t = 0; t < nterms; ++t) {
+        const BTerm gt = M.terms[t];
+        FastIO2<T> io;
+        io.stride = kBufBytes;
+        const char* xin = reinterpret_cast<const char*>(xr_p) + (int)gt.xrel * kBufBytes;
+        const char* sst = reinterpret_cast<const char*>(sl_p) + (int)gt.sstream0 * kBufBytes;
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int e0 = (i * kConsumers + tid) * V;
+          const bool first = (flags & F_BLK0) && e0 == 0;
+          const int last = (flags & F_BLKEND) ? nvalid - 1 - e0 : (1 << 30);
+          T val[V];
+          io.bin = xin + i * kConsumers * 16;
+          io.bst = sst + i * kConsumers * 16;
+          eval_fast<T>(gt.pattern, io, stages + gt.stage0, first, last, val);
+          if (gt.sign >= 0) {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[j];
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[j];
+          }
+        }
+      }
+      __syncwarp();
+      if ((tid & 31) == 0) {
+        mbar_arrive(sempty0 + 8 * slot);   // state slot may be refilled
+        int m = xrelease;
+        while (m) {                        // input tiles whose last use this group was
+          const int s = __ffs(m) - 1;
+          m &= m - 1;
+          mbar_arrive(xempty0 + 8 * s);
+        }
+      }
+      if (flags & F_LAST) {
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int e0 = (i * kConsumers + tid) * V;
+          if (e0 + V <= nvalid) {
+            Vec v;
+            T* vs = reinterpret_cast<T*>(&v);
+#pragma unroll
+            for (int j = 0; j < V; ++j) vs[j] = acc[i][j];
+            *reinterpret_cast<Vec*>(out_tile + e0) = v;
+          } else {
+#pragma unroll
+            for (int j = 0; j < V; ++j)
+              if (e0 + j < nvalid) out_tile[e0 + j] = acc[i][j];
+          }
+        }
+      }
+      sl_p += slot_bytes;
+      if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
+    }
+  }
+}
+
+template <typename T, int CW, int VPT>
+void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
+  constexpr int kBufBytes = CW * 32 * 16 * VPT + 2 * kPad;
+  const size_t smem = kHdrAligned + (size_t)f.NX * kBufBytes + (size_t)f.NS * f.sstreams * kBufBytes;
+  JETS_CHECK(smem <= (size_t)kSmemLimit && f.NX >= 1 && f.NX <= kMaxRing && f.NS >= 1 && f.NS <= kMaxRing,
+             JETS_ERR_INVALID, "internal: bundle kernel ring sizes NX=%d NS=%d do not fit", f.NX, f.NS);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(jets_fused_bundle_kernel<T, CW, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    attr_set = true;
+  }
+  int64_t grid = ctx().sm_count;
+  if (grid > P.nunits) grid = P.nunits > 0 ? P.nunits : 1;
+  jets_fused_bundle_kernel<T, CW, VPT><<<(unsigned)grid, CW * 32 + 32, smem, s>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
+
+template <typename T>
+void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s) {
+  switch (f.variant) {
+    case 1: launch_variant<T, 8, 2>(f, P, s); break;
+    case 2: launch_variant<T, 16, 2>(f, P, s); break;
+    default: launch_variant<T, 16, 1>(f, P, s); break;
+  }
+}
+
+}  // namespace
+
+int bundle_buf_bytes(int variant) { return (variant == 2 ? 16384 : 8192) + 2 * kPad; }
+int bundle_smem_budget() { return kSmemLimit - kHdrAligned; }
+
+void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s) {
+  if (f.nbundles == 0 || f.nunits == 0) return;
+  BundleParams P;
+  P.groups = f.bgroups; P.bundles = f.bundles;
+  P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
+  P.tile_elems = f.tile_elems; P.nunits = f.nunits;
+  P.in = in; P.out = out; P.hl = f.hl; P.hr = f.hr;
+  if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
+  else launch_dtype<double>(f, P, s);
+}
+
+}  // namespace jets

@@ -19,6 +19,7 @@ namespace {
 constexpr int kMaxStagesPerTerm = 6;
 constexpr int kMaxStreamsPerTerm = 4;
 constexpr size_t kMaxEntries = 1u << 20;
+constexpr int kMaxRing = 16;   // x ring / state ring capacity of the bundle kernel
 
 struct Entry {
   int r = 0, c = 0;
@@ -359,6 +360,7 @@ struct Builder {
       for (auto l : out_sp.len) longest = std::max(longest, l);
       variant = (longest * (int64_t)esz >= 4 * 16384) ? 2 : 0;
     }
+    if (all_fast && !ctx().no_bundle && engine != 3 && emit_bundle(es, out_sp, in_sp, dst, src, acc, hl, hr, variant)) return;
     const int tile = all_fast ? fast_tile_bytes(variant) / (int)esz : fused_tile_elems(dtype);
     size_t k = 0;
     bool heavy = false;
@@ -499,6 +501,255 @@ struct Builder {
     }
     plan.engines |= use_tma ? 1 : 2;
     plan.steps.push_back(std::move(st));
+  }
+
+  // ---- bundle engine (kernels_fused_bundle.cu) ------------------------------------------------
+  // Rows are grouped into BUNDLES of consecutive equal-length rows that share input blocks; one CTA
+  // evaluates a whole bundle at one tile position, keeping every input tile in the shared-memory x
+  // ring from its first to its last use.  The planner replays the kernel's ring allocation (ring
+  // order, `NX` buffers) to fix, per term, the allocation index of its input tile and whether the
+  // term is the tile's first use (the producer loads it) and/or its last use (consumers release it).
+  struct PTerm {
+    int pattern = 0, sign = 1;
+    int64_t key = 0;                 // input block: byte offset from the apply's `in`
+    std::vector<int64_t> sptr;       // state streams
+    std::vector<CStage> stages;
+  };
+  struct PRow {
+    int64_t out_off = 0, len = 0;
+    std::vector<PTerm> terms;
+  };
+  struct BundleSim {
+    std::vector<BGroupRec> groups;
+    std::vector<BundleRec> bundles;
+    int maxdist = 0, sstreams = 0, max_rows = 1;
+  };
+
+  static void simulate_bundles(const std::vector<PRow>& rows, int NX, int Bmax, bool accflag, BundleSim& o) {
+    o = BundleSim{};
+    size_t ri = 0;
+    while (ri < rows.size()) {
+      BundleRec B{};
+      B.len = rows[ri].len;
+      B.group_begin = (int32_t)o.groups.size();
+      std::map<int64_t, int> where;                      // input key -> latest allocation
+      std::vector<std::pair<int, int>> last_use;         // per allocation: (group index, term index)
+      int next_alloc = 0, nrows = 0;
+      auto resident = [&](int64_t key) {
+        auto it = where.find(key);
+        return (it != where.end() && next_alloc - it->second <= NX) ? it->second : -1;
+      };
+      while (ri < rows.size() && nrows < Bmax && rows[ri].len == B.len && next_alloc < 60000) {
+        const PRow& row = rows[ri];
+        if (nrows > 0) {
+          bool share = false;
+          for (const PTerm& t : row.terms) share = share || resident(t.key) >= 0;
+          if (!share) break;
+        }
+        BGroupRec cur{};
+        int nst = 0;
+        bool first = true;
+        auto flush = [&](bool row_last) {
+          cur.out_off = row.out_off;
+          cur.flags = (first ? BG_ROW_FIRST : 0) | (row_last ? BG_ROW_LAST : 0) | (accflag ? BG_ACC : 0);
+          o.sstreams = std::max(o.sstreams, (int)cur.nsstreams);
+          o.groups.push_back(cur);
+          cur = BGroupRec{};
+          nst = 0;
+          first = false;
+        };
+        for (const PTerm& t : row.terms) {
+          if (cur.nterms > 0 && (cur.nterms == kGroupTerms || cur.nsstreams + (int)t.sptr.size() > kMaxStreams ||
+                                 nst + (int)t.stages.size() > kGroupStages))
+            flush(false);
+          int gi = (int)o.groups.size();
+          int a = resident(t.key);
+          uint8_t xf = 0;
+          if (a >= 0) {
+            o.maxdist = std::max(o.maxdist, next_alloc - a);
+          } else {
+            a = next_alloc;
+            const int occ = a - NX;                      // the allocation this one recycles
+            if (occ >= 0 && last_use[occ].first >= gi) { // still in use by the group being packed
+              flush(false);
+              gi = (int)o.groups.size();
+            }
+            ++next_alloc;
+            where[t.key] = a;
+            last_use.emplace_back(gi, 0);
+            xf = XF_LOAD;
+          }
+          const int ti = cur.nterms++;
+          last_use[a] = {gi, ti};
+          BTerm& bt = cur.terms[ti];
+          bt.stage0 = (uint8_t)nst;
+          bt.nstages = (uint8_t)t.stages.size();
+          bt.sstream0 = (uint8_t)cur.nsstreams;
+          bt.pattern = (uint8_t)t.pattern;
+          bt.sign = (int8_t)t.sign;
+          bt.xflags = xf;
+          bt.xrel = (uint16_t)a;
+          cur.xptr[ti] = t.key;
+          cur.xrel_mask |= 1 << ti;
+          for (int64_t p : t.sptr) cur.sptr[cur.nsstreams++] = p;
+          for (const CStage& c : t.stages) cur.stages[nst++] = c;
+        }
+        flush(true);
+        ++nrows;
+        ++ri;
+      }
+      for (auto& lu : last_use) o.groups[lu.first].terms[lu.second].xflags |= XF_RELEASE;
+      B.ngroups = (int32_t)o.groups.size() - B.group_begin;
+      B.nx = next_alloc;
+      o.max_rows = std::max(o.max_rows, nrows);
+      o.bundles.push_back(B);
+    }
+  }
+
+  // Largest number of lanes that may issue groups of one unit in parallel such that a lane never
+  // waits for an x buffer whose release depends on a group issued by its own batch.
+  static int safe_lanes(const BundleSim& sim, int NX, int NS) {
+    int G = std::min(NS, 32);
+    for (; G > 1; --G) {
+      bool ok = true;
+      for (const BundleRec& B : sim.bundles) {
+        std::vector<int> first_g(B.nx, 0), last_g(B.nx, 0);
+        for (int g = 0; g < B.ngroups; ++g) {
+          const BGroupRec& r = sim.groups[B.group_begin + g];
+          for (int t = 0; t < r.nterms; ++t) {
+            if (r.terms[t].xflags & XF_LOAD) first_g[r.terms[t].xrel] = g;
+            if (r.terms[t].xflags & XF_RELEASE) last_g[r.terms[t].xrel] = g;
+          }
+        }
+        for (int a = NX; a < B.nx && ok; ++a) ok = last_g[a - NX] / G < first_g[a] / G;
+        if (!ok) break;
+      }
+      if (ok) break;
+    }
+    return G;
+  }
+
+  bool emit_bundle(Entries& es, const Space& out_sp, const Space& in_sp, Ref dst, Ref src, int acc, int hl, int hr,
+                   int variant_hint) {
+    const size_t esz = dsize(dtype);
+    const auto oo = offsets_of(out_sp), io = offsets_of(in_sp);
+    std::vector<PRow> rows;
+    size_t k = 0;
+    for (size_t r = 0; r < out_sp.len.size(); ++r) {
+      PRow row;
+      row.out_off = dst.off + oo[r];
+      row.len = out_sp.len[r];
+      while (k < es.size() && es[k].r == (int)r) {
+        const Entry& e = es[k++];
+        JETS_CHECK(in_sp.len[e.c] == out_sp.len[r], JETS_ERR_SHAPE, "elementwise block (%d,%d) maps %lld -> %lld elements",
+                   (int)r, e.c, (long long)in_sp.len[e.c], (long long)out_sp.len[r]);
+        PTerm t;
+        t.pattern = classify(e.chain);
+        t.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
+        t.key = (src.off + io[e.c]) * (int64_t)esz;
+        for (const FStage& s : e.chain) {
+          CStage cs{};
+          cs.op = (uint8_t)s.op; cs.fn = (uint8_t)s.fn; cs.has_stream = s.ptr != nullptr; cs.c0 = s.c0;
+          t.stages.push_back(cs);
+          if (s.ptr) t.sptr.push_back((int64_t)reinterpret_cast<uintptr_t>(s.ptr));
+        }
+        row.terms.push_back(std::move(t));
+      }
+      if (row.len == 0) continue;
+      if (row.terms.empty() && acc != ACC_SET) continue;  // nothing to add
+      rows.push_back(std::move(row));
+    }
+    Step st;
+    st.kind = ST_FUSED;
+    st.src = src; st.dst = dst; st.acc = acc;
+    DevFused& f = st.fused;
+    f.hl = hl; f.hr = hr;
+    f.fast = f.use_tma = f.bundle = true;
+    if (rows.empty()) {
+      plan.engines |= 1;
+      plan.steps.push_back(std::move(st));
+      return true;
+    }
+    const bool accflag = acc != ACC_SET;
+    // reuse distance with an unbounded ring -> how many buffers sharing needs
+    BundleSim sim;
+    simulate_bundles(rows, kMaxRing, 1 << 30, accflag, sim);
+    const int live = std::max(1, std::min(sim.maxdist, 8));
+    const int budget = bundle_smem_budget();
+    int variant = -1, NX = 0, NS = 0;
+    for (int v : {variant_hint, 0}) {
+      const int buf = bundle_buf_bytes(v);
+      const int slot = sim.sstreams * buf;
+      const int D = (budget - live * buf) / (buf + slot);
+      int nx = std::min(kMaxRing, std::max(4, live + D));
+      if (ctx().bundle_nx > 0) nx = std::min(kMaxRing, ctx().bundle_nx);     // tuning / test overrides
+      int ns = slot > 0 ? std::min(kMaxRing, (budget - nx * buf) / slot) : kMaxRing;
+      if (ctx().bundle_ns > 0) ns = std::min(ns, ctx().bundle_ns);
+      const int need = ctx().bundle_ns > 0 ? 1 : 2;
+      if (ns < need || nx * buf + ns * slot > budget) continue;
+      variant = v; NX = nx; NS = ns;
+      break;
+    }
+    if (variant < 0) return false;
+    // bundle length: long bundles share the most, but there must be enough units to fill the GPU
+    const int grid = std::max(1, ctx().sm_count);
+    const int64_t cap = (bundle_buf_bytes(variant) - 32) / (int64_t)esz;
+    auto units = [&](const BundleSim& s, int64_t te) {
+      int64_t u = 0;
+      for (const BundleRec& b : s.bundles) u += (b.len + te - 1) / te;
+      return u;
+    };
+    int Bmax = ctx().bundle_bmax > 0 ? ctx().bundle_bmax : (1 << 30);
+    while (true) {
+      simulate_bundles(rows, NX, Bmax, accflag, sim);
+      if (units(sim, cap) >= 2 * (int64_t)grid || sim.max_rows <= 1) break;
+      Bmax = std::max(1, std::min(Bmax, sim.max_rows) / 2);
+    }
+    // tile length: the largest one (within 25% of the capacity) whose unit count fills whole waves
+    int64_t te = cap;
+    {
+      const int64_t step = 128 / (int64_t)esz;
+      double best = -1;
+      for (int64_t c = cap; c >= cap - cap / 4 && c >= step; c -= step) {
+        const int64_t u = units(sim, c);
+        const int64_t waves = (u + grid - 1) / grid;
+        const double eff = (double)u / (double)(waves * grid);
+        if (eff > best + 1e-3) { best = eff; te = c; }
+      }
+    }
+    for (BGroupRec& gr : sim.groups)          // split every allocation index for the kernel (no division per term)
+      for (int t = 0; t < gr.nterms; ++t) {
+        BTerm& bt = gr.terms[t];
+        bt.xflags = (uint8_t)((bt.xflags & 3) | (((bt.xrel / NX) & 1) << 2) | ((bt.xrel % NX) << 4));
+      }
+    int64_t unit = 0;
+    for (BundleRec& b : sim.bundles) {
+      b.unit_begin = unit;
+      unit += (b.len + te - 1) / te;
+    }
+    f.variant = variant;
+    f.NX = NX; f.NS = NS; f.sstreams = sim.sstreams;
+    f.G = safe_lanes(sim, NX, NS);
+    f.tile_elems = (int)te;
+    f.nbundles = (int32_t)sim.bundles.size();
+    f.nunits = unit;
+    f.nrows = (int32_t)rows.size();
+    f.ntiles = unit;
+    const size_t gb = (sim.groups.size() * sizeof(BGroupRec) + 255) & ~(size_t)255;
+    const size_t bb = sim.bundles.size() * sizeof(BundleRec);
+    std::vector<char> host(gb + bb, 0);
+    memcpy(host.data(), sim.groups.data(), sim.groups.size() * sizeof(BGroupRec));
+    memcpy(host.data() + gb, sim.bundles.data(), bb);
+    char* blob = nullptr;
+    CUDA_TRY(cudaMalloc(&blob, host.size()));
+    CUDA_TRY(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
+    plan.blobs.push_back(blob);
+    f.blob = blob;
+    f.bgroups = reinterpret_cast<BGroupRec*>(blob);
+    f.bundles = reinterpret_cast<BundleRec*>(blob + gb);
+    plan.engines |= 1 | 32;
+    plan.steps.push_back(std::move(st));
+    return true;
   }
 
   // Dense entries sharing one orientation; groups = distinct output blocks.
@@ -788,7 +1039,8 @@ void run_plan(Plan& p, int dtype, char* in, char* out) {
   for (Step& st : p.steps) {
     switch (st.kind) {
       case ST_FUSED:
-        if (st.fused.fast) launch_fused_fast(st.fused, dtype, base(st.src), base(st.dst), c.stream);
+        if (st.fused.bundle) launch_fused_bundle(st.fused, dtype, base(st.src), base(st.dst), c.stream);
+        else if (st.fused.fast) launch_fused_fast(st.fused, dtype, base(st.src), base(st.dst), c.stream);
         else launch_fused(st.fused, dtype, base(st.src), base(st.dst), c.stream);
         break;
       case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;

@@ -7,6 +7,8 @@ import jets_b200 as B
 
 which = sys.argv[1] if len(sys.argv) > 1 else "c5"
 T = np.float32
+B.init(0)
+B.set_fused_engine(os.environ.get("PROF_ENGINE", "auto"))   # auto | tma_nocache | ldg
 if which == "c5":
     nb, blk = 32, 3_906_252
     sp = B.JetSpace(T, blk)
@@ -20,6 +22,13 @@ elif which == "c2":
     sp = B.JetSpace(T, n)
     A = B.jacobian(B.JopDiagonal(B.rand(sp, seed=1)) @ B.JopStencil(T, n, "fdiff") @ B.JopPointwise(T, n, "square"),
                    B.rand(sp, seed=2))
+elif which == "c4":
+    nb, n, T = 8, 1 << 20, np.float64
+    sp = B.JetSpace(T, n)
+    W = B.rand(B.JetBSpace([sp] * nb), seed=4001)
+    Bd = B.blockop([[B.JopDiagonal(B.getblock(W, i + 1)) if i == j else B.JopZeroBlock(sp, sp) for j in range(nb)] for i in range(nb)])
+    Sd = B.blockop([[B.JopStencil(T, n, "lap") if i == j else B.JopZeroBlock(sp, sp) for j in range(nb)] for i in range(nb)])
+    A = Bd - 0.5 * Sd
 else:
     n = 1_000_000
     sp = B.JetSpace(np.float64, n)
