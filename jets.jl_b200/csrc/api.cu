@@ -265,6 +265,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_BUNDLE_NX")) c.bundle_nx = atoi(v);
     if (const char* v = getenv("JETS_B200_BUNDLE_NS")) c.bundle_ns = atoi(v);
     if (const char* v = getenv("JETS_B200_BUNDLE_BMAX")) c.bundle_bmax = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_PDL")) c.no_pdl = atoi(v);
     c.ready = true;
   });
 }

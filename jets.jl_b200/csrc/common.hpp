@@ -66,6 +66,7 @@ struct Context {
   int bundle_nx = 0;     // JETS_B200_BUNDLE_NX / _NS / _BMAX: override the planner's ring sizes (tuning)
   int bundle_ns = 0;
   int bundle_bmax = 0;
+  int no_pdl = 0;        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
   double* host_scratch = nullptr;  // pinned, 64 doubles
   double* dev_scratch = nullptr;   // device partials for reductions
   size_t dev_scratch_elems = 0;
@@ -214,7 +215,8 @@ enum Pattern : int {
   PAT_DIAG_BDIFF_J2,  // 2 mo .* S'(w .* x)          (config 2 adjoint)
   PAT_LAP_SCALE, PAT_FDIFF_SCALE, PAT_BDIFF_SCALE,   // c .* S(x)   (config 4: B - c*S)
   PAT_J2,             // 2 mo .* x                   (Jacobian of x^2)
-  PAT_SQUARE          // x .* x
+  PAT_SQUARE,         // x .* x
+  PAT_SCALE_LAP, PAT_SCALE_FDIFF, PAT_SCALE_BDIFF    // S(c .* x)   (adjoint of c*S: config 4's A')
 };
 struct GTerm {       // 8 bytes
   uint8_t stage0, nstages;   // into the group's stage pool

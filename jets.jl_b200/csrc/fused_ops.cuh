@@ -198,41 +198,43 @@ struct FastIO2 {
   }
 };
 
-template <typename T>
+// EDGE=false: the tile touches neither end of its block, so no element needs a boundary mask
+// (`first` is false and `last` is past the vector): same arithmetic, fewer selects.
+template <typename T, bool EDGE = true>
 __device__ __forceinline__ void st_fdiff(const T (&x)[VecOf<T>::V], T xr, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const T nx = (j + 1 < V) ? x[(j + 1 < V) ? j + 1 : j] : xr;
-    o[j] = (j < last) ? (nx - x[j]) : T(0);
+    o[j] = (!EDGE || j < last) ? (nx - x[j]) : T(0);
   }
 }
-template <typename T>
+template <typename T, bool EDGE = true>
 __device__ __forceinline__ void st_bdiff(const T (&x)[VecOf<T>::V], T xl, bool first, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const T pv = (j > 0) ? x[(j > 0) ? j - 1 : 0] : xl;
-    const T l = (j > 0 || !first) ? pv : T(0);
-    const T r = (j < last) ? x[j] : T(0);
+    const T l = (!EDGE || j > 0 || !first) ? pv : T(0);
+    const T r = (!EDGE || j < last) ? x[j] : T(0);
     o[j] = l - r;
   }
 }
-template <typename T>
+template <typename T, bool EDGE = true>
 __device__ __forceinline__ void st_lap(const T (&x)[VecOf<T>::V], T xl, T xr, bool first, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
 #pragma unroll
   for (int j = 0; j < V; ++j) {
     const T pv = (j > 0) ? x[(j > 0) ? j - 1 : 0] : xl;
     const T nx = (j + 1 < V) ? x[(j + 1 < V) ? j + 1 : j] : xr;
-    const T l = (j > 0 || !first) ? pv : T(0);
-    const T r = (j < last) ? nx : T(0);
+    const T l = (!EDGE || j > 0 || !first) ? pv : T(0);
+    const T r = (!EDGE || j < last) ? nx : T(0);
     o[j] = (l - T(2) * x[j]) + r;
   }
 }
 
 // Returns false when `pattern` has no fast path (the caller falls back to the interpreter).
-template <typename T, class IO>
+template <typename T, bool EDGE = true, class IO>
 __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStage* stages,
                                           bool first, int last, T (&o)[VecOf<T>::V]) {
   constexpr int V = VecOf<T>::V;
@@ -246,9 +248,9 @@ __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStag
       for (int j = 0; j < V; ++j) o[j] = w[j] * x[j];
       return true;
     }
-    case PAT_FDIFF: io.vec(0, x); st_fdiff<T>(x, io.at(0, V), last, o); return true;
-    case PAT_BDIFF: io.vec(0, x); st_bdiff<T>(x, io.at(0, -1), first, last, o); return true;
-    case PAT_LAP: io.vec(0, x); st_lap<T>(x, io.at(0, -1), io.at(0, V), first, last, o); return true;
+    case PAT_FDIFF: io.vec(0, x); st_fdiff<T, EDGE>(x, io.at(0, V), last, o); return true;
+    case PAT_BDIFF: io.vec(0, x); st_bdiff<T, EDGE>(x, io.at(0, -1), first, last, o); return true;
+    case PAT_LAP: io.vec(0, x); st_lap<T, EDGE>(x, io.at(0, -1), io.at(0, V), first, last, o); return true;
     case PAT_SCALE: {
       const T c = (T)load_stage(stages).c0;
       io.vec(0, x);
@@ -260,11 +262,22 @@ __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStag
       const T c = (T)load_stage(stages + 1).c0;
       T s[V];
       io.vec(0, x);
-      if (pattern == PAT_LAP_SCALE) st_lap<T>(x, io.at(0, -1), io.at(0, V), first, last, s);
-      else if (pattern == PAT_FDIFF_SCALE) st_fdiff<T>(x, io.at(0, V), last, s);
-      else st_bdiff<T>(x, io.at(0, -1), first, last, s);
+      if (pattern == PAT_LAP_SCALE) st_lap<T, EDGE>(x, io.at(0, -1), io.at(0, V), first, last, s);
+      else if (pattern == PAT_FDIFF_SCALE) st_fdiff<T, EDGE>(x, io.at(0, V), last, s);
+      else st_bdiff<T, EDGE>(x, io.at(0, -1), first, last, s);
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] = c * s[j];
+      return true;
+    }
+    case PAT_SCALE_LAP: case PAT_SCALE_FDIFF: case PAT_SCALE_BDIFF: {
+      const T c = (T)load_stage(stages).c0;
+      T y[V];
+      io.vec(0, x);
+#pragma unroll
+      for (int j = 0; j < V; ++j) y[j] = c * x[j];
+      if (pattern == PAT_SCALE_LAP) st_lap<T, EDGE>(y, c * io.at(0, -1), c * io.at(0, V), first, last, o);
+      else if (pattern == PAT_SCALE_FDIFF) st_fdiff<T, EDGE>(y, c * io.at(0, V), last, o);
+      else st_bdiff<T, EDGE>(y, c * io.at(0, -1), first, last, o);
       return true;
     }
     case PAT_J2: {
@@ -286,7 +299,7 @@ __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStag
 #pragma unroll
       for (int j = 0; j < V; ++j) y[j] = (T(2) * m[j]) * x[j];
       const T yr = (T(2) * io.at(1, V)) * io.at(0, V);
-      st_fdiff<T>(y, yr, last, s);
+      st_fdiff<T, EDGE>(y, yr, last, s);
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] = w[j] * s[j];
       return true;
@@ -297,7 +310,7 @@ __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStag
 #pragma unroll
       for (int j = 0; j < V; ++j) y[j] = w[j] * x[j];
       const T yl = io.at(1, -1) * io.at(0, -1);
-      st_bdiff<T>(y, yl, first, last, s);
+      st_bdiff<T, EDGE>(y, yl, first, last, s);
 #pragma unroll
       for (int j = 0; j < V; ++j) o[j] = (T(2) * m[j]) * s[j];
       return true;

@@ -23,6 +23,7 @@
 //                   and the x buffers whose last use this group was, store the row tile once.
 // Tiles have a run-time length (<= the template's capacity) chosen by the planner so that the
 // number of units is a multiple of the grid: no ragged last wave.
+#include <type_traits>
 #include "fused_ops.cuh"
 
 namespace jets {
@@ -105,6 +106,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  // Programmatic dependent launch: the next kernel of the stream may start its own prologue while
+  // this grid drains; this grid's prologue (barrier init, plan-table fetch: immutable data) ran
+  // while the previous grid drained.  Nothing the previous kernel may have written -- or may still
+  // be reading -- is touched before griddepcontrol.wait.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  BundleRec B = P.bundles[0];
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
 
   if (tid >= kConsumers) {
@@ -117,7 +125,6 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     uint32_t par = 0;
     uint32_t xbase = 0;            // x-ring allocations made by this CTA so far
     int b = 0;
-    BundleRec B = P.bundles[0];
     int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
 
     // One lane issues one term group of unit `q` into state slot `my`.
@@ -277,30 +284,36 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       }
-      for (int t = 0; t < nterms; ++t) {
-        const BTerm gt = M.terms[t];
-        FastIO2<T> io;
-        io.stride = kBufBytes;
-        const char* xin = reinterpret_cast<const char*>(xr_p) + (int)gt.xrel * kBufBytes;
-        const char* sst = reinterpret_cast<const char*>(sl_p) + (int)gt.sstream0 * kBufBytes;
+      auto run_terms = [&](auto edge_tag) {
+        constexpr bool EDGE = decltype(edge_tag)::value;
+        for (int t = 0; t < nterms; ++t) {
+          const BTerm gt = M.terms[t];
+          FastIO2<T> io;
+          io.stride = kBufBytes;
+          const char* xin = reinterpret_cast<const char*>(xr_p) + (int)gt.xrel * kBufBytes;
+          const char* sst = reinterpret_cast<const char*>(sl_p) + (int)gt.sstream0 * kBufBytes;
 #pragma unroll
-        for (int i = 0; i < VPT; ++i) {
-          const int e0 = (i * kConsumers + tid) * V;
-          const bool first = (flags & F_BLK0) && e0 == 0;
-          const int last = (flags & F_BLKEND) ? nvalid - 1 - e0 : (1 << 30);
-          T val[V];
-          io.bin = xin + i * kConsumers * 16;
-          io.bst = sst + i * kConsumers * 16;
-          eval_fast<T>(gt.pattern, io, stages + gt.stage0, first, last, val);
-          if (gt.sign >= 0) {
+          for (int i = 0; i < VPT; ++i) {
+            const int e0 = (i * kConsumers + tid) * V;
+            const bool first = EDGE && (flags & F_BLK0) && e0 == 0;
+            const int last = (EDGE && (flags & F_BLKEND)) ? nvalid - 1 - e0 : (1 << 30);
+            T val[V];
+            io.bin = xin + i * kConsumers * 16;
+            io.bst = sst + i * kConsumers * 16;
+            eval_fast<T, EDGE>(gt.pattern, io, stages + gt.stage0, first, last, val);
+            if (gt.sign >= 0) {
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[j];
-          } else {
+              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[j];
+            } else {
 #pragma unroll
-            for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[j];
+              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[j];
+            }
           }
         }
-      }
+      };
+      // interior tiles (neither block end inside the tile) run the mask-free instantiation
+      if (flags & (F_BLK0 | F_BLKEND)) run_terms(std::true_type{});
+      else run_terms(std::false_type{});
       __syncwarp();
       if ((tid & 31) == 0) {
         mbar_arrive(sempty0 + 8 * slot);   // state slot may be refilled
@@ -347,7 +360,17 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
   }
   int64_t grid = ctx().sm_count;
   if (grid > P.nunits) grid = P.nunits > 0 ? P.nunits : 1;
-  jets_fused_bundle_kernel<T, CW, VPT><<<(unsigned)grid, CW * 32 + 32, smem, s>>>(P);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CW * 32 + 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = ctx().no_pdl ? 0 : 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, jets_fused_bundle_kernel<T, CW, VPT>, P));
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }
@@ -357,13 +380,19 @@ void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s) {
   switch (f.variant) {
     case 1: launch_variant<T, 8, 2>(f, P, s); break;
     case 2: launch_variant<T, 16, 2>(f, P, s); break;
+    case 3: launch_variant<T, 8, 4>(f, P, s); break;
+    case 4: launch_variant<T, 30, 1>(f, P, s); break;
+    case 5: launch_variant<T, 24, 1>(f, P, s); break;
     default: launch_variant<T, 16, 1>(f, P, s); break;
   }
 }
 
 }  // namespace
 
-int bundle_buf_bytes(int variant) { return (variant == 2 ? 16384 : 8192) + 2 * kPad; }
+int bundle_buf_bytes(int variant) {
+  static const int tile[6] = {8192, 8192, 16384, 16384, 15360, 12288};   // CW*32*16*VPT of launch_dtype's variants
+  return tile[variant >= 0 && variant < 6 ? variant : 0] + 2 * kPad;
+}
 int bundle_smem_budget() { return kSmemLimit - kHdrAligned; }
 
 void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s) {

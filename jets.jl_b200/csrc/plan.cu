@@ -276,6 +276,11 @@ int classify(const std::vector<FStage>& ch) {
     if (is(0, S_FDIFF)) return PAT_FDIFF_SCALE;
     if (is(0, S_BDIFF)) return PAT_BDIFF_SCALE;
   }
+  if (n == 2 && is(0, S_SCALE)) {
+    if (is(1, S_LAP)) return PAT_SCALE_LAP;
+    if (is(1, S_FDIFF)) return PAT_SCALE_FDIFF;
+    if (is(1, S_BDIFF)) return PAT_SCALE_BDIFF;
+  }
   if (n == 3 && j2(0) && is(1, S_FDIFF) && is(2, S_DIAG)) return PAT_J2_FDIFF_DIAG;
   if (n == 3 && is(0, S_DIAG) && is(1, S_BDIFF) && j2(2)) return PAT_DIAG_BDIFF_J2;
   return PAT_GENERIC;
@@ -355,7 +360,7 @@ struct Builder {
     // config 2 vs 53% / 87% with 8 KB tiles.  Blocks shorter than a few tiles keep 8 KB tiles.
     int variant = ctx().fast_variant;
     (void)max_row_terms; (void)max_term_streams;
-    if (variant < 0 || variant > 2) {
+    if (variant < 0 || variant > 5) {
       int64_t longest = 0;
       for (auto l : out_sp.len) longest = std::max(longest, l);
       variant = (longest * (int64_t)esz >= 4 * 16384) ? 2 : 0;
@@ -685,7 +690,9 @@ struct Builder {
       if (ctx().bundle_nx > 0) nx = std::min(kMaxRing, ctx().bundle_nx);     // tuning / test overrides
       int ns = slot > 0 ? std::min(kMaxRing, (budget - nx * buf) / slot) : kMaxRing;
       if (ctx().bundle_ns > 0) ns = std::min(ns, ctx().bundle_ns);
-      const int need = ctx().bundle_ns > 0 ? 1 : 2;
+      // 16 KB tiles need a state ring at least 3 deep to keep loads in flight while a slot is being
+      // consumed (measured on the 4x4 diagonal shape: 2 slots of 4 streams lose 6% to 8 KB tiles)
+      const int need = ctx().bundle_ns > 0 ? 1 : (v >= 2 ? 3 : 2);
       if (ns < need || nx * buf + ns * slot > budget) continue;
       variant = v; NX = nx; NS = ns;
       break;

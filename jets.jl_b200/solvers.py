@@ -86,55 +86,79 @@ def _axpby(out, sa, ca, af, x, sb=None, cb=0.0, bf=0, y=None):
                              sb.h if sb is not None else None, cb, bf, y._h if y is not None else None))
 
 
-def lsqr_graph(A, b, iters=10):
-    """Same recurrences with every scalar resident on the device; one iteration is captured once
-    in a CUDA graph and replayed ``iters`` times (no host synchronisation inside the loop)."""
-    x = J.zeros(J.domain(A))
-    At = J.adjoint(A)
-    u = b.copy()
-    beta, alpha, rho, rhobar, phibar, phi, theta, c, s, t1, t2 = (_S() for _ in range(11))
-    check(lib.jets_norm_dev(u._h, 2.0, beta.h))
-    _axpby(u, beta, 0.0, L.COEF_INV, u)
-    v = At * u
-    check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
-    _axpby(v, alpha, 0.0, L.COEF_INV, v)
-    w = v.copy()
-    _sop(phibar, "+", beta)      # phibar = beta  (x + 0)
-    _sop(rhobar, "+", alpha)
-    tmp_u = J.zeros(J.range_(A))
-    tmp_v = J.zeros(J.domain(A))
+class LsqrGraph:
+    """Golub-Kahan LSQR with every scalar resident on the device; one iteration is captured once in
+    a CUDA graph and replayed (no host synchronisation inside the loop).  ``LsqrGraph(A, b)`` runs
+    the start-up and the first iteration and captures the graph; ``run(k)`` replays k further
+    iterations asynchronously on the library stream; ``result()`` synchronises."""
 
-    def body():
-        J.mul_(tmp_u, A, v)
-        _axpby(u, None, 1.0, 0, tmp_u, alpha, 0.0, L.COEF_NEG, u)        # u = A v - alpha u
+    def __init__(self, A, b):
+        self.x = x = J.zeros(J.domain(A))
+        At = J.adjoint(A)
+        u = b.copy()
+        beta, alpha, rho, rhobar, phibar, phi, theta, c, s, t1, t2 = (_S() for _ in range(11))
+        self.alpha, self.beta = alpha, beta
         check(lib.jets_norm_dev(u._h, 2.0, beta.h))
         _axpby(u, beta, 0.0, L.COEF_INV, u)
-        J.mul_(tmp_v, At, u)
-        _axpby(v, None, 1.0, 0, tmp_v, beta, 0.0, L.COEF_NEG, v)         # v = A' u - beta v
+        v = At * u
         check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
         _axpby(v, alpha, 0.0, L.COEF_INV, v)
-        _sop(rho, "h", rhobar, beta)
-        _sop(c, "/", rhobar, rho)
-        _sop(s, "/", beta, rho)
-        _sop(theta, "*", s, alpha)
-        _sop(t1, "*", c, alpha)
-        _sop(rhobar, "n", t1)
-        _sop(phi, "*", c, phibar)
-        _sop(phibar, "*", s, phibar)
-        _sop(t1, "/", phi, rho)
-        _sop(t2, "/", theta, rho)
-        _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                        # x += (phi/rho) w
-        _axpby(w, None, 1.0, 0, v, t2, 0.0, L.COEF_NEG, w)               # w = v - (theta/rho) w
+        w = v.copy()
+        _sop(phibar, "+", beta)      # phibar = beta  (x + 0)
+        _sop(rhobar, "+", alpha)
+        tmp_u = J.zeros(J.range_(A))
+        tmp_v = J.zeros(J.domain(A))
+        self._keep = (A, At, u, v, w, tmp_u, tmp_v, rho, rhobar, phibar, phi, theta, c, s, t1, t2)
 
-    body()  # warm-up builds every plan outside the capture
-    check(lib.jets_graph_begin())
-    try:
-        body()
-    finally:
-        g = C.c_void_p()
-        check(lib.jets_graph_end(C.byref(g)))
-    for _ in range(iters - 1):
-        check(lib.jets_graph_launch(g))
-    J.sync()
-    check(lib.jets_graph_destroy(g))
-    return x, (alpha.get(), beta.get())
+        def body():
+            J.mul_(tmp_u, A, v)
+            _axpby(u, None, 1.0, 0, tmp_u, alpha, 0.0, L.COEF_NEG, u)        # u = A v - alpha u
+            check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+            _axpby(u, beta, 0.0, L.COEF_INV, u)
+            J.mul_(tmp_v, At, u)
+            _axpby(v, None, 1.0, 0, tmp_v, beta, 0.0, L.COEF_NEG, v)         # v = A' u - beta v
+            check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+            _axpby(v, alpha, 0.0, L.COEF_INV, v)
+            _sop(rho, "h", rhobar, beta)
+            _sop(c, "/", rhobar, rho)
+            _sop(s, "/", beta, rho)
+            _sop(theta, "*", s, alpha)
+            _sop(t1, "*", c, alpha)
+            _sop(rhobar, "n", t1)
+            _sop(phi, "*", c, phibar)
+            _sop(phibar, "*", s, phibar)
+            _sop(t1, "/", phi, rho)
+            _sop(t2, "/", theta, rho)
+            _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                        # x += (phi/rho) w
+            _axpby(w, None, 1.0, 0, v, t2, 0.0, L.COEF_NEG, w)               # w = v - (theta/rho) w
+
+        body()  # iteration 1; builds every plan outside the capture
+        check(lib.jets_graph_begin())
+        try:
+            body()  # captured, not executed
+        finally:
+            g = C.c_void_p()
+            check(lib.jets_graph_end(C.byref(g)))
+        self._g = g
+
+    def run(self, iters):
+        for _ in range(iters):
+            check(lib.jets_graph_launch(self._g))
+
+    def result(self):
+        J.sync()
+        return self.x, (self.alpha.get(), self.beta.get())
+
+    def __del__(self):
+        try:
+            if self._g:
+                lib.jets_graph_destroy(self._g)
+        except Exception:
+            pass
+
+
+def lsqr_graph(A, b, iters=10):
+    """``iters`` iterations of LsqrGraph; returns (x, (alpha, beta))."""
+    G = LsqrGraph(A, b)
+    G.run(iters - 1)
+    return G.result()

@@ -99,12 +99,15 @@ for name in (sys.argv[1:] or ["c1", "c2", "c4", "c5s"]):
                 B.mul_(s_[4], s_[1], s_[3])
             f_med, f_min = timeit(fwd, steps, 2 * ROT, False)
             t_med, t_min = timeit(adj, steps, 2 * ROT, False)
+            cnt[0] = cnt[1] = 0
+            p_med, p_min = timeit(lambda: (fwd(), adj(), fwd(), adj()), steps, ROT, False)   # 4 dependent launches, no events between
         else:
             f_med, f_min = timeit(lambda: B.mul_(d, A, m), steps, 3, do_flush)
             t_med, t_min = timeit(lambda: B.mul_(m2, At, d), steps, 3, do_flush)
+            p_med, p_min = timeit(lambda: (B.mul_(d, A, m), B.mul_(m2, At, d), B.mul_(d, A, m), B.mul_(m2, At, d)), steps, 3, do_flush)
         lhs, rhs = B.dot_product_test(A, m, B.rand(B.range_(A), seed=8))
         print(json.dumps({"config": name, "engine": eng, "info": B.plan_info(A),
-                          "fwd_ms": round(f_med, 4), "adj_ms": round(t_med, 4), "fwd_min_ms": round(f_min, 4),
+                          "fwd_ms": round(f_med, 4), "adj_ms": round(t_med, 4), "fwd_min_ms": round(f_min, 4), "per_apply_in_4chain_ms": round(p_med / 4, 4), "chain_frac": round(nbytes / (p_med / 4) / 1e6 / PEAK, 4),
                           "fwd_gbs": round(nbytes / f_med / 1e6, 1), "adj_gbs": round(nbytes / t_med / 1e6, 1),
                           "frac": round(nbytes / ((f_med + t_med) / 2) / 1e6 / PEAK, 4),
                           "dpt": float(abs(lhs - rhs) / abs(lhs + rhs)),

@@ -128,7 +128,11 @@ def test_ragged_rows_split_bundles(O, D):
         def blk(r, c):
             if lens[r] != lens[c] or r == 2:
                 return K.JopZeroBlock(K.JetSpace(T, lens[c]), K.JetSpace(T, lens[r]))
-            return K.JopDiagonal(W[(r, c)]) if r != c else 2.5 * K.JopStencil(T, lens[r], "fdiff")
+            if r == c:
+                return 2.5 * K.JopStencil(T, lens[r], "fdiff")
+            if c == r + 1:   # (c*S')' = S o c: scale-then-stencil chains in the adjoint
+                return 0.75 * K.adjoint(K.JopStencil(T, lens[r], "fdiff"))
+            return K.JopDiagonal(W[(r, c)])
         return K.blockop([[blk(r, c) for c in range(nb)] for r in range(nb)])
     both_ways(O, D, build, T, seed=5)
 
@@ -218,6 +222,7 @@ def test_large_rows_many_units(D):
     {"JETS_B200_BUNDLE_NX": "5", "JETS_B200_BUNDLE_NS": "3", "JETS_B200_BUNDLE_BMAX": "3"},
     {"JETS_B200_FAST_VARIANT": "0"},
     {"JETS_B200_FAST_VARIANT": "1", "JETS_B200_BUNDLE_NX": "3"},
+    {"JETS_B200_NO_PDL": "1"},
 ])
 def test_tiny_rings_and_other_tile_shapes(env):
     """Re-runs the scenarios above with ring sizes that force recycling waits, group splits and
