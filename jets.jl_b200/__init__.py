@@ -10,3 +10,4 @@ from .core import *  # noqa: F401,F403
 from .core import (DeviceArray, JetSpace, JetBSpace, JopNl, JopLn, JopAdjoint, Jop)  # noqa: F401
 from . import solvers  # noqa: F401
 from . import dist  # noqa: F401
+from . import pipeline  # noqa: F401

@@ -304,6 +304,7 @@ struct DevFused {   // device copy + launch geometry
   BundleRec* bundles = nullptr;
   int32_t nbundles = 0, NX = 0, NS = 0, G = 1, sstreams = 0;
   int64_t nunits = 0;
+  size_t table_bytes = 0;
   void* blob = nullptr;
 };
 

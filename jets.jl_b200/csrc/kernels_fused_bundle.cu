@@ -51,6 +51,7 @@ struct BundleParams {
   const BundleRec* bundles;
   int32_t nbundles, NX, NS, sstreams, G, tile_elems;
   int64_t nunits;
+  int64_t table_bytes;        // bytes of the plan tables starting at `groups` (prefetch bound)
   const char* in;
   char* out;
   int32_t hl, hr;
@@ -98,12 +99,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   const uint32_t sring0 = xring0 + (uint32_t)NX * kBufBytes;
   const uint32_t slot_bytes = (uint32_t)P.sstreams * kBufBytes;
   const int tid = threadIdx.x;
-  if (tid == 0) {
-    for (int s = 0; s < kMaxRing; ++s) {
-      mbar_init(sfull0 + 8 * s, 1);
-      mbar_init(sempty0 + 8 * s, CW);
-      mbar_init(xempty0 + 8 * s, CW);
-    }
+  if (tid < kMaxRing) {            // 16 threads initialise the three barrier arrays side by side
+    mbar_init(sfull0 + 8 * tid, 1);
+    mbar_init(sempty0 + 8 * tid, CW);
+    mbar_init(xempty0 + 8 * tid, CW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // Programmatic dependent launch: the next kernel of the stream may start its own prologue while
@@ -111,6 +110,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   // while the previous grid drained.  Nothing the previous kernel may have written -- or may still
   // be reading -- is touched before griddepcontrol.wait.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (tid >= kConsumers) {         // warm L2/L1 with the head of the plan tables (first records of the first bundle)
+    const int64_t o = (int64_t)(tid - kConsumers) * 128;
+    if (o < P.table_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.groups) + o));
+  }
   BundleRec B = P.bundles[0];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
@@ -401,6 +404,7 @@ void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out
   P.groups = f.bgroups; P.bundles = f.bundles;
   P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
   P.tile_elems = f.tile_elems; P.nunits = f.nunits;
+  P.table_bytes = (int64_t)f.table_bytes;
   P.in = in; P.out = out; P.hl = f.hl; P.hr = f.hr;
   if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
   else launch_dtype<double>(f, P, s);

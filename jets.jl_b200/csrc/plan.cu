@@ -754,6 +754,7 @@ struct Builder {
     f.blob = blob;
     f.bgroups = reinterpret_cast<BGroupRec*>(blob);
     f.bundles = reinterpret_cast<BundleRec*>(blob + gb);
+    f.table_bytes = host.size();
     plan.engines |= 1 | 32;
     plan.steps.push_back(std::move(st));
     return true;
