@@ -246,13 +246,16 @@ def run_ours(args):
     part, comm = S["part"], S["comm"]
     lib = B.lib
 
-    def fwd():
-        B.dist.forward(B, part, comm, A, S["xext"], S["d"])
+    if world > 1:
+        # halo traffic on an auxiliary stream, overlapped with the interior rows / own columns (dist.py)
+        ov = B.dist.OverlappedBanded(B, part, comm, S["make_block"], S["zero_block"], S["xext"], S["d"], S["mext"], comm.view)
+        fwd, adj = ov.forward, ov.adjoint
+    else:
+        def fwd():
+            B.mul_(S["d"], A, S["xext"])
 
-    def adj():
-        comm_m = comm
-        B.mul_(S["mext"], At, S["d"])
-        comm_m.halo_reduce(S["mext"], part.halo, part.nloc)
+        def adj():
+            B.mul_(S["mext"], At, S["d"])
 
     def barrier():
         torch.cuda.synchronize()
@@ -330,7 +333,7 @@ def run_ours(args):
     if world == 1:
         # block-row chunks pipelined over three streams: upload k | forward k-1, adjoint k-2 | download k-2
         pipe = B.pipeline.ChunkedBandedApply(B, torch, part, S["make_block"], S["zero_block"], S["xext"], S["d"], S["mext"],
-                                             nchunks=16)
+                                             nchunks=64)
         pipe.step(h_in, h_out, stream)
         barrier()
         e0 = pipe.start_event(stream)
@@ -338,7 +341,7 @@ def run_ours(args):
             e1 = pipe.step(h_in, h_out, stream)
         barrier()
         e2e_what = ("pinned host m -> H2D -> d=A*m -> m'=A'*d -> D2H m' through jets_buf_upload_async/jets_apply/"
-                    "jets_buf_download_async, 16 block-row chunks pipelined on 3 streams (jets.jl_b200/pipeline.py)")
+                    "jets_buf_download_async, 64 block-row chunks pipelined on 3 streams (jets.jl_b200/pipeline.py)")
     else:
         def e2e_step():
             B.check(lib.jets_buf_upload_async(S["x_own"]._h, -1, C.c_void_p(h_in.data_ptr()), nloc))

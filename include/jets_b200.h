@@ -72,6 +72,13 @@ const char* jets_last_error(void);
 /* Adopt an external cudaStream_t (e.g. torch's current stream) / read the active one.        */
 int  jets_stream_set(void* cuda_stream);
 void* jets_stream_get(void);
+/* Fork/join onto one of two internal high-priority auxiliary streams, so that a communication call
+ * overlaps the compute calls that follow: fork(a) makes the aux stream wait for everything issued
+ * so far and directs subsequent calls to it; main() directs calls back to the main stream (the aux
+ * work keeps running); join(a) makes the main stream wait for the aux stream.                   */
+int  jets_stream_fork(int aux);
+int  jets_stream_main(void);
+int  jets_stream_join(int aux);
 int  jets_sync(void);
 /* Introspection used by tests and bench: total kernels launched by this library so far.       */
 int64_t jets_launch_count(void);
@@ -234,6 +241,11 @@ int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, j
 /* Adjoint halo reduce: send partial contributions lo/hi to the neighbours and add what they
  * send into the first `nlo` / last `nhi` blocks of x, in rank order.                           */
 int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
+/* The same in two halves, so that the transfer (begin: sends lo/hi, receives the mirror images into
+ * library-owned staging) overlaps the local adjoint apply that writes x; end adds the received
+ * partials into x's first nhi / last nlo blocks, previous rank first (deterministic).           */
+int jets_dist_halo_reduce_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
+int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi);
 /* Dense-structure exchange: all-gather domain shards / reduce-scatter partial domains.         */
 int jets_dist_allgather(jets_buf shard, jets_buf full);
 int jets_dist_reduce_scatter(jets_buf full, jets_buf shard);

@@ -50,6 +50,9 @@ SIGNATURES = {
     "jets_shutdown": (_i, []),
     "jets_last_error": (C.c_char_p, []),
     "jets_stream_set": (_i, [_p]),
+    "jets_stream_fork": (_i, [_i]),
+    "jets_stream_main": (_i, []),
+    "jets_stream_join": (_i, [_i]),
     "jets_stream_get": (_p, []),
     "jets_sync": (_i, []),
     "jets_launch_count": (_i64, []),
@@ -123,6 +126,8 @@ SIGNATURES = {
     "jets_dist_sum_scalar": (_i, [_pd]),
     "jets_dist_halo_exchange": (_i, [_p, _i32, _p, _i32, _p]),
     "jets_dist_halo_reduce": (_i, [_p, _i32, _p, _i32, _p]),
+    "jets_dist_halo_reduce_begin": (_i, [_p, _i32, _p, _i32, _p]),
+    "jets_dist_halo_reduce_end": (_i, [_p, _i32, _i32]),
     "jets_dist_allgather": (_i, [_p, _p]),
     "jets_dist_reduce_scatter": (_i, [_p, _p]),
 }

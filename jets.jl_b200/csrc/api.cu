@@ -266,6 +266,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_BUNDLE_NS")) c.bundle_ns = atoi(v);
     if (const char* v = getenv("JETS_B200_BUNDLE_BMAX")) c.bundle_bmax = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_PDL")) c.no_pdl = atoi(v);
+    if (const char* v = getenv("JETS_B200_STATIC_SCHED")) c.static_sched = atoi(v);
     c.ready = true;
   });
 }
@@ -286,12 +287,49 @@ int jets_stream_set(void* s) {
   return guard([&] {
     require_ready();
     Context& c = ctx();
+    JETS_CHECK(!c.on_aux, JETS_ERR_INVALID, "jets_stream_set while forked onto an auxiliary stream");
     if (c.own_stream && c.stream) { cudaStreamSynchronize(c.stream); cudaStreamDestroy(c.stream); }
     c.stream = reinterpret_cast<cudaStream_t>(s);
     c.own_stream = false;
   });
 }
 void* jets_stream_get(void) { return ctx().stream; }
+int jets_stream_fork(int aux) {
+  return guard([&] {
+    require_ready();
+    Context& c = ctx();
+    JETS_CHECK(aux >= 0 && aux < 2, JETS_ERR_INVALID, "auxiliary stream index must be 0 or 1");
+    if (!c.aux[aux]) {
+      int lo = 0, hi = 0;
+      CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+      CUDA_TRY(cudaStreamCreateWithPriority(&c.aux[aux], cudaStreamNonBlocking, hi));   // hi = greatest priority
+      CUDA_TRY(cudaEventCreateWithFlags(&c.ev_join[aux], cudaEventDisableTiming));
+    }
+    if (!c.ev_fork) CUDA_TRY(cudaEventCreateWithFlags(&c.ev_fork, cudaEventDisableTiming));
+    if (!c.on_aux) c.main_stream = c.stream;
+    CUDA_TRY(cudaEventRecord(c.ev_fork, c.main_stream));
+    CUDA_TRY(cudaStreamWaitEvent(c.aux[aux], c.ev_fork, 0));
+    c.stream = c.aux[aux];
+    c.on_aux = true;
+  });
+}
+int jets_stream_main(void) {
+  return guard([&] {
+    require_ready();
+    Context& c = ctx();
+    if (c.on_aux) { c.stream = c.main_stream; c.on_aux = false; }
+  });
+}
+int jets_stream_join(int aux) {
+  return guard([&] {
+    require_ready();
+    Context& c = ctx();
+    JETS_CHECK(aux >= 0 && aux < 2 && c.aux[aux], JETS_ERR_INVALID, "jets_stream_join(%d) without a fork", aux);
+    if (c.on_aux) { c.stream = c.main_stream; c.on_aux = false; }
+    CUDA_TRY(cudaEventRecord(c.ev_join[aux], c.aux[aux]));
+    CUDA_TRY(cudaStreamWaitEvent(c.stream, c.ev_join[aux], 0));
+  });
+}
 int jets_sync(void) {
   return guard([&] { require_ready(); CUDA_TRY(cudaStreamSynchronize(ctx().stream)); });
 }

@@ -58,6 +58,11 @@ struct Context {
   int sm_count = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  // fork/join onto auxiliary streams (communication overlapped with compute, dist.py)
+  cudaStream_t main_stream = nullptr;   // saved while the context stream is an auxiliary one
+  cudaStream_t aux[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  bool on_aux = false;
   int64_t launches = 0;
   int fused_engine = 0;  // 0 auto, 1 TMA, 2 LDG
   int fast_variant = -1; // JETS_B200_FAST_VARIANT (-1 = chosen per plan): consumer shape of the fast TMA kernel
@@ -66,7 +71,8 @@ struct Context {
   int bundle_nx = 0;     // JETS_B200_BUNDLE_NX / _NS / _BMAX: override the planner's ring sizes (tuning)
   int bundle_ns = 0;
   int bundle_bmax = 0;
-  int no_pdl = 0;        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
+  int no_pdl = 0;
+  int static_sched = 0;  // JETS_B200_STATIC_SCHED=1: deal units round-robin instead of claiming them dynamically        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
   double* host_scratch = nullptr;  // pinned, 64 doubles
   double* dev_scratch = nullptr;   // device partials for reductions
   size_t dev_scratch_elems = 0;
@@ -305,6 +311,8 @@ struct DevFused {   // device copy + launch geometry
   int32_t nbundles = 0, NX = 0, NS = 0, G = 1, sstreams = 0;
   int64_t nunits = 0;
   size_t table_bytes = 0;
+  int32_t* sched = nullptr;   // dynamic unit scheduler counters (in the plan blob) or null
+  int32_t chunk = 1;
   void* blob = nullptr;
 };
 

@@ -187,36 +187,63 @@ int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, j
   });
 }
 
+namespace {
+struct HaloStage { char* from_prev; char* from_next; int64_t n_from_prev, n_from_next; };
+// lo = my partial contribution to the previous rank's last nlo blocks; hi = to the next rank's
+// first nhi blocks.  I receive the mirror images into staging memory.
+HaloStage halo_reduce_xfer(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
+  Dist& d = dist();
+  Context& c = ctx();
+  const int nb = x->nblocks();
+  const int ty = nccl_type(x->dtype);
+  const size_t es = dsize(x->dtype);
+  const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+  HaloStage h;
+  h.n_from_prev = (has_prev && nhi > 0) ? blocks_len(x, 0, nhi) : 0;
+  h.n_from_next = (has_next && nlo > 0) ? blocks_len(x, nb - nlo, nlo) : 0;
+  const size_t need = (size_t)(h.n_from_prev + h.n_from_next) * es + 512;
+  if (need > d.halo_tmp_bytes) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    if (d.halo_tmp) cudaFree(d.halo_tmp);
+    CUDA_TRY(cudaMalloc(&d.halo_tmp, need));
+    d.halo_tmp_bytes = need;
+  }
+  h.from_prev = d.halo_tmp;
+  h.from_next = d.halo_tmp + (((size_t)h.n_from_prev * es + 255) & ~(size_t)255);
+  NCCL_TRY(d.n.GroupStart());
+  if (has_prev && nlo > 0 && lo) NCCL_TRY(d.n.Send(lo->ptr(), (size_t)lo->length(), ty, d.rank - 1, d.comm, c.stream));
+  if (has_next && nhi > 0 && hi) NCCL_TRY(d.n.Send(hi->ptr(), (size_t)hi->length(), ty, d.rank + 1, d.comm, c.stream));
+  if (h.n_from_prev) NCCL_TRY(d.n.Recv(h.from_prev, (size_t)h.n_from_prev, ty, d.rank - 1, d.comm, c.stream));
+  if (h.n_from_next) NCCL_TRY(d.n.Recv(h.from_next, (size_t)h.n_from_next, ty, d.rank + 1, d.comm, c.stream));
+  NCCL_TRY(d.n.GroupEnd());
+  return h;
+}
+void halo_reduce_add(jets_buf x, int32_t nlo, int32_t nhi) {   // previous rank first: deterministic
+  Dist& d = dist();
+  const int nb = x->nblocks();
+  const size_t es = dsize(x->dtype);
+  const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+  const int64_t n_from_prev = (has_prev && nhi > 0) ? blocks_len(x, 0, nhi) : 0;
+  const int64_t n_from_next = (has_next && nlo > 0) ? blocks_len(x, nb - nlo, nlo) : 0;
+  char* from_prev = d.halo_tmp;
+  char* from_next = d.halo_tmp + (((size_t)n_from_prev * es + 255) & ~(size_t)255);
+  if (n_from_prev) add_inplace(x->dtype, x->block_ptr(0), from_prev, n_from_prev, ctx().stream);
+  if (n_from_next) add_inplace(x->dtype, x->block_ptr(nb - nlo), from_next, n_from_next, ctx().stream);
+}
+}  // namespace
+
 int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
   return guard([&] {
     require_ready(); need_dist();
-    Dist& d = dist();
-    Context& c = ctx();
-    const int nb = x->nblocks();
-    const int ty = nccl_type(x->dtype);
-    const size_t es = dsize(x->dtype);
-    const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
-    // lo = my partial contribution to the previous rank's last nlo blocks; hi = to the next rank's
-    // first nhi blocks.  I receive the mirror images and add them, previous rank first.
-    const int64_t n_from_prev = (has_prev && nhi > 0) ? blocks_len(x, 0, nhi) : 0;
-    const int64_t n_from_next = (has_next && nlo > 0) ? blocks_len(x, nb - nlo, nlo) : 0;
-    const size_t need = (size_t)(n_from_prev + n_from_next) * es + 512;
-    if (need > d.halo_tmp_bytes) {
-      if (d.halo_tmp) cudaFree(d.halo_tmp);
-      CUDA_TRY(cudaMalloc(&d.halo_tmp, need));
-      d.halo_tmp_bytes = need;
-    }
-    char* from_prev = d.halo_tmp;
-    char* from_next = d.halo_tmp + (((size_t)n_from_prev * es + 255) & ~(size_t)255);
-    NCCL_TRY(d.n.GroupStart());
-    if (has_prev && nlo > 0 && lo) NCCL_TRY(d.n.Send(lo->ptr(), (size_t)lo->length(), ty, d.rank - 1, d.comm, c.stream));
-    if (has_next && nhi > 0 && hi) NCCL_TRY(d.n.Send(hi->ptr(), (size_t)hi->length(), ty, d.rank + 1, d.comm, c.stream));
-    if (n_from_prev) NCCL_TRY(d.n.Recv(from_prev, (size_t)n_from_prev, ty, d.rank - 1, d.comm, c.stream));
-    if (n_from_next) NCCL_TRY(d.n.Recv(from_next, (size_t)n_from_next, ty, d.rank + 1, d.comm, c.stream));
-    NCCL_TRY(d.n.GroupEnd());
-    if (n_from_prev) add_inplace(x->dtype, x->block_ptr(0), from_prev, n_from_prev, c.stream);
-    if (n_from_next) add_inplace(x->dtype, x->block_ptr(nb - nlo), from_next, n_from_next, c.stream);
+    halo_reduce_xfer(x, nlo, lo, nhi, hi);
+    halo_reduce_add(x, nlo, nhi);
   });
+}
+int jets_dist_halo_reduce_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
+  return guard([&] { require_ready(); need_dist(); halo_reduce_xfer(x, nlo, lo, nhi, hi); });
+}
+int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi) {
+  return guard([&] { require_ready(); need_dist(); halo_reduce_add(x, nlo, nhi); });
 }
 
 int jets_dist_allgather(jets_buf shard, jets_buf full) {

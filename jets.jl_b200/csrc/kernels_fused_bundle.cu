@@ -52,6 +52,8 @@ struct BundleParams {
   int32_t nbundles, NX, NS, sstreams, G, tile_elems;
   int64_t nunits;
   int64_t table_bytes;        // bytes of the plan tables starting at `groups` (prefetch bound)
+  int32_t* sched;             // {next chunk, finished CTAs} or null (static round-robin)
+  int32_t chunk;              // units per claim
   const char* in;
   char* out;
   int32_t hl, hr;
@@ -195,9 +197,35 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
     };
 
-    for (int64_t q = blockIdx.x; q < P.nunits;) {
-      if (q >= unit_end) {  // next bundle (units are enumerated bundle-major; q only grows)
-        int lo = b, hi = P.nbundles - 1;
+    // Units are dealt either statically (unit q = blockIdx.x + k*gridDim.x) or, when the plan carries
+    // a scheduler counter, dynamically in chunks of `chunk` consecutive units claimed with one atomic
+    // (the next claim is issued while the current chunk is processed): CTAs that start late -- SMs
+    // held by a concurrent NCCL kernel, by the previous grid's tail under programmatic launch --
+    // simply take fewer chunks instead of stretching the tail.
+    const bool dyn = P.sched != nullptr;
+    const int64_t stride = dyn ? 1 : (int64_t)gridDim.x;
+    // claim_issue() starts the atomic (lane 0 keeps the ticket in a register); claim_take() broadcasts
+    // it when the next chunk is actually needed, so the atomic's latency hides behind a whole chunk.
+    int ticket = 0;
+    auto claim_issue = [&]() { if (lane == 0) ticket = atomicAdd(P.sched, 1); };
+    auto claim_take = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * P.chunk; };
+    int64_t q = blockIdx.x, q_end = P.nunits;
+    if (dyn) {
+      claim_issue();
+      q = claim_take();
+      q_end = q + P.chunk < P.nunits ? q + P.chunk : P.nunits;
+      claim_issue();
+    }
+    while (true) {
+      if (q >= q_end) {
+        if (!dyn) break;
+        q = claim_take();
+        if (q >= P.nunits) break;
+        q_end = q + P.chunk < P.nunits ? q + P.chunk : P.nunits;
+        claim_issue();
+      }
+      if (q >= unit_end || q < B.unit_begin) {  // another bundle (units are enumerated bundle-major)
+        int lo = 0, hi = P.nbundles - 1;
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
           if (__ldg(&P.bundles[mid].unit_begin) <= q) lo = mid; else hi = mid - 1;
@@ -212,7 +240,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       if (2 * B.ngroups <= G) {
         U = G / B.ngroups;
         if (B.nx > 0 && U > NX / B.nx) U = NX / B.nx;
-        const int64_t mine = (unit_end - 1 - q) / gridDim.x + 1;   // units of this bundle this CTA still owns
+        const int64_t lim = unit_end < q_end ? unit_end : q_end;
+        const int64_t mine = (lim - 1 - q) / stride + 1;   // units of this bundle this CTA still owns
         if (U > mine) U = (int)mine;
         if (U < 1) U = 1;
       }
@@ -223,7 +252,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           int my = slot + lane;
           uint32_t mypar = par;
           if (my >= NS) { my -= NS; mypar ^= 1; }
-          issue(P.groups + B.group_begin + g, q + (int64_t)u * gridDim.x, xbase + (uint32_t)(u * B.nx), my, mypar);
+          issue(P.groups + B.group_begin + g, q + (int64_t)u * stride, xbase + (uint32_t)(u * B.nx), my, mypar);
         }
         slot += n;
         if (slot >= NS) { slot -= NS; par ^= 1; }
@@ -243,7 +272,15 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
       }
       xbase += (uint32_t)(U * B.nx);
-      q += (int64_t)U * gridDim.x;
+      q += (int64_t)U * stride;
+    }
+    if (dyn && lane == 0) {   // the last CTA to run out of work re-arms the counters for the next launch
+      __threadfence();
+      if (atomicAdd(P.sched + 1, 1) == (int)gridDim.x - 1) {
+        P.sched[0] = 0;
+        P.sched[1] = 0;
+        __threadfence();
+      }
     }
     if (lane == 0) {  // end-of-work sentinel
       mbar_wait(sempty0 + 8 * slot, par ^ 1);
@@ -362,7 +399,8 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
     attr_set = true;
   }
   int64_t grid = ctx().sm_count;
-  if (grid > P.nunits) grid = P.nunits > 0 ? P.nunits : 1;
+  const int64_t nclaims = P.sched ? (P.nunits + P.chunk - 1) / P.chunk : P.nunits;
+  if (grid > nclaims) grid = nclaims > 0 ? nclaims : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(CW * 32 + 32);
@@ -405,6 +443,7 @@ void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out
   P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
   P.tile_elems = f.tile_elems; P.nunits = f.nunits;
   P.table_bytes = (int64_t)f.table_bytes;
+  P.sched = f.sched; P.chunk = f.chunk > 0 ? f.chunk : 1;
   P.in = in; P.out = out; P.hl = f.hl; P.hr = f.hr;
   if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
   else launch_dtype<double>(f, P, s);

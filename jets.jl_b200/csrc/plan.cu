@@ -742,11 +742,22 @@ struct Builder {
     f.nunits = unit;
     f.nrows = (int32_t)rows.size();
     f.ntiles = unit;
+    // units per dynamic claim: what the producer can issue side by side for the shortest bundles
+    int chunk = 1;
+    for (const BundleRec& b : sim.bundles)
+      if (2 * b.ngroups <= f.G) {
+        int u = f.G / b.ngroups;
+        if (b.nx > 0) u = std::min(u, NX / b.nx);
+        chunk = std::max(chunk, u);
+      }
+    // ... but keep at least ~8 claims per CTA so that the last wave stays short
+    chunk = (int)std::max<int64_t>(1, std::min<int64_t>(chunk, unit / (8 * (int64_t)grid)));
+    f.chunk = chunk;
     const size_t gb = (sim.groups.size() * sizeof(BGroupRec) + 255) & ~(size_t)255;
-    const size_t bb = sim.bundles.size() * sizeof(BundleRec);
-    std::vector<char> host(gb + bb, 0);
+    const size_t bb = (sim.bundles.size() * sizeof(BundleRec) + 255) & ~(size_t)255;
+    std::vector<char> host(gb + bb + 256, 0);     // tables, then the (zeroed) scheduler counters
     memcpy(host.data(), sim.groups.data(), sim.groups.size() * sizeof(BGroupRec));
-    memcpy(host.data() + gb, sim.bundles.data(), bb);
+    memcpy(host.data() + gb, sim.bundles.data(), sim.bundles.size() * sizeof(BundleRec));
     char* blob = nullptr;
     CUDA_TRY(cudaMalloc(&blob, host.size()));
     CUDA_TRY(cudaMemcpy(blob, host.data(), host.size(), cudaMemcpyHostToDevice));
@@ -754,7 +765,8 @@ struct Builder {
     f.blob = blob;
     f.bgroups = reinterpret_cast<BGroupRec*>(blob);
     f.bundles = reinterpret_cast<BundleRec*>(blob + gb);
-    f.table_bytes = host.size();
+    f.table_bytes = gb + bb;
+    f.sched = (!ctx().static_sched && unit > (int64_t)chunk * grid) ? reinterpret_cast<int32_t*>(blob + gb + bb) : nullptr;
     plan.engines |= 1 | 32;
     plan.steps.push_back(std::move(st));
     return true;

@@ -102,6 +102,86 @@ def adjoint(K, part: RowPartition, comm, A_loc, m_ext, d_loc):
     return m_ext
 
 
+class OverlappedBanded:
+    """The rank-local part of a block-banded operator, split so that the halo traffic overlaps the
+    local compute (the exchange is ~0.2-0.8 ms against ~1 ms of local work at 8 GPUs):
+
+    forward   the halo gather runs on an auxiliary stream while the INTERIOR rows (which read own
+              blocks only) are applied; the `halo` first/last BOUNDARY rows follow once it landed.
+    adjoint   the partial sums for the neighbours' columns (they come from the boundary rows only)
+              are computed first and sent while the OWN columns are computed; the partials
+              received from the neighbours are added last, previous rank first (deterministic).
+
+    Every piece is an ordinary JopBlock over views of ``x_ext`` / ``d`` / ``m_ext``, so each output
+    block is computed by the same row sum as in the monolithic local operator.  ``K`` is the
+    backend (the device package, or a CPU stand-in in the gloo tests); ``comm`` provides ``halo_exchange``,
+    ``halo_reduce_begin/_end`` and the ``fork/main/join`` stream hooks (no-ops on the CPU).
+    """
+
+    def __init__(self, K, part: RowPartition, comm, make_block, zero_block, x_ext, d, m_ext, view):
+        self.K, self.part, self.comm = K, part, comm
+        h, n = part.halo, part.nloc
+        bmap = part.local_block_map()
+        Z = zero_block()
+        cache = {}
+
+        def blk(rc):
+            if rc is None:
+                return Z
+            if rc not in cache:
+                cache[rc] = make_block(*rc)
+            return cache[rc]
+
+        def sub(r0, r1, c0, c1):
+            return K.blockop([[blk(bmap[i][j]) for j in range(c0, c1)] for i in range(r0, r1)])
+        self.x_ext, self.d, self.m_ext = x_ext, d, m_ext
+        lo_i = h if part.has_prev else 0            # interior rows [lo_i, hi_i) read own blocks only
+        hi_i = n - h if part.has_next else n
+        self.f_int = None
+        if hi_i > lo_i:
+            self.f_int = (sub(lo_i, hi_i, lo_i, hi_i + 2 * h), view(d, lo_i, hi_i - lo_i), view(x_ext, lo_i, hi_i - lo_i + 2 * h))
+        self.f_bnd = []
+        if part.has_prev:
+            self.f_bnd.append((sub(0, h, 0, 3 * h), view(d, 0, h), view(x_ext, 0, 3 * h)))
+        if part.has_next:
+            self.f_bnd.append((sub(n - h, n, n - h, n + 2 * h), view(d, n - h, h), view(x_ext, n - h, 3 * h)))
+        # adjoint: partial sums for the neighbours' columns live in the halo blocks of m_ext
+        self.t_halo = []
+        if part.has_prev:       # extended columns [0,h) <- rows [0,h)
+            self.t_halo.append((K.adjoint(sub(0, h, 0, h)), view(m_ext, 0, h), view(d, 0, h)))
+        if part.has_next:       # extended columns [n+h, n+2h) <- rows [n-h, n)
+            self.t_halo.append((K.adjoint(sub(n - h, n, n + h, n + 2 * h)), view(m_ext, n + h, h), view(d, n - h, h)))
+        self.t_own = (K.adjoint(sub(0, n, h, n + h)), view(m_ext, h, n), d)
+
+    def forward(self):
+        """d = (A x)[own rows]; x_ext's own blocks hold x."""
+        K, c, p = self.K, self.comm, self.part
+        c.fork()
+        c.halo_exchange(self.x_ext, p.halo, p.nloc)
+        c.main()
+        if self.f_int is not None:
+            A, dv, xv = self.f_int
+            K.mul_(dv, A, xv)
+        c.join()
+        for A, dv, xv in self.f_bnd:
+            K.mul_(dv, A, xv)
+        return self.d
+
+    def adjoint(self):
+        """m_ext[own] = (A' d)[own columns]."""
+        K, c, p = self.K, self.comm, self.part
+        for At, mv, dv in self.t_halo:
+            K.mul_(mv, At, dv)
+        c.fork()
+        c.halo_reduce_begin(self.m_ext, p.halo, p.nloc)
+        c.main()
+        At, mv, dv = self.t_own
+        K.mul_(mv, At, dv)
+        c.join()
+        c.halo_reduce_end(self.m_ext, p.halo, p.nloc)
+        return self.m_ext
+
+
 class LibComm:
     """NCCL inside libjets_b200.so (device buffers).  ``x_ext`` is a DeviceArray with
     nloc + 2*halo blocks."""
@@ -131,6 +211,33 @@ class LibComm:
             return
         own, lo, hi = self._view(m_ext, h, n), self._view(m_ext, 0, h), self._view(m_ext, h + n, h)
         self.B.check(self.B.lib.jets_dist_halo_reduce(own._h, h, lo._h, h, hi._h))
+
+    def halo_reduce_begin(self, m_ext, h, n):
+        if self.part.world == 1:
+            return
+        own, lo, hi = self._view(m_ext, h, n), self._view(m_ext, 0, h), self._view(m_ext, h + n, h)
+        self.B.check(self.B.lib.jets_dist_halo_reduce_begin(own._h, h, lo._h, h, hi._h))
+
+    def halo_reduce_end(self, m_ext, h, n):
+        if self.part.world == 1:
+            return
+        self.B.check(self.B.lib.jets_dist_halo_reduce_end(self._view(m_ext, h, n)._h, h, h))
+
+    # stream hooks: the transfer goes to an auxiliary high-priority stream of the library
+    def fork(self):
+        if self.part.world > 1:
+            self.B.check(self.B.lib.jets_stream_fork(0))
+
+    def main(self):
+        if self.part.world > 1:
+            self.B.check(self.B.lib.jets_stream_main())
+
+    def join(self):
+        if self.part.world > 1:
+            self.B.check(self.B.lib.jets_stream_join(0))
+
+    def view(self, x, first, n):
+        return self._view(x, first, n)
 
     def own(self, x_ext):
         return self._view(x_ext, self.part.halo, self.part.nloc)

@@ -62,6 +62,38 @@ class GlooComm:
                 blk[k][...] = got[i]
                 i += 1
 
+    # split form used by dist.OverlappedBanded (no streams on the CPU: the hooks are no-ops)
+    def halo_reduce_begin(self, m_ext, h, n):
+        p = self.part
+        blk = m_ext.arrays
+        tdt = torch.from_numpy(blk[0]).dtype
+        sends, recvs = [], []
+        if p.has_prev:
+            sends += [(p.rank - 1, blk[k]) for k in range(h)]
+            recvs += [(p.rank - 1, blk[h + k].shape, tdt) for k in range(h)]
+        if p.has_next:
+            sends += [(p.rank + 1, blk[h + n + k]) for k in range(h)]
+            recvs += [(p.rank + 1, blk[n + k].shape, tdt) for k in range(h)]
+        self._staged = self._xfer(sends, recvs)
+
+    def halo_reduce_end(self, m_ext, h, n):
+        p = self.part
+        blk = m_ext.arrays
+        got, i = self._staged, 0
+        if p.has_prev:
+            for k in range(h):
+                blk[h + k][...] = blk[h + k] + got[i]
+                i += 1
+        if p.has_next:
+            for k in range(h):
+                blk[n + k][...] = blk[n + k] + got[i]
+                i += 1
+
+    def fork(self):
+        pass
+
+    main = join = fork
+
     def halo_reduce(self, m_ext, h, n):
         p = self.part
         blk = m_ext.arrays
@@ -124,6 +156,24 @@ def _worker(rank, world, port, nblk, n, out_dir):
     for k in range(part.nloc):
         dd.arrays[k][...] = d[(part.r0 + k) * n:(part.r0 + k + 1) * n]
     m_ext = D.adjoint(J, part, comm, A, J.zeros(J.domain(A)), dd)
+    # the overlapped decomposition (interior/boundary rows, halo partials first) must give the same bits
+    def view(x, first, cnt):
+        idx, o = [], 0
+        for a in x.arrays[first:first + cnt]:
+            idx.append((o + 1, o + a.size))
+            o += a.size
+        return J.BlockArray(x.arrays[first:first + cnt], idx)
+    x2, d2, m2 = J.zeros(J.domain(A)), J.zeros(J.range_(A)), J.zeros(J.domain(A))
+    for k in range(part.nloc):
+        x2.arrays[1 + k][...] = m[(part.r0 + k) * n:(part.r0 + k + 1) * n]
+    ov = D.OverlappedBanded(J, part, comm, _make_block(J, T, n, W), lambda: J.JopZeroBlock(sp, sp), x2, d2, m2, view)
+    ov.forward()
+    assert np.array_equal(J.to_array(d2), J.to_array(d_loc))
+    for k in range(part.nloc):
+        d2.arrays[k][...] = dd.arrays[k]
+    ov.adjoint()
+    for k in range(part.nloc):
+        assert np.array_equal(m2.arrays[1 + k], m_ext.arrays[1 + k])
     np.save(os.path.join(out_dir, f"f{rank}.npy"), J.to_array(d_loc))
     np.save(os.path.join(out_dir, f"t{rank}.npy"), np.concatenate([m_ext.arrays[1 + k] for k in range(part.nloc)]))
     dist.barrier()
