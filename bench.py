@@ -248,6 +248,8 @@ def run_ours(args):
 
     if world > 1:
         # halo traffic on an auxiliary stream, overlapped with the interior rows / own columns (dist.py)
+        comm.register(S["xext"])     # peer-memory halos: copy engines over NVLink, no SMs
+        comm.register(S["mext"])
         ov = B.dist.OverlappedBanded(B, part, comm, S["make_block"], S["zero_block"], S["xext"], S["d"], S["mext"], comm.view)
         fwd, adj = ov.forward, ov.adjoint
     else:
@@ -385,7 +387,7 @@ def run_ours(args):
         "gpu_launches": int(ln.item()),
         "clocks": clocks,
         "parity": {"dot_product_test_rel": dpt, "tolerance": 1e-5, "checksum": checksum},
-        "engine": B.plan_info(A),
+        "engine": B.plan_info(A if world == 1 else ov.f_int[0]),
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_arm(2, 1)

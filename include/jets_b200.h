@@ -241,6 +241,15 @@ int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, j
 /* Adjoint halo reduce: send partial contributions lo/hi to the neighbours and add what they
  * send into the first `nlo` / last `nhi` blocks of x, in rank order.                           */
 int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
+/* Peer memory: registers the allocation behind x with the neighbouring ranks (CUDA IPC handles
+ * all-gathered over NCCL; collective; every rank must hold the same layout).  Halo calls on a
+ * registered vector move the blocks with the copy engines over NVLink -- they take no SM from the
+ * kernels running meanwhile -- fenced by one tiny all-reduce before and after.                   */
+int jets_dist_register(jets_buf x);
+/* Forward halo gather in two halves: begin starts the transfer (asynchronously to the calls that
+ * follow), end makes the stream wait for it.  Apply the interior rows in between.              */
+int jets_dist_halo_exchange_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
+int jets_dist_halo_exchange_end(void);
 /* The same in two halves, so that the transfer (begin: sends lo/hi, receives the mirror images into
  * library-owned staging) overlaps the local adjoint apply that writes x; end adds the received
  * partials into x's first nhi / last nlo blocks, previous rank first (deterministic).           */

@@ -126,6 +126,9 @@ SIGNATURES = {
     "jets_dist_sum_scalar": (_i, [_pd]),
     "jets_dist_halo_exchange": (_i, [_p, _i32, _p, _i32, _p]),
     "jets_dist_halo_reduce": (_i, [_p, _i32, _p, _i32, _p]),
+    "jets_dist_register": (_i, [_p]),
+    "jets_dist_halo_exchange_begin": (_i, [_p, _i32, _p, _i32, _p]),
+    "jets_dist_halo_exchange_end": (_i, []),
     "jets_dist_halo_reduce_begin": (_i, [_p, _i32, _p, _i32, _p]),
     "jets_dist_halo_reduce_end": (_i, [_p, _i32, _i32]),
     "jets_dist_allgather": (_i, [_p, _p]),

@@ -72,6 +72,7 @@ struct Context {
   int bundle_ns = 0;
   int bundle_bmax = 0;
   int no_pdl = 0;
+  int grid_limit = 0;    // JETS_B200_GRID=n: launch the fused kernels with at most n CTAs (leaves SMs to concurrent kernels)
   int static_sched = 0;  // JETS_B200_STATIC_SCHED=1: deal units round-robin instead of claiming them dynamically        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
   double* host_scratch = nullptr;  // pinned, 64 doubles
   double* dev_scratch = nullptr;   // device partials for reductions

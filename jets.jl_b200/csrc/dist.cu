@@ -3,6 +3,7 @@
 // and (b) inside a process that already loaded torch's bundled libnccl.so.2 the same copy is
 // reused (two NCCL copies in one process would each build their own transport state).
 #include <dlfcn.h>
+#include <map>
 #include "common.hpp"
 
 namespace jets {
@@ -37,6 +38,13 @@ struct Dist {
   double* dev_gather = nullptr;  // [size] doubles
   char* halo_tmp = nullptr;      // receive staging for halo_reduce
   size_t halo_tmp_bytes = 0;
+  // peer memory (CUDA IPC): base pointers of the neighbours' copies of registered allocations
+  struct Peer { void* prev = nullptr; void* next = nullptr; size_t bytes = 0; };
+  std::map<const void*, Peer> peers;   // keyed by the local allocation base
+  cudaStream_t copy[2] = {nullptr, nullptr};          // copy-engine streams (pull from prev / next)
+  cudaEvent_t ev_begin = nullptr, ev_copy[2] = {nullptr, nullptr};
+  float* dev_flag = nullptr;     // 2 floats for the barrier all-reduce
+  bool pending_nccl = false;     // begin() used the NCCL fallback on an auxiliary stream
 };
 Dist& dist() {
   static Dist d;
@@ -104,6 +112,55 @@ __global__ void sum_in_order_kernel(const double* v, int n, double* out) {
 
 int64_t blocks_len(jets_buf x, int first, int n) { return x->blk_off[first + n] - x->blk_off[first]; }
 
+const void* alloc_base(jets_buf x) { return x->st->alloc ? x->st->alloc : (const void*)x->st->data; }
+Dist::Peer* peer_of(jets_buf x) {
+  auto it = dist().peers.find(alloc_base(x));
+  return it == dist().peers.end() ? nullptr : &it->second;
+}
+// Remote twin of a local address inside a registered allocation (all ranks share one layout).
+const char* remote(const void* peer_base, jets_buf x, const char* local_ptr) {
+  return reinterpret_cast<const char*>(peer_base) + (local_ptr - reinterpret_cast<const char*>(alloc_base(x)));
+}
+void ensure_copy_streams() {
+  Dist& d = dist();
+  if (d.copy[0]) return;
+  for (int i = 0; i < 2; ++i) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&d.copy[i], cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&d.ev_copy[i], cudaEventDisableTiming));
+  }
+  CUDA_TRY(cudaEventCreateWithFlags(&d.ev_begin, cudaEventDisableTiming));
+  CUDA_TRY(cudaMalloc(&d.dev_flag, 2 * sizeof(float)));
+  CUDA_TRY(cudaMemset(d.dev_flag, 0, 2 * sizeof(float)));
+}
+// Every rank has reached this point of its stream (and finished everything before it) once the
+// all-reduce completes anywhere: the cross-process fence around peer-memory copies.
+void stream_barrier() {
+  Dist& d = dist();
+  NCCL_TRY(d.n.AllReduce(d.dev_flag, d.dev_flag + 1, 1, ncclFloat32, ncclSum, d.comm, ctx().stream));
+}
+// Copy-engine pulls from the neighbours, ordered after everything on the context stream.
+void pull_begin(char* dst_prev, const char* src_prev, size_t n_prev, char* dst_next, const char* src_next, size_t n_next) {
+  Dist& d = dist();
+  ensure_copy_streams();
+  stream_barrier();
+  CUDA_TRY(cudaEventRecord(d.ev_begin, ctx().stream));
+  if (n_prev) {
+    CUDA_TRY(cudaStreamWaitEvent(d.copy[0], d.ev_begin, 0));
+    CUDA_TRY(cudaMemcpyAsync(dst_prev, src_prev, n_prev, cudaMemcpyDeviceToDevice, d.copy[0]));
+  }
+  if (n_next) {
+    CUDA_TRY(cudaStreamWaitEvent(d.copy[1], d.ev_begin, 0));
+    CUDA_TRY(cudaMemcpyAsync(dst_next, src_next, n_next, cudaMemcpyDeviceToDevice, d.copy[1]));
+  }
+  CUDA_TRY(cudaEventRecord(d.ev_copy[0], d.copy[0]));
+  CUDA_TRY(cudaEventRecord(d.ev_copy[1], d.copy[1]));
+}
+void pull_end() {
+  Dist& d = dist();
+  CUDA_TRY(cudaStreamWaitEvent(ctx().stream, d.ev_copy[0], 0));
+  CUDA_TRY(cudaStreamWaitEvent(ctx().stream, d.ev_copy[1], 0));
+}
+
 }  // namespace
 }  // namespace jets
 
@@ -145,6 +202,11 @@ int jets_dist_shutdown(void) {
     d.n.CommDestroy(d.comm);
     cudaFree(d.dev_gather);
     if (d.halo_tmp) cudaFree(d.halo_tmp);
+    for (auto& kv : d.peers) {
+      if (kv.second.prev) cudaIpcCloseMemHandle(kv.second.prev);
+      if (kv.second.next) cudaIpcCloseMemHandle(kv.second.next);
+    }
+    d.peers.clear();
     d.comm = nullptr; d.ready = false; d.size = 1; d.rank = 0;
     d.halo_tmp = nullptr; d.halo_tmp_bytes = 0;
   });
@@ -239,11 +301,131 @@ int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jet
     halo_reduce_add(x, nlo, nhi);
   });
 }
+// ---- peer-memory registration (CUDA IPC) ------------------------------------------------------
+int jets_dist_register(jets_buf x) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    JETS_CHECK(x && x->st && x->st->alloc, JETS_ERR_INVALID, "jets_dist_register needs a library-owned buffer");
+    const void* base = alloc_base(x);
+    if (d.peers.count(base)) return;
+    cudaIpcMemHandle_t mine;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine, const_cast<void*>(base)));
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    char* dev = nullptr;
+    CUDA_TRY(cudaMalloc(&dev, (size_t)(d.size + 1) * 64));
+    CUDA_TRY(cudaMemcpyAsync(dev + (size_t)d.size * 64, &mine, 64, cudaMemcpyHostToDevice, ctx().stream));
+    NCCL_TRY(d.n.AllGather(dev + (size_t)d.size * 64, dev, 16, ncclFloat32, d.comm, ctx().stream));
+    std::vector<cudaIpcMemHandle_t> all(d.size);
+    CUDA_TRY(cudaMemcpyAsync(all.data(), dev, (size_t)d.size * 64, cudaMemcpyDeviceToHost, ctx().stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+    cudaFree(dev);
+    Dist::Peer p;
+    p.bytes = x->st->bytes;
+    if (d.rank > 0) CUDA_TRY(cudaIpcOpenMemHandle(&p.prev, all[d.rank - 1], cudaIpcMemLazyEnablePeerAccess));
+    if (d.rank + 1 < d.size) CUDA_TRY(cudaIpcOpenMemHandle(&p.next, all[d.rank + 1], cudaIpcMemLazyEnablePeerAccess));
+    d.peers[base] = p;
+  });
+}
+
+// ---- forward halo gather, split so that it overlaps the interior rows ---------------------------
+int jets_dist_halo_exchange_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    Context& c = ctx();
+    const int nb = x->nblocks();
+    const size_t es = dsize(x->dtype);
+    const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+    d.pending_nccl = false;
+    if (Dist::Peer* p = peer_of(x)) {
+      // pull the previous rank's last nlo own blocks and the next rank's first nhi own blocks with the
+      // copy engines over NVLink: no SM is taken from the compute kernel that runs meanwhile
+      const size_t n_prev = (has_prev && nlo > 0 && lo) ? (size_t)lo->length() * es : 0;
+      const size_t n_next = (has_next && nhi > 0 && hi) ? (size_t)hi->length() * es : 0;
+      pull_begin(n_prev ? lo->ptr() : nullptr, n_prev ? remote(p->prev, x, x->block_ptr(nb - nlo)) : nullptr, n_prev,
+                 n_next ? hi->ptr() : nullptr, n_next ? remote(p->next, x, x->block_ptr(0)) : nullptr, n_next);
+      return;
+    }
+    // NCCL fallback on a side stream (serialises with kernels of a different shared-memory carve-out)
+    ensure_copy_streams();
+    CUDA_TRY(cudaEventRecord(d.ev_begin, c.stream));
+    CUDA_TRY(cudaStreamWaitEvent(d.copy[0], d.ev_begin, 0));
+    cudaStream_t keep = c.stream;
+    c.stream = d.copy[0];
+    const int rc = jets_dist_halo_exchange(x, nlo, lo, nhi, hi);
+    c.stream = keep;
+    if (rc != JETS_OK) throw Fail{rc};
+    CUDA_TRY(cudaEventRecord(d.ev_copy[0], d.copy[0]));
+    d.pending_nccl = true;
+  });
+}
+int jets_dist_halo_exchange_end(void) {
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    if (d.pending_nccl) {
+      CUDA_TRY(cudaStreamWaitEvent(ctx().stream, d.ev_copy[0], 0));
+      d.pending_nccl = false;
+      return;
+    }
+    pull_end();
+    stream_barrier();   // nobody may overwrite what a neighbour is still pulling
+  });
+}
+
 int jets_dist_halo_reduce_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
-  return guard([&] { require_ready(); need_dist(); halo_reduce_xfer(x, nlo, lo, nhi, hi); });
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    Context& c = ctx();
+    d.pending_nccl = false;
+    if (Dist::Peer* p = peer_of(x)) {
+      const int nb = x->nblocks();
+      const size_t es = dsize(x->dtype);
+      const bool has_prev = d.rank > 0, has_next = d.rank + 1 < d.size;
+      const int64_t n_from_prev = (has_prev && nhi > 0) ? blocks_len(x, 0, nhi) : 0;
+      const int64_t n_from_next = (has_next && nlo > 0) ? blocks_len(x, nb - nlo, nlo) : 0;
+      const size_t need = (size_t)(n_from_prev + n_from_next) * es + 512;
+      if (need > d.halo_tmp_bytes) {
+        CUDA_TRY(cudaDeviceSynchronize());
+        if (d.halo_tmp) cudaFree(d.halo_tmp);
+        CUDA_TRY(cudaMalloc(&d.halo_tmp, need));
+        d.halo_tmp_bytes = need;
+      }
+      char* from_prev = d.halo_tmp;
+      char* from_next = d.halo_tmp + (((size_t)n_from_prev * es + 255) & ~(size_t)255);
+      JETS_CHECK((!n_from_prev || hi) && (!n_from_next || lo), JETS_ERR_INVALID, "halo views are required on the peer-memory path");
+      // the previous rank's partial for my first blocks sits in ITS hi halo (same offset as mine),
+      // the next rank's partial for my last blocks in ITS lo halo
+      pull_begin(from_prev, n_from_prev ? remote(p->prev, x, hi->ptr()) : nullptr, (size_t)n_from_prev * es,
+                 from_next, n_from_next ? remote(p->next, x, lo->ptr()) : nullptr, (size_t)n_from_next * es);
+      return;
+    }
+    ensure_copy_streams();
+    CUDA_TRY(cudaEventRecord(d.ev_begin, c.stream));
+    CUDA_TRY(cudaStreamWaitEvent(d.copy[0], d.ev_begin, 0));
+    cudaStream_t keep = c.stream;
+    c.stream = d.copy[0];
+    try { halo_reduce_xfer(x, nlo, lo, nhi, hi); } catch (...) { c.stream = keep; throw; }
+    c.stream = keep;
+    CUDA_TRY(cudaEventRecord(d.ev_copy[0], d.copy[0]));
+    d.pending_nccl = true;
+  });
 }
 int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi) {
-  return guard([&] { require_ready(); need_dist(); halo_reduce_add(x, nlo, nhi); });
+  return guard([&] {
+    require_ready(); need_dist();
+    Dist& d = dist();
+    if (d.pending_nccl) {
+      CUDA_TRY(cudaStreamWaitEvent(ctx().stream, d.ev_copy[0], 0));
+      d.pending_nccl = false;
+    } else {
+      pull_end();
+      stream_barrier();
+    }
+    halo_reduce_add(x, nlo, nhi);
+  });
 }
 
 int jets_dist_allgather(jets_buf shard, jets_buf full) {

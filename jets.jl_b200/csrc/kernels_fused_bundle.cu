@@ -399,6 +399,7 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
     attr_set = true;
   }
   int64_t grid = ctx().sm_count;
+  if (ctx().grid_limit > 0 && ctx().grid_limit < grid) grid = ctx().grid_limit;
   const int64_t nclaims = P.sched ? (P.nunits + P.chunk - 1) / P.chunk : P.nunits;
   if (grid > nclaims) grid = nclaims > 0 ? nclaims : 1;
   cudaLaunchConfig_t cfg = {};

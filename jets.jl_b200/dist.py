@@ -114,8 +114,9 @@ class OverlappedBanded:
 
     Every piece is an ordinary JopBlock over views of ``x_ext`` / ``d`` / ``m_ext``, so each output
     block is computed by the same row sum as in the monolithic local operator.  ``K`` is the
-    backend (the device package, or a CPU stand-in in the gloo tests); ``comm`` provides ``halo_exchange``,
-    ``halo_reduce_begin/_end`` and the ``fork/main/join`` stream hooks (no-ops on the CPU).
+    backend (the device package, or a CPU stand-in in the gloo tests); ``comm`` provides
+    ``halo_exchange_begin/_end`` and ``halo_reduce_begin/_end`` (transfers asynchronous to the
+    compute calls issued in between).
     """
 
     def __init__(self, K, part: RowPartition, comm, make_block, zero_block, x_ext, d, m_ext, view):
@@ -156,13 +157,11 @@ class OverlappedBanded:
     def forward(self):
         """d = (A x)[own rows]; x_ext's own blocks hold x."""
         K, c, p = self.K, self.comm, self.part
-        c.fork()
-        c.halo_exchange(self.x_ext, p.halo, p.nloc)
-        c.main()
+        c.halo_exchange_begin(self.x_ext, p.halo, p.nloc)
         if self.f_int is not None:
             A, dv, xv = self.f_int
             K.mul_(dv, A, xv)
-        c.join()
+        c.halo_exchange_end()
         for A, dv, xv in self.f_bnd:
             K.mul_(dv, A, xv)
         return self.d
@@ -172,12 +171,9 @@ class OverlappedBanded:
         K, c, p = self.K, self.comm, self.part
         for At, mv, dv in self.t_halo:
             K.mul_(mv, At, dv)
-        c.fork()
         c.halo_reduce_begin(self.m_ext, p.halo, p.nloc)
-        c.main()
         At, mv, dv = self.t_own
         K.mul_(mv, At, dv)
-        c.join()
         c.halo_reduce_end(self.m_ext, p.halo, p.nloc)
         return self.m_ext
 
@@ -223,18 +219,21 @@ class LibComm:
             return
         self.B.check(self.B.lib.jets_dist_halo_reduce_end(self._view(m_ext, h, n)._h, h, h))
 
-    # stream hooks: the transfer goes to an auxiliary high-priority stream of the library
-    def fork(self):
-        if self.part.world > 1:
-            self.B.check(self.B.lib.jets_stream_fork(0))
+    def halo_exchange_begin(self, x_ext, h, n):
+        if self.part.world == 1:
+            return
+        own, lo, hi = self._view(x_ext, h, n), self._view(x_ext, 0, h), self._view(x_ext, h + n, h)
+        self.B.check(self.B.lib.jets_dist_halo_exchange_begin(own._h, h, lo._h, h, hi._h))
 
-    def main(self):
+    def halo_exchange_end(self):
         if self.part.world > 1:
-            self.B.check(self.B.lib.jets_stream_main())
+            self.B.check(self.B.lib.jets_dist_halo_exchange_end())
 
-    def join(self):
+    def register(self, x_ext):
+        """Collective: map the neighbours' copies of this vector (CUDA IPC) so that its halo traffic
+        goes through the copy engines over NVLink instead of NCCL kernels."""
         if self.part.world > 1:
-            self.B.check(self.B.lib.jets_stream_join(0))
+            self.B.check(self.B.lib.jets_dist_register(x_ext._h))
 
     def view(self, x, first, n):
         return self._view(x, first, n)

@@ -89,10 +89,11 @@ class GlooComm:
                 blk[n + k][...] = blk[n + k] + got[i]
                 i += 1
 
-    def fork(self):
-        pass
+    def halo_exchange_begin(self, x_ext, h, n):
+        self.halo_exchange(x_ext, h, n)
 
-    main = join = fork
+    def halo_exchange_end(self):
+        pass
 
     def halo_reduce(self, m_ext, h, n):
         p = self.part
