@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-(timeout 1200 python -m pytest tests -x -q -m gpu) > gpurun_out/t_all.log 2>&1; tail -4 gpurun_out/t_all.log
-run() { echo "## $*"; env "$@" AB_ROTATE=6 timeout 300 python profiles/ab_bundle.py $CFG 2>&1 | grep '"engine": "auto"' | cut -c1-330; }
-CFG="c5s c1 c4 c2"
-run X=1
-run JETS_B200_STATIC_SCHED=1
+NCU="ncu --set full --clock-control none --import-source on"
+timeout 400 $NCU -k regex:jets_gemm_tc -s 2 -c 2 -o gpurun_out/r01_c3b_tc -f python profiles/prof_dense.py 64 > gpurun_out/prof_c3b.log 2>&1
+tail -2 gpurun_out/prof_c3b.log
+ls -la gpurun_out/*.ncu-rep
