@@ -521,6 +521,34 @@ def extra_workloads(B, torch, stream, peak):
         "algorithmic_bytes_per_iteration": by_iter, "iterations": iters,
         "what": "A*v, A'*u, 2 norms, 4 axpby-class updates per iteration; scalars on device; one CUDA graph per iteration",
         "final_alpha_beta": [a4, b4], "norm_x": nx4, "engine": B.plan_info(A4)}
+    # the same loop with the updates folded into the applies (jets_apply_axpby, LsqrGraphFused): 16 instead of
+    # 24 vector passes per iteration, so the fraction of the PER-PRIMITIVE roofline may exceed 1
+    torch.cuda.synchronize()
+    B.check(B.lib.jets_stream_set(C.c_void_p(s4.cuda_stream)))
+    try:
+        Gf = B.solvers.LsqrGraphFused(A4, rhs4)
+        Gf.run(5)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s4)
+        Gf.run(iters)
+        e1.record(s4)
+        torch.cuda.synchronize()
+        msf = e0.elapsed_time(e1)
+        xf, (af, bf) = Gf.result()
+        nxf = float(B.norm(xf))
+    finally:
+        torch.cuda.synchronize()
+        B.check(B.lib.jets_stream_set(C.c_void_p(stream.cuda_stream)))
+    out["config4_lsqr_200it_fused_updates"] = {
+        "total_ms": round(msf, 3), "us_per_iteration": round(1e3 * msf / iters, 2), "value": round(by_iter * iters / msf / 1e6, 1),
+        "unit": "GB/s (per-primitive algorithmic bytes / time)", "frac_of_per_primitive_roofline": round(by_iter * iters / msf / 1e6 / peak, 4),
+        "bytes_actually_required_per_iteration": 16 * nb * n4 * 8,
+        "frac_of_fused_roofline": round(16 * nb * n4 * 8 * iters / msf / 1e6 / peak, 4),
+        "what": "u, v unnormalised; u = A v/alpha - (alpha/beta) u and v = A'u/beta - (beta/alpha) v each ONE fused apply; "
+                "two scalar programs; > 1.0 of the per-primitive roofline comes from fusion",
+        "final_alpha_beta": [af, bf], "norm_x": nxf, "rel_diff_norm_x_vs_unfused": abs(nxf - nx4) / nx4}
+    del Gf, xf
     del G, A4, Bd, Sd, W4, rhs4, x4
     # config 3a: 64x64 dense 2048x2048 Float32 blocks (64 GiB of matrices generated on device), GEMV
     try:

@@ -142,6 +142,8 @@ int jets_norm_dev(jets_buf x, double p, jets_scalar out);
 /* scalar arithmetic on device: out = a (op) b, op in '+','-','*','/' ; 'n' -> -a ; 's' sqrt(a);
  * 'h' -> hypot(a,b).                                                                           */
 int jets_scalar_op(jets_scalar out, char op, jets_scalar a, jets_scalar b);
+/* n scalar operations in one launch (out[i] = a[i] op[i] b[i], in order; b[i] may be null).     */
+int jets_scalar_prog(int32_t n, const jets_scalar* out, const char* op, const jets_scalar* a, const jets_scalar* b);
 /* out .= (sa? *sa : ca) .* x .+ (sb? *sb : cb) .* y ; a null scalar handle means "use the
  * constant"; negate flags fold a sign; inv flags use the reciprocal (x ./ beta).              */
 int jets_axpby_dev(jets_buf out, jets_scalar sa, double ca, int a_flags, jets_buf x,
@@ -217,6 +219,13 @@ int jets_op_jacobian(jets_op a, jets_buf mo, jets_op* out);
  * (src/Jets.jl:1001,1024).  With accumulate==0 `out` is overwritten, which equals the
  * reference whenever `out` came from zeros(range(A)), i.e. for every `A*m` (:399).              */
 int jets_apply(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate);
+/* out .= cA .* (A in) .+ cO .* out with device-resident coefficients (null scalar = use the
+ * constant; JETS_COEF_* flags as for jets_axpby_dev): the Golub-Kahan updates u = A v - alpha u,
+ * v = A'u - beta v of LSQR/CG (docs/src/index.md:235-246) in ONE pass -- fused into the store
+ * epilogue of the block-apply kernel when the operator is elementwise/stencil, staged through a
+ * temporary otherwise.                                                                          */
+int jets_apply_axpby(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar sa, double ca, int a_flags,
+                     jets_scalar so, double co, int o_flags);
 /* Which engine the last plan for (op,mode) used: bit0 TMA-fused, bit1 LDG-fused, bit2 dense
  * GEMV, bit3 tcgen05 GEMM, bit4 staged through HBM temporaries, bit5 TMA-fused with the
  * shared-memory input-tile cache (rows sharing an input block fetch it once).                   */

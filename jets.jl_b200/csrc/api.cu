@@ -118,7 +118,7 @@ static bool needs_point(jets_op a) {
   return false;
 }
 
-static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate) {
+static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate, const ApplyCoef* coef = nullptr) {
   require_ready();
   check_op(a); check_buf(out); check_buf(in);
   JETS_CHECK(mode >= 0 && mode <= 2, JETS_ERR_INVALID, "bad mode %d", mode);
@@ -142,6 +142,23 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
   else {
     plan = build_plan(a, mode, accumulate, io_ok, engine);
     a->plans[key] = plan;
+  }
+  if (coef) {
+    // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...
+    if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef)) return;
+    // ... else through a temporary owned by the operator (dense / staged plans)
+    const size_t bytes = (size_t)out->length() * dsize(a->dtype);
+    if (!a->axpby_tmp || a->axpby_tmp_bytes < bytes) {
+      if (a->axpby_tmp) { cudaStreamSynchronize(ctx().stream); cudaFree(a->axpby_tmp); }
+      CUDA_TRY(cudaMalloc(&a->axpby_tmp, bytes + 2 * kGuardBytes));
+      a->axpby_tmp_bytes = bytes;
+    }
+    char* tmp = reinterpret_cast<char*>(a->axpby_tmp) + kGuardBytes;
+    // the plan was built for guarded, aligned in/out; the temporary is both
+    run_plan(*plan, a->dtype, in->ptr(), tmp);
+    vec_axpby_dev(a->dtype, out->ptr(), out->length(), coef->a_ptr, coef->a_const, coef->a_flags, tmp, coef->o_ptr,
+                  coef->o_const, coef->o_flags, out->ptr(), ctx().stream);
+    return;
   }
   run_plan(*plan, a->dtype, in->ptr(), out->ptr());
 }
@@ -225,6 +242,7 @@ static jets_op clone_tree(jets_op a) {  // copy(F,false): new nodes, shared (imm
 
 jets_op_s::~jets_op_s() {
   plans.clear();
+  if (axpby_tmp) cudaFree(axpby_tmp);
   if (w && --w->refs == 0) delete w;
   if (mo && --mo->refs == 0) delete mo;
   for (jets_op k : kids)
@@ -883,6 +901,33 @@ int jets_op_jacobian(jets_op a, jets_buf mo, jets_op* out) {
 // ------------------------------------------------------------------ apply ----------------
 int jets_apply(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate) {
   return guard([&] { apply_impl(a, mode, out, in, accumulate); });
+}
+int jets_apply_axpby(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar sa, double ca, int a_flags,
+                     jets_scalar so, double co, int o_flags) {
+  return guard([&] {
+    ApplyCoef c;
+    c.a_ptr = sa ? sa->dev : nullptr; c.a_const = ca; c.a_flags = a_flags;
+    c.o_ptr = so ? so->dev : nullptr; c.o_const = co; c.o_flags = o_flags;
+    apply_impl(a, mode, out, in, 0, &c);
+  });
+}
+int jets_scalar_prog(int32_t n, const jets_scalar* out, const char* op, const jets_scalar* a, const jets_scalar* b) {
+  return guard([&] {
+    require_ready();
+    JETS_CHECK(n >= 0 && out && op && a && b, JETS_ERR_INVALID, "null argument");
+    for (int32_t i0 = 0; i0 < n; i0 += kMaxScalarProg) {
+      ScalarProg p{};
+      p.n = std::min<int32_t>(kMaxScalarProg, n - i0);
+      for (int i = 0; i < p.n; ++i) {
+        JETS_CHECK(out[i0 + i] && a[i0 + i], JETS_ERR_INVALID, "null scalar in program step %d", i0 + i);
+        p.out[i] = out[i0 + i]->dev;
+        p.a[i] = a[i0 + i]->dev;
+        p.b[i] = b[i0 + i] ? b[i0 + i]->dev : nullptr;
+        p.op[i] = op[i0 + i];
+      }
+      scalar_prog(p, ctx().stream);
+    }
+  });
 }
 int jets_op_plan_info(jets_op a, int mode, int32_t* engines, int32_t* nlaunches) {
   return guard([&] {

@@ -157,6 +157,8 @@ struct jets_op_s {
   // plan cache, keyed by mode | accumulate<<2 | engine<<3 ; invalidated when `version` bumps
   uint64_t version = 0;
   std::map<int, std::shared_ptr<jets::Plan>> plans;
+  void* axpby_tmp = nullptr;      // staging of jets_apply_axpby for plans that are not one fused launch
+  size_t axpby_tmp_bytes = 0;
   ~jets_op_s();
 };
 
@@ -314,6 +316,7 @@ struct DevFused {   // device copy + launch geometry
   size_t table_bytes = 0;
   int32_t* sched = nullptr;   // dynamic unit scheduler counters (in the plan blob) or null
   int32_t chunk = 1;
+  bool covers_out = false;    // the launch writes every element of the apply's `out`
   void* blob = nullptr;
 };
 
@@ -372,6 +375,8 @@ struct Plan {
 // plan.cu
 std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
 void run_plan(Plan& p, int dtype, char* in, char* out);
+struct ApplyCoef;
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef);  // false: plan is not one bundle launch
 
 // kernels_fused.cu
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
@@ -383,7 +388,14 @@ void launch_fused_fast(const DevFused& f, int dtype, const char* in, char* out, 
 // kernels_fused_bundle.cu
 int bundle_buf_bytes(int variant);
 int bundle_smem_budget();
-void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
+// out = cA * (A in) + cO * out_old in the store epilogue of the bundle kernel; each coefficient is a
+// device scalar (with JETS_COEF_* flags applied) or a constant.
+struct ApplyCoef {
+  const double* a_ptr = nullptr; double a_const = 1.0; int a_flags = 0;
+  const double* o_ptr = nullptr; double o_const = 0.0; int o_flags = 0;
+};
+void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s,
+                         const ApplyCoef* coef = nullptr);
 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);
@@ -405,6 +417,9 @@ void vec_hadamard(int dtype, void* out, const void* x, const void* y, int64_t n,
 void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, double p,
                 double* dev_out, cudaStream_t s);
 void scalar_op(double* out, char op, const double* a, const double* b, cudaStream_t s);
+constexpr int kMaxScalarProg = 16;
+struct ScalarProg { double* out[kMaxScalarProg]; const double* a[kMaxScalarProg]; const double* b[kMaxScalarProg]; char op[kMaxScalarProg]; int n; };
+void scalar_prog(const ScalarProg& p, cudaStream_t s);
 void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca, int af,
                    const void* x, const double* sb, double cb, int bf, const void* y,
                    cudaStream_t s);

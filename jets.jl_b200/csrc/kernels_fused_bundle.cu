@@ -57,6 +57,8 @@ struct BundleParams {
   const char* in;
   char* out;
   int32_t hl, hr;
+  int32_t axpby;              // store epilogue out = cA*acc + cO*out_old (coefficients below)
+  ApplyCoef coef;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -292,6 +294,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     T acc[VPT][V];
     int slot = 0;
     uint32_t par = 0;
+    T cA = T(1), cO = T(0);
+    if (P.axpby) {   // device scalars of the caller (read after griddepcontrol.wait: a previous kernel may produce them)
+      double a = P.coef.a_ptr ? *P.coef.a_ptr : P.coef.a_const;
+      if (P.coef.a_flags & JETS_COEF_INV) a = 1.0 / a;
+      if (P.coef.a_flags & JETS_COEF_NEG) a = -a;
+      double o = P.coef.o_ptr ? *P.coef.o_ptr : P.coef.o_const;
+      if (P.coef.o_flags & JETS_COEF_INV) o = 1.0 / o;
+      if (P.coef.o_flags & JETS_COEF_NEG) o = -o;
+      cA = (T)a; cO = (T)o;
+    }
     const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
     const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
     while (true) {
@@ -371,13 +383,20 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           if (e0 + V <= nvalid) {
             Vec v;
             T* vs = reinterpret_cast<T*>(&v);
+            if (P.axpby) {
+              const Vec old = *reinterpret_cast<const Vec*>(out_tile + e0);
+              const T* os = reinterpret_cast<const T*>(&old);
 #pragma unroll
-            for (int j = 0; j < V; ++j) vs[j] = acc[i][j];
+              for (int j = 0; j < V; ++j) vs[j] = cA * acc[i][j] + cO * os[j];
+            } else {
+#pragma unroll
+              for (int j = 0; j < V; ++j) vs[j] = acc[i][j];
+            }
             *reinterpret_cast<Vec*>(out_tile + e0) = v;
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
-              if (e0 + j < nvalid) out_tile[e0 + j] = acc[i][j];
+              if (e0 + j < nvalid) out_tile[e0 + j] = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
           }
         }
       }
@@ -437,9 +456,11 @@ int bundle_buf_bytes(int variant) {
 }
 int bundle_smem_budget() { return kSmemLimit - kHdrAligned; }
 
-void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s) {
+void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s, const ApplyCoef* coef) {
   if (f.nbundles == 0 || f.nunits == 0) return;
   BundleParams P;
+  P.axpby = coef ? 1 : 0;
+  if (coef) P.coef = *coef;
   P.groups = f.bgroups; P.bundles = f.bundles;
   P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
   P.tile_elems = f.tile_elems; P.nunits = f.nunits;

@@ -20,7 +20,7 @@
 //               (cp.async.bulk.tensor, evict-first), an 8-deep ring = 128 KB in flight per SM
 //   warp 9      X producer: one box of the pre-split right-hand sides [x_hi | x_lo] per stage
 //               (evict-last: every tile re-reads them from L2), a 4-deep ring
-//   warps 4-7   read the landed A tile ONCE from shared memory, one matrix row per thread, split it
+//   warps 4-7, 12-15   read the landed A tile ONCE from shared memory, one matrix row (half a stage's k) per thread, split it
 //               and write a_hi / a_lo straight into TENSOR MEMORY (tcgen05.st): the MMA takes its A
 //               operand from TMEM, so shared memory carries the matrix bytes exactly twice
 //               (TMA write + this read) instead of ~8x with hi/lo copies in shared memory
@@ -40,13 +40,14 @@ namespace {
 
 constexpr int BM = 128;            // output rows per tile (= TMEM lanes)
 constexpr int BK = 32;             // k per stage
-constexpr int kAStages = 8;        // matrix ring (HBM latency)
-constexpr int kXStages = 4;        // right-hand-side ring == TMEM operand ring
+constexpr int kAStages = 8;        // matrix ring (HBM latency: 128 KB in flight per SM)
+constexpr int kXStages = 4;        // right-hand-side ring (measured: 6 matrix + 8 right-hand-side stages is 9% slower)
+constexpr int kTStages = 4;        // TMEM operand ring (hi|lo slots of 64 columns), own barriers
 constexpr int kABytes = BM * BK * 4;           // 16 KB
 constexpr int kXBytes = 128 * BK * 4;          // 2*NP rows of 128 B, NP <= 64
 constexpr int kDrainStages = 8;    // TMEM accumulation length (256 k) before folding into registers
-constexpr int kThreads = 352;      // 11 warps
-constexpr int kTmemCols = 512;     // [0,256): 2 accumulator buffers x (main | correction) x 64; [256,512): 4 A slots x (hi | lo) x 32
+constexpr int kThreads = 512;      // 16 warps: 0-3 epilogue, 4-7 + 12-15 split, 8 A producer, 9 X producer, 10 MMA
+constexpr int kTmemCols = 512;     // [0,256): 2 accumulator buffers x (main | correction) x 64; [256,512): kTStages A slots x (hi | lo) x 32
 constexpr int kBufCols = 128;
 constexpr int kASlotCol = 256;
 constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kXStages * kXBytes + 512;
@@ -62,6 +63,7 @@ struct TcParams {
   int32_t nrhs, n0;           // right-hand sides handled by this launch: [n0, n0+nrhs)
   int32_t trans, acc;
   float* out;
+  int32_t expt;               // JETS_B200_TC_EXPT: 1 = skip the a_lo MMAs, 2 = skip all MMAs (timing experiments only)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +101,41 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, u
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
       "}" ::"r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// One k-stage (BK = 32 = four tf32 k-steps) of the split product in ONE asm block:
+//   D_main|corr (+)= a_hi x [x_hi | x_lo]   and   D_corr += a_lo x x_hi   for each k-step.
+// A k-step advances the TMEM operand by 8 columns and the shared-memory descriptor by 32 bytes
+// (start-address field += 2).  The issuing thread is the pipeline's narrowest point (ncu: ~155
+// single-lane instructions per stage with one asm block per MMA, ~900 cycles, while the tensor
+// pipe needs 384), so everything loop-invariant is folded into this block's immediates.
+__device__ __forceinline__ void umma_stage_tf32(uint32_t d_main, uint32_t d_corr, uint32_t a_hi, uint32_t a_lo, uint64_t xdesc,
+                                                uint32_t idesc_main, uint32_t idesc_corr, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .b64 x1, x2, x3;\n\t"
+      ".reg .b32 h1, h2, h3, l1, l2, l3;\n\t"
+      "setp.ne.b32 p0, %7, 0;\n\t"
+      "setp.ne.b32 p1, %5, 0;\n\t"          // always true (an instruction descriptor is never 0)
+      "add.s64 x1, %4, 2;\n\t"
+      "add.s64 x2, %4, 4;\n\t"
+      "add.s64 x3, %4, 6;\n\t"
+      "add.u32 h1, %2, 8;\n\t"
+      "add.u32 h2, %2, 16;\n\t"
+      "add.u32 h3, %2, 24;\n\t"
+      "add.u32 l1, %3, 8;\n\t"
+      "add.u32 l2, %3, 16;\n\t"
+      "add.u32 l3, %3, 24;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%2], %4, %5, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%1], [%3], %4, %6, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h1], x1, %5, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%1], [l1], x1, %6, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h2], x2, %5, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%1], [l2], x2, %6, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h3], x3, %5, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%1], [l3], x3, %6, p1;\n\t"
+      "}" ::"r"(d_main), "r"(d_corr), "r"(a_hi), "r"(a_lo), "l"(xdesc), "r"(idesc_main), "r"(idesc_corr), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -108,6 +145,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
       : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]) : "memory");
 }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -147,19 +190,22 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
   unsigned char* sbase = smem_raw + (base - raw);
   const uint32_t a0 = base, x0 = base + kAStages * kABytes;
   const uint32_t bars = x0 + kXStages * kXBytes;
-  const uint32_t a_full0 = bars, a_empty0 = bars + 64, x_full0 = bars + 128, t_ready0 = bars + 160, mma_done0 = bars + 192,
-                 acc_full0 = bars + 224, acc_empty0 = bars + 240;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAStages * kABytes + kXStages * kXBytes + 256);
+  const uint32_t a_full0 = bars, a_empty0 = bars + 64, x_full0 = bars + 128, x_empty0 = bars + 192, t_ready0 = bars + 256,
+                 mma_done0 = bars + 288, acc_full0 = bars + 320, acc_empty0 = bars + 336;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAStages * kABytes + kXStages * kXBytes + 384);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(a_full0 + 8 * s, 1);
-      mbar_init(a_empty0 + 8 * s, 4);
+      mbar_init(a_empty0 + 8 * s, 8);
     }
     for (int s = 0; s < kXStages; ++s) {
       mbar_init(x_full0 + 8 * s, 1);
-      mbar_init(t_ready0 + 8 * s, 4);
+      mbar_init(x_empty0 + 8 * s, 1);
+    }
+    for (int s = 0; s < kTStages; ++s) {
+      mbar_init(t_ready0 + 8 * s, 8);
       mbar_init(mma_done0 + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -225,7 +271,7 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
           const int koff = P.koff[e];
           for (int kc = 0; kc < nk; ++kc, ++it) {
             const int s = it % kXStages;
-            mbar_wait(mma_done0 + 8 * s, ((it / kXStages) & 1) ^ 1);
+            mbar_wait(x_empty0 + 8 * s, ((it / kXStages) & 1) ^ 1);
             mbar_expect_tx(x_full0 + 8 * s, xbytes);
             tma_2d(x0 + s * kXBytes, &xmap, koff + kc * BK, 0, x_full0 + 8 * s, pol);
           }
@@ -236,6 +282,7 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
     // =============================== MMA issuer =================================
     const uint32_t idesc_main = make_idesc(2 * np);   // a_hi x [x_hi | x_lo]
     const uint32_t idesc_corr = make_idesc(np);       // a_lo x x_hi
+    const uint64_t xdesc0 = make_desc_k128(x0);       // X slot s: start-address field += s * kXBytes / 16
     uint32_t it = 0, cn = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const int g = find_group(P.tile_ptr, P.ngroups, tile);
@@ -251,21 +298,22 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
           // columns [np,2np): a_hi*x_lo + a_lo*x_hi (2^-11 smaller, so its rounding does not matter)
           const uint32_t d_tmem = tmem_base + buf * kBufCols;
           for (int kc = c0; kc < c1; ++kc, ++it) {
-            const int s = it % kXStages;
-            const uint32_t ph = (it / kXStages) & 1;
-            mbar_wait(x_full0 + 8 * s, ph);
-            mbar_wait(t_ready0 + 8 * s, ph);
+            const int s = it % kXStages, t = it % kTStages;
+            mbar_wait(x_full0 + 8 * s, (it / kXStages) & 1);
+            mbar_wait(t_ready0 + 8 * t, (it / kTStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (lane == 0) {
-              const uint32_t xs = x0 + s * kXBytes;
-              const uint32_t a_hi = tmem_base + kASlotCol + s * 64, a_lo = a_hi + 32;
+              const uint32_t a_hi = tmem_base + kASlotCol + t * 64;
+              if (P.expt == 0)
+                umma_stage_tf32(d_tmem, d_tmem + np, a_hi, a_hi + 32, xdesc0 + (uint64_t)(s * (kXBytes >> 4)), idesc_main, idesc_corr,
+                                kc > c0 ? 1u : 0u);
+              else if (P.expt == 1) {
 #pragma unroll
-              for (int ks = 0; ks < BK / 8; ++ks) {
-                const uint64_t x_all = make_desc_k128(xs + ks * 32);   // a k-step advances 32 bytes inside the 128-byte row
-                umma_tf32_ts(d_tmem, a_hi + ks * 8, x_all, idesc_main, (kc > c0 || ks > 0) ? 1u : 0u);
-                umma_tf32_ts(d_tmem + np, a_lo + ks * 8, x_all, idesc_corr, 1u);
+                for (int ks = 0; ks < 4; ++ks)
+                  umma_tf32_ts(d_tmem, a_hi + ks * 8, xdesc0 + (uint64_t)(s * (kXBytes >> 4) + 2 * ks), idesc_main, (kc > c0 || ks > 0) ? 1u : 0u);
               }
-              umma_commit(mma_done0 + 8 * s);                      // X slot and TMEM operand slot are free once the MMAs retire
+              umma_commit(x_empty0 + 8 * s);                       // right-hand-side slot free once the MMAs retire
+              umma_commit(mma_done0 + 8 * t);                      // TMEM operand slot likewise
               if (kc + 1 == c1) umma_commit(acc_full0 + 8 * buf);  // accumulator chunk complete
             }
             __syncwarp();
@@ -273,9 +321,12 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         }
       }
     }
-  } else if (warp >= 4) {
-    // =============================== split A into TMEM (warps 4-7) ==============
-    const int q = warp - 4;                 // TMEM lane quarter == 32-row box of the tile
+  } else if (warp >= 4 && warp != 11) {
+    // =============================== split A into TMEM (warps 4-7 and 12-15) =====
+    // Two warps per TMEM lane quarter: warps 4-7 take k columns [0,16) of the stage, warps 12-15
+    // columns [16,32) -- one warp per quarter could not split a stage as fast as HBM delivers it.
+    const int q = warp & 3;                 // TMEM lane quarter == 32-row box of the tile
+    const int half = warp >= 12 ? 1 : 0;    // which 16 of the stage's 32 k columns
     const int r = q * 32 + lane;            // this thread's tile row
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     uint32_t it = 0;
@@ -285,37 +336,37 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         const int kdim = P.trans ? P.blocks[e].rows : P.blocks[e].cols;
         const int nk = (kdim + BK - 1) / BK;
         for (int kc = 0; kc < nk; ++kc, ++it) {
-          const int sa = it % kAStages, st = it % kXStages;
+          const int sa = it % kAStages, st = it % kTStages;
           mbar_wait(a_full0 + 8 * sa, (it / kAStages) & 1);
-          uint32_t hi[32], lo[32];
+          uint32_t hi[16], lo[16];
           const unsigned char* tile_p = sbase + (size_t)sa * kABytes;
           if (P.trans) {
             // [col][32 k], 128B swizzle: 16-byte chunk c of row r sits at chunk (c ^ (r & 7))
             const uint4* row = reinterpret_cast<const uint4*>(tile_p + r * 128);
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const uint4 v = row[c ^ (r & 7)];
+            for (int c = 0; c < 4; ++c) {
+              const uint4 v = row[(4 * half + c) ^ (r & 7)];
               hi[4 * c + 0] = v.x; hi[4 * c + 1] = v.y; hi[4 * c + 2] = v.z; hi[4 * c + 3] = v.w;
             }
           } else {
             // [k][32 rows] per 32-row box, no swizzle: the warp reads one 128-byte line per k
-            const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_p + q * 4096) + lane;
+            const uint32_t* col = reinterpret_cast<const uint32_t*>(tile_p + q * 4096) + lane + half * 16 * 32;
 #pragma unroll
-            for (int k = 0; k < 32; ++k) hi[k] = col[k * 32];
+            for (int k = 0; k < 16; ++k) hi[k] = col[k * 32];
           }
 #pragma unroll
-          for (int k = 0; k < 32; ++k) {
+          for (int k = 0; k < 16; ++k) {
             const uint32_t a = hi[k];
             hi[k] = a & 0xFFFFE000u;
             lo[k] = __float_as_uint(__uint_as_float(a) - __uint_as_float(hi[k])) & 0xFFFFE000u;
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(a_empty0 + 8 * sa);            // the shared-memory slot can be refilled
-          mbar_wait(mma_done0 + 8 * st, ((it / kXStages) & 1) ^ 1);  // TMEM operand slot free (MMAs of it-4 retired)
+          mbar_wait(mma_done0 + 8 * st, ((it / kTStages) & 1) ^ 1);  // TMEM operand slot free (MMAs of it-4 retired)
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t taddr = tmem_base + lane_addr + kASlotCol + st * 64;
-          tmem_st32(taddr, hi);
-          tmem_st32(taddr + 32, lo);
+          const uint32_t taddr = tmem_base + lane_addr + kASlotCol + st * 64 + half * 16;
+          tmem_st16(taddr, hi);
+          tmem_st16(taddr + 32, lo);
           asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           __syncwarp();
@@ -323,6 +374,8 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         }
       }
     }
+  } else if (warp == 11) {
+    // idle
   } else {
     // =============================== epilogue (warps 0-3) =======================
     float acc[64];
@@ -551,6 +604,7 @@ void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
     P.trans = st.dblocks[0].trans;
     P.acc = st.acc;
     P.out = reinterpret_cast<float*>(out);
+    { const char* e = getenv("JETS_B200_TC_EXPT"); P.expt = e ? atoi(e) : 0; }
     const int grid = (int)std::min<int64_t>(st.gemv_tiles, ctx().sm_count);
     CUtensorMap xmap;
     memcpy(&xmap, st.tc_xmap, sizeof(xmap));

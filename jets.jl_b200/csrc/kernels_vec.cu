@@ -367,6 +367,26 @@ void reduce_dispatch(int kind, const void* x, const void* y, int64_t n, double p
   }
 }
 
+__device__ __forceinline__ double scalar_eval(char op, double x, double y) {
+  switch (op) {
+    case '+': return x + y;
+    case '-': return x - y;
+    case '*': return x * y;
+    case '/': return x / y;
+    case 'n': return -x;
+    case 's': return sqrt(x);
+    case 'h': return sqrt(x * x + y * y);
+    default: return x;
+  }
+}
+// A short straight-line program of scalar operations in ONE launch (the scalar recurrences of a
+// CG/LSQR iteration); operations see the results of the ones before them.
+__global__ void scalar_prog_kernel(const ScalarProg p) {
+  for (int i = 0; i < p.n; ++i) {
+    const double x = p.a[i] ? *p.a[i] : 0.0, y = p.b[i] ? *p.b[i] : 0.0;
+    *p.out[i] = scalar_eval(p.op[i], x, y);
+  }
+}
 __global__ void scalar_op_kernel(double* out, char op, const double* a, const double* b) {
   const double x = a ? *a : 0.0, y = b ? *b : 0.0;
   double r;
@@ -456,6 +476,12 @@ void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, do
   else reduce_dispatch<double>(kind, x, y, n, p, dev_out, s);
 }
 
+void scalar_prog(const ScalarProg& p, cudaStream_t s) {
+  if (p.n <= 0) return;
+  scalar_prog_kernel<<<1, 1, 0, s>>>(p);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
 void scalar_op(double* out, char op, const double* a, const double* b, cudaStream_t s) {
   scalar_op_kernel<<<1, 1, 0, s>>>(out, op, a, b);
   CUDA_TRY(cudaGetLastError());

@@ -742,6 +742,7 @@ struct Builder {
     f.nunits = unit;
     f.nrows = (int32_t)rows.size();
     f.ntiles = unit;
+    f.covers_out = dst.off == 0;   // every non-empty output row is written by this launch (ACC_SET keeps term-less rows)
     // units per dynamic claim: what the producer can issue side by side for the shortest bundles
     int chunk = 1;
     for (const BundleRec& b : sim.bundles)
@@ -1047,6 +1048,18 @@ std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok
   b.lower(a, mode, Ref{1, 0}, Ref{0, 0}, acc);
   plan->version = g_epoch;
   return plan;
+}
+
+// out = cA*(A in) + cO*out fused into the store epilogue when the whole apply is ONE bundle launch
+// that writes every output row (otherwise the caller stages through a temporary).
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef) {
+  if (p.steps.size() != 1) return false;
+  Step& st = p.steps[0];
+  if (st.kind != ST_FUSED || !st.fused.bundle || st.acc != ACC_SET || st.src.which != 0 || st.dst.which != 1 ||
+      !st.fused.covers_out)
+    return false;
+  launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
+  return true;
 }
 
 void run_plan(Plan& p, int dtype, char* in, char* out) {

@@ -157,6 +157,71 @@ class LsqrGraph:
             pass
 
 
+def _apply_axpby(out, A, x, sa, ca, af, so, co, of):
+    """out = cA*(A x) + cO*out with device-resident coefficients (jets_apply_axpby)."""
+    check(lib.jets_apply_axpby(A._h.h, A._mode, out._h, x._h, sa.h if sa is not None else None, ca, af,
+                               so.h if so is not None else None, co, of))
+
+
+def _sprog(steps):
+    """[(out, op, a, b|None), ...] scalar operations in ONE launch (jets_scalar_prog)."""
+    n = len(steps)
+    arr = C.c_void_p * n
+    outs = arr(*[st[0].h.value for st in steps])
+    a = arr(*[st[2].h.value for st in steps])
+    b = arr(*[(st[3].h.value if st[3] is not None else None) for st in steps])
+    ops = "".join(st[1] for st in steps).encode()
+    check(lib.jets_scalar_prog(n, outs, ops, a, b))
+
+
+class LsqrGraphFused(LsqrGraph):
+    """The same Golub-Kahan LSQR with the vector updates folded into the applies: u and v are kept
+    UNNORMALISED (u~ = beta*u, v~ = alpha*v) so that
+
+        u~ <- (1/alpha) A v~  - (alpha/beta) u~        one fused apply (reads v~, state, u~; writes u~)
+        v~ <- (1/beta') A'u~  - (beta'/alpha) v~       one fused apply
+
+    replace apply + axpy + scale (9 -> 4 vector passes per half iteration), the scalar recurrences
+    run as two scalar programs, and the normalisations are folded into the coefficients of the
+    x / w updates.  Same iterates as ``LsqrGraph`` up to rounding."""
+
+    def __init__(self, A, b):
+        self.x = x = J.zeros(J.domain(A))
+        At = J.adjoint(A)
+        u = b.copy()
+        (beta, alpha, rho, rhobar, phibar, phi, theta, c, s, t, t1, t2, tab, tba) = (_S() for _ in range(14))
+        self.alpha, self.beta = alpha, beta
+        check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+        v = J.zeros(J.domain(A))
+        _apply_axpby(v, At, u, beta, 0.0, L.COEF_INV, None, 0.0, 0)          # v~ = (1/beta) A' u~
+        check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+        w = J.zeros(J.domain(A))
+        _axpby(w, alpha, 0.0, L.COEF_INV, v)                                   # w = v~ / alpha
+        _sprog([(phibar, "+", beta, None), (rhobar, "+", alpha, None), (tab, "/", alpha, beta)])
+        self._keep = (A, At, u, v, w, rho, rhobar, phibar, phi, theta, c, s, t, t1, t2, tab, tba)
+
+        def body():
+            _apply_axpby(u, A, v, alpha, 0.0, L.COEF_INV, tab, 0.0, L.COEF_NEG)    # u~ = A v~/alpha - (alpha/beta) u~
+            check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+            _sprog([(tba, "/", beta, alpha)])
+            _apply_axpby(v, At, u, beta, 0.0, L.COEF_INV, tba, 0.0, L.COEF_NEG)   # v~ = A'u~/beta - (beta/alpha) v~
+            check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+            _sprog([(rho, "h", rhobar, beta), (c, "/", rhobar, rho), (s, "/", beta, rho), (theta, "*", s, alpha),
+                    (t, "*", c, alpha), (rhobar, "n", t, None), (phi, "*", c, phibar), (phibar, "*", s, phibar),
+                    (t1, "/", phi, rho), (t2, "/", theta, rho), (tab, "/", alpha, beta)])
+            _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                             # x += (phi/rho) w
+            _axpby(w, alpha, 0.0, L.COEF_INV, v, t2, 0.0, L.COEF_NEG, w)          # w = v~/alpha - (theta/rho) w
+
+        body()  # iteration 1; builds every plan outside the capture
+        check(lib.jets_graph_begin())
+        try:
+            body()
+        finally:
+            g = C.c_void_p()
+            check(lib.jets_graph_end(C.byref(g)))
+        self._g = g
+
+
 def lsqr_graph(A, b, iters=10):
     """``iters`` iterations of LsqrGraph; returns (x, (alpha, beta))."""
     G = LsqrGraph(A, b)

@@ -28,4 +28,5 @@ for c in per.values():
 print("by reason:", [(k, v) for k, v in agg.most_common(8)])
 for key, c in sorted(per.items(), key=lambda kv: -kv[1]["_all"])[:topn]:
     st = ", ".join(f"{k[6:]}={v}" for k, v in c.most_common(6) if k.startswith("stall_"))
+    if key is None: continue
     print(f"{100*c['_all']/tot:5.1f}% inst={c['_inst']:>9} L{key[1]:>4} {src.get(key,'').strip()[:78]:78} | {st}")

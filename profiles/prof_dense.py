@@ -14,8 +14,18 @@ A = B.blockop([[B.JopDense(B.getblock(mats, 1 + r + nb * c), nrhs=nrhs) for c in
 m = B.rand(B.domain(A), seed=3)
 d = B.zeros(B.range_(A))
 m2 = B.zeros(B.domain(A))
+import time
+At = A.T
 for _ in range(3):
     B.mul_(d, A, m)
-    B.mul_(m2, A.T, d)
+    B.mul_(m2, At, d)
 B.sync()
+for nm, fn in (("fwd", lambda: B.mul_(d, A, m)), ("adj", lambda: B.mul_(m2, At, d))):
+    B.sync()
+    t0 = time.perf_counter()
+    for _ in range(10):
+        fn()
+    B.sync()
+    ms = (time.perf_counter() - t0) * 100
+    print(f"dense nrhs={nrhs} {nm}: {ms:.3f} ms  {nb * nb * k * k * 4 / ms / 1e6:.0f} GB/s of matrix bytes")
 print("dense", nrhs, B.plan_info(A))

@@ -724,3 +724,55 @@ def test_lsqr_loop_config4(O, D):
     assert abs(ag - ho[-1][0]) <= 1e-10 * abs(ag)
     info = D.B.plan_info(Ad)
     assert info["engines"] == ["tma"] and info["launches"] == 1  # sum + blocks fused into one launch
+
+
+def test_lsqr_fused_updates_config4(O, D):
+    """LsqrGraphFused (u, v kept unnormalised, updates folded into the applies through
+    jets_apply_axpby, scalar recurrences in two scalar programs) reproduces the oracle's LSQR."""
+    T = np.float64
+    nb, n = 4, 4096
+    g = np.random.default_rng(19)
+    W = [1.0 + g.random(n) for _ in range(nb)]
+    rhs = g.random(nb * n)
+
+    def build(K):
+        sp = K.JetSpace(T, n)
+        Bd = K.blockop([[K.JopDiagonal(W[i]) if i == j else K.JopZeroBlock(sp, sp) for j in range(nb)] for i in range(nb)])
+        Sd = K.blockop([[K.JopStencil(T, n, "lap") if i == j else K.JopZeroBlock(sp, sp) for j in range(nb)] for i in range(nb)])
+        return Bd - 0.5 * Sd
+    Ao, Ad = build(O), build(D)
+    iters = 25
+    xo, ho = _lsqr_oracle(O.J, Ao, O.arr(rhs, O.range_(Ao)), iters)
+    G = D.B.solvers.LsqrGraphFused(Ad, D.arr(rhs, D.range_(Ad)))
+    G.run(iters - 1)
+    xg, (ag, bg) = G.result()
+    assert relerr(D.host(xg), O.host(xo)) <= 1e-9
+    assert abs(ag - ho[-1][0]) <= 1e-10 * abs(ag) and abs(bg - ho[-1][1]) <= 1e-10 * abs(bg)
+
+
+@pytest.mark.parametrize("kind", ["elementwise", "dense"])
+def test_apply_axpby_matches_separate_ops(D, kind):
+    """jets_apply_axpby: out = cA*(A x) + cO*out, fused into the store epilogue of the block-apply
+    kernel (elementwise operator) or staged (dense operator) -- bit-identical to apply + axpby."""
+    import ctypes as C
+    B = D.B
+    L = B.solvers.L
+    T = np.float64
+    g = np.random.default_rng(23)
+    n, nb = 6000, 3
+    if kind == "elementwise":
+        W = [[g.random(n) for _ in range(nb)] for _ in range(nb)]
+        A = B.blockop([[B.JopDiagonal(W[r][c]) if r != c else 0.5 * B.JopStencil(T, n, "lap") for c in range(nb)] for r in range(nb)])
+    else:
+        A = B.blockop([[B.JopDense(g.random((64, 48))) for _ in range(2)] for _ in range(2)])
+    x = B.rand(B.domain(A), seed=1)
+    out0 = B.rand(B.range_(A), seed=2)
+    sa, so = B.solvers._S(1.7), B.solvers._S(0.3)
+    for op in (A, B.adjoint(A)):
+        xin, o0 = (x, out0) if op is A else (out0, x)
+        got = o0.copy()
+        B.solvers._apply_axpby(got, op, xin, sa, 0.0, L.COEF_INV, so, 0.0, L.COEF_NEG)
+        ref = o0.copy()
+        tmp = op * xin
+        B.solvers._axpby(ref, sa, 0.0, L.COEF_INV, tmp, so, 0.0, L.COEF_NEG, ref)
+        assert_bits(got.to_host(), ref.to_host())
