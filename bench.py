@@ -335,7 +335,7 @@ def run_ours(args):
     if world == 1:
         # block-row chunks pipelined over three streams: upload k | forward k-1, adjoint k-2 | download k-2
         pipe = B.pipeline.ChunkedBandedApply(B, torch, part, S["make_block"], S["zero_block"], S["xext"], S["d"], S["mext"],
-                                             nchunks=64)
+                                             nchunks=int(os.environ.get("JETS_BENCH_E2E_CHUNKS", "32")))
         pipe.step(h_in, h_out, stream)
         barrier()
         e0 = pipe.start_event(stream)
@@ -343,7 +343,7 @@ def run_ours(args):
             e1 = pipe.step(h_in, h_out, stream)
         barrier()
         e2e_what = ("pinned host m -> H2D -> d=A*m -> m'=A'*d -> D2H m' through jets_buf_upload_async/jets_apply/"
-                    "jets_buf_download_async, 64 block-row chunks pipelined on 3 streams (jets.jl_b200/pipeline.py)")
+                    f"jets_buf_download_async, {len(pipe.chunks)} block-row chunks pipelined on 3 streams (jets.jl_b200/pipeline.py)")
     else:
         def e2e_step():
             B.check(lib.jets_buf_upload_async(S["x_own"]._h, -1, C.c_void_p(h_in.data_ptr()), nloc))
