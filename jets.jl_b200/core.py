@@ -851,6 +851,23 @@ def linearization_test(F, mo, mu=(1.0, 0.5, 0.25, 0.125, 0.0625, 0.03125), dm=No
     return muobs, muexp
 
 
+def vec(x):
+    """vec(R) (src/Jets.jl:66,:758), vec(x) for arrays, and B = vec(A) (:1129-1154): the same operator
+    with "vectorised" domain and range, which is what IterativeSolvers-style callers expect.  Device
+    vectors are flat already, so vec(A) shares A's operator handle and only relabels the spaces."""
+    if isinstance(x, JetAbstractSpace):
+        return x.vec()
+    if isinstance(x, DeviceArray):
+        return x if isinstance(x.space, JetBSpace) else reshape(x, x.space.vec())
+    if isinstance(x, JopAdjoint):
+        return adjoint(vec(x.op))
+    if isinstance(x, Jop):
+        if domain(x).ndims == 1 and range_(x).ndims == 1:   # :1130
+            return x
+        return type(x)(x._h, domain(x).vec(), range_(x).vec(), x.meta)
+    raise TypeError(f"vec is not defined for {type(x).__name__}")
+
+
 def plan_info(A, mode=None):
     e, n = C.c_int32(), C.c_int32()
     check(lib.jets_op_plan_info(A._h.h, A._mode if mode is None else mode, C.byref(e), C.byref(n)))

@@ -776,3 +776,32 @@ def test_apply_axpby_matches_separate_ops(D, kind):
         tmp = op * xin
         B.solvers._axpby(ref, sa, 0.0, L.COEF_INV, tmp, so, 0.0, L.COEF_NEG, ref)
         assert_bits(got.to_host(), ref.to_host())
+
+
+def test_vectorized_operator(O, D):
+    """test/runtests.jl:797-838: B = vec(A) applied to vec(x) equals A*x, for a matrix-shaped space and
+    for a block operator; vec(A') maps back to the domain."""
+    T = np.float64
+    g = np.random.default_rng(31)
+    w = np.asfortranarray(g.random((10, 11)))
+    xv = g.random((10, 11))
+
+    def scn(K):
+        A = K.JopDiagonal(w) if K.name == "oracle" else K.B.JopDiagonal(K.B.to_device(w, K.JetSpace(T, 10, 11)))
+        x = K.arr(xv, K.domain(A))
+        vec = K.J.vec if K.name == "oracle" else K.B.vec
+        Bv = vec(A)
+        assert tuple(K.domain(Bv).size()) == (110,) and tuple(K.domain(A).size()) == (10, 11)
+        d = A * x
+        _d = Bv * vec(x)
+        A2 = K.blockop([[A], [A]])
+        x2 = K.arr(xv, K.domain(A2))
+        d2 = A2 * x2
+        _d2 = vec(A2) * vec(x2)
+        a2 = vec(K.adjoint(A2)) * d2
+        return [np.asarray(K.host(v)).reshape(-1, order="F") for v in (d, _d, d2, _d2, a2)]
+    o, dv = scn(O), scn(D)
+    assert_bits(dv[0], dv[1])
+    assert_bits(dv[2], dv[3])
+    for a, b in zip(o, dv):
+        assert_bits(a, b)
