@@ -42,7 +42,10 @@ typedef enum {
   JETS_ERR_NCCL = 8
 } jets_status;
 
-typedef enum { JETS_F32 = 0, JETS_F64 = 1 } jets_dtype;
+/* JETS_C64 / JETS_C128 = ComplexF32 / ComplexF64, interleaved (re, im) like Julia's Array{Complex{T}}
+ * (complex JetSpace / JetBSpace / JetSSpace: test/runtests.jl:58-75, :228-282, :542-550, :915-917).
+ * Lengths and offsets always count ELEMENTS of the buffer's eltype.                               */
+typedef enum { JETS_F32 = 0, JETS_F64 = 1, JETS_C64 = 2, JETS_C128 = 3 } jets_dtype;
 
 /* mul! dispatch (src/Jets.jl:390-392): F -> f!, DF -> df!, DFT -> df'! */
 typedef enum { JETS_MODE_F = 0, JETS_MODE_DF = 1, JETS_MODE_DFT = 2 } jets_mode;
@@ -112,8 +115,13 @@ int jets_buf_download(jets_buf x, int32_t block, void* host, int64_t count);
 /* Asynchronous variants for pinned host memory (no stream sync).                              */
 int jets_buf_upload_async(jets_buf x, int32_t block, const void* host, int64_t count);
 int jets_buf_download_async(jets_buf x, int32_t block, void* host, int64_t count);
+/* x[first .. first+count) (0-based element offset) <-> host, synchronous: scalar getindex /
+ * setindex! (src/Jets.jl:819-832) and SymmetricArray element access (:455-484).                */
+int jets_buf_write(jets_buf x, int64_t first, const void* host, int64_t count);
+int jets_buf_read(jets_buf x, int64_t first, void* host, int64_t count);
 int jets_buf_copy(jets_buf dst, jets_buf src);                   /* dst .= src                 */
 int jets_buf_fill(jets_buf x, double a);                         /* fill!(x,a)  :880-885       */
+int jets_buf_fill_c(jets_buf x, double re, double im);           /* the same with a complex a  */
 /* rand(R)/randn(R): counter-based (Philox4x32-10) stream keyed by (seed, element index), so the
  * same (seed, logical index) gives the same value for any block/GPU partition.
  * dist 0: U[0,1)   dist 1: N(0,1)                                                             */
@@ -122,12 +130,23 @@ int jets_buf_rand(jets_buf x, uint64_t seed, uint64_t index_offset, int dist);
 /* ------------------------------------------- BlockArray reductions and broadcast updates ---- */
 /* dot(x,y) (src/Jets.jl:850-856); norm(x,p) (:834-848) with p in {2,1,0,+Inf,-Inf,other};
  * extrema(x) (:870-878).  Fixed-order two-pass reductions accumulated in f64; no atomics.     */
-int jets_dot(jets_buf x, jets_buf y, double* out);
+int jets_dot(jets_buf x, jets_buf y, double* out);               /* complex: the real part      */
 int jets_norm(jets_buf x, double p, double* out);
-int jets_extrema(jets_buf x, double* mn, double* mx);
+int jets_extrema(jets_buf x, double* mn, double* mx);            /* real eltypes only           */
+/* dot(x,y) = sum conj(x_i) y_i for the complex eltypes (conj on the FIRST argument as :853 /
+ * LinearAlgebra.dot); out_re_im[0..1] = (real, imag).  Real vectors give imag = 0.              */
+int jets_dot_c(jets_buf x, jets_buf y, double* out_re_im);
+/* norm over the LOGICAL array of a SymmetricArray (src/Jets.jl:443-462): x is the stored parent
+ * (complex), w (Float64, one weight per stored element) = 1 + number of mirrored positions whose
+ * index map lands on that element.  p as jets_norm.                                             */
+int jets_norm_weighted(jets_buf x, jets_buf w, double p, double* out);
+/* out .= abs.(x) for complex x; out has the real eltype (test/runtests.jl:545-547).             */
+int jets_abs(jets_buf out, jets_buf x);
 /* out .= c[0].*x[0] .+ c[1].*x[1] ... (n<=4; left-to-right, one rounding per op, matching the
  * BlockArray broadcast copyto! src/Jets.jl:905-911).  out may alias any x[i].                  */
 int jets_lincomb(jets_buf out, int32_t n, const double* c, const jets_buf* x);
+/* The same with complex coefficients c_re_im[2i], c_re_im[2i+1] (complex eltypes only).         */
+int jets_lincomb_c(jets_buf out, int32_t n, const double* c_re_im, const jets_buf* x);
 /* out .= x .* y  (mask application in dot_product_test, src/Jets.jl:1215-1216).                */
 int jets_hadamard(jets_buf out, jets_buf x, jets_buf y);
 
@@ -161,6 +180,8 @@ int jets_graph_destroy(void* graph_exec);
 int jets_op_diag(jets_buf w, jets_op* out);
 /* d .= a*m (_constdiag_df!, src/Jets.jl:1159-1160).                                            */
 int jets_op_scale(jets_dtype dt, int64_t n, double a, jets_op* out);
+/* complex a on a complex space; the adjoint applies conj(a) (_constdiag_df'!, :1160).          */
+int jets_op_scale_c(jets_dtype dt, int64_t n, double a_re, double a_im, jets_op* out);
 /* JopNl(f! = phi(m), df! = phi'(mo).*dm) -- fixture JopBar test/runtests.jl:20-25.            */
 int jets_op_pointwise(jets_dtype dt, int64_t n, int fn, double p, jets_op* out);
 int jets_op_stencil(jets_dtype dt, int64_t n, int kind, jets_op* out);
@@ -190,6 +211,7 @@ int jets_op_block(int32_t nrow, int32_t ncol, const jets_op* ops, int dadom, jet
 /* a*A (src/Jets.jl:1161-1164) = scale(range(A), a) ∘ A.  (The reference builds the scalar op on
  * domain(A), quirk Q6; identical for square A.)                                                 */
 int jets_op_scalar_mul(double a, jets_op A, jets_op* out);
+int jets_op_scalar_mul_c(double a_re, double a_im, jets_op A, jets_op* out);
 
 /* ------------------------------------------------------------------ operator queries -------- */
 int jets_op_retain(jets_op a);

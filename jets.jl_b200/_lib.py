@@ -11,7 +11,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libjets_b200.so")
 
-F32, F64 = 0, 1
+F32, F64, C64, C128 = 0, 1, 2, 3
 MODE_F, MODE_DF, MODE_DFT = 0, 1, 2
 PW = {"square": 0, "power": 1, "exp": 2, "sin": 3, "tanh": 4}
 STENCIL = {"fdiff": 0, "lap": 1}
@@ -72,7 +72,16 @@ SIGNATURES = {
     "jets_buf_download": (_i, [_p, _i32, _p, _i64]),
     "jets_buf_upload_async": (_i, [_p, _i32, _p, _i64]),
     "jets_buf_download_async": (_i, [_p, _i32, _p, _i64]),
+    "jets_buf_write": (_i, [_p, _i64, _p, _i64]),
+    "jets_buf_read": (_i, [_p, _i64, _p, _i64]),
     "jets_buf_copy": (_i, [_p, _p]),
+    "jets_buf_fill_c": (_i, [_p, _d, _d]),
+    "jets_dot_c": (_i, [_p, _p, _pd]),
+    "jets_norm_weighted": (_i, [_p, _p, _d, _pd]),
+    "jets_abs": (_i, [_p, _p]),
+    "jets_lincomb_c": (_i, [_p, _i32, _pd, _pp]),
+    "jets_op_scale_c": (_i, [_i, _i64, _d, _d, _pp]),
+    "jets_op_scalar_mul_c": (_i, [_d, _d, _p, _pp]),
     "jets_buf_fill": (_i, [_p, _d]),
     "jets_buf_rand": (_i, [_p, _u64, _u64, _i]),
     "jets_dot": (_i, [_p, _p, _pd]),

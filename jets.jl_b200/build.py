@@ -25,6 +25,7 @@ SOURCES = {
     "kernels_fused_fast.cu": ["-fmad=false"],
     "kernels_fused_bundle.cu": ["-fmad=false"],
     "kernels_vec.cu": ["-fmad=false"],
+    "kernels_cplx.cu": ["-fmad=false"],
     "kernels_dense.cu": [],
     "kernels_gemm_tc.cu": [],
     "dist.cu": [],

@@ -30,15 +30,21 @@ import numpy as np
 from . import _lib as L
 from ._lib import JetsError, lib, check
 
-_DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64}
-_NP = {L.F32: np.dtype(np.float32), L.F64: np.dtype(np.float64)}
+_DT = {np.dtype(np.float32): L.F32, np.dtype(np.float64): L.F64,
+       np.dtype(np.complex64): L.C64, np.dtype(np.complex128): L.C128}
+_NP = {v: k for k, v in _DT.items()}
+_REAL = {np.dtype(np.complex64): np.dtype(np.float32), np.dtype(np.complex128): np.dtype(np.float64)}
 
 
 def _dt(T):
     T = np.dtype(T)
     if T not in _DT:
-        raise JetsError(3, f"eltype {T} is not supported on the device path (Float32/Float64 only)")
+        raise JetsError(3, f"eltype {T} is not supported on the device path (Float32/Float64/ComplexF32/ComplexF64)")
     return _DT[T]
+
+
+def _iscomplex(T):
+    return np.dtype(T).kind == "c"
 
 
 # ------------------------------------------------------------------ spaces ----------------
@@ -127,6 +133,75 @@ class JetBSpace(JetAbstractSpace):
         return [len(s) for s in self.spaces]
 
 
+class JetSSpace(JetAbstractSpace):
+    """Symmetric space (src/Jets.jl:408-441): logical size ``n``, stored parent of size ``M``;
+    an index beyond the parent in some dimension reads ``conj(parent[map(I)])`` (:455-462).
+    ``map`` takes and returns a 1-based index tuple, as the reference's ``map(I)`` does with a
+    CartesianIndex."""
+
+    def __init__(self, T, n, M, map):
+        self.T = np.dtype(T)
+        self.n = tuple(int(k) for k in n)
+        self.M = tuple(int(k) for k in M)
+        self.map = map
+        self._weights = None   # device vector: logical entries represented by each stored element
+
+    def __eq__(self, o):
+        return isinstance(o, JetSSpace) and self.T == o.T and self.n == o.n and self.M == o.M and self.map is o.map
+
+    def __hash__(self):
+        return hash((self.T, self.n, self.M))
+
+    def __repr__(self):
+        return f"JetSSpace({self.T}, {self.n}, {self.M})"
+
+    eltype = property(lambda s: s.T)
+    ndims = property(lambda s: len(s.n))
+
+    def size(self, i=None):
+        return self.n if i is None else self.n[i - 1]
+
+    def __len__(self):
+        return int(np.prod(self.n, dtype=np.int64))
+
+    def similar(self, *dims):
+        if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+            dims = tuple(dims[0])
+        return JetSSpace(self.T, dims, self.M, self.map)
+
+    def _block_lens(self):   # what is stored: the parent
+        return [int(np.prod(self.M, dtype=np.int64))]
+
+    def _beyond(self, I):
+        return any(I[d] > self.M[d] for d in range(len(self.n)))
+
+    def _parent_linear(self, I):
+        """0-based column-major offset into the parent of the stored element behind logical index I
+        (1-based tuple), and whether it enters conjugated."""
+        cj = self._beyond(I)
+        J = tuple(self.map(tuple(I))) if cj else tuple(I)
+        off, stride = 0, 1
+        for d, j in enumerate(J):
+            off += (int(j) - 1) * stride
+            stride *= self.M[d]
+        return off, cj
+
+    def multiplicity(self):
+        """Host table, one entry per stored element: 1 + the number of mirrored logical positions
+        that map onto it -- the weights with which norm() over the logical array (generic
+        AbstractArray iteration through getindex :455-462) sees each stored value."""
+        w = np.ones(self._block_lens()[0], dtype=np.float64)
+        for I in itertools.product(*[range(1, k + 1) for k in reversed(self.n)]):
+            I = tuple(reversed(I))
+            if self._beyond(I):
+                w[self._parent_linear(I)[0]] += 1.0
+        return w
+
+
+def symspace():
+    return None
+
+
 def indices(R, iblock):
     return R.indices[iblock - 1]
 
@@ -188,14 +263,69 @@ class DeviceArray:
     def to_host(self):
         """convert(Array, x) (src/Jets.jl:862-868): flat host vector for block arrays, shaped
         (column-major) array for plain spaces."""
+        if isinstance(self.space, JetSSpace):
+            return self.full()
         out = np.empty(len(self), dtype=self.dtype)
         check(lib.jets_buf_download(self._h, -1, out.ctypes.data_as(C.c_void_p), out.size))
         if self.isblock:
             return out
         return out.reshape(self.space.n, order="F")
 
+    # --- SymmetricArray interface (src/Jets.jl:443-484)
+    @property
+    def issymmetric(self):
+        return isinstance(self.space, JetSSpace)
+
+    def parent(self):
+        """parent(A::SymmetricArray) (:449): the stored part, as a host array of size M."""
+        R = self.space
+        if not isinstance(R, JetSSpace):
+            return self.to_host()
+        out = np.empty(R._block_lens()[0], dtype=self.dtype)
+        check(lib.jets_buf_download(self._h, -1, out.ctypes.data_as(C.c_void_p), out.size))
+        return out.reshape(R.M, order="F")
+
+    A = property(lambda self: self.parent())
+
+    def full(self):
+        """The logical n-sized array, mirrored entries filled in through getindex (:455-462)."""
+        R = self.space
+        P = self.parent().reshape(-1, order="F")
+        out = np.empty(R.n, dtype=self.dtype)
+        for I in itertools.product(*[range(1, k + 1) for k in R.n]):
+            off, cj = R._parent_linear(I)
+            out[tuple(i - 1 for i in I)] = np.conj(P[off]) if cj else P[off]
+        return out
+
+    def _elem_offset(self, I):
+        """(0-based storage offset, conjugated?) of a 1-based index: tuple (Cartesian) or int (linear,
+        column-major over the logical size, :465-468)."""
+        R = self.space
+        if isinstance(R, JetSSpace):
+            if not isinstance(I, tuple):
+                I = tuple(int(k) + 1 for k in np.unravel_index(int(I) - 1, R.n, order="F"))
+            return R._parent_linear(I)
+        if isinstance(I, tuple):
+            I = int(np.ravel_multi_index(tuple(int(k) - 1 for k in I), R.n, order="F")) + 1
+        return int(I) - 1, False
+
+    def __getitem__(self, I):
+        """x[i] / x[i1,i2,...] with the reference's 1-based indices (scalar getindex, :819-825, :455-468)."""
+        off, cj = self._elem_offset(I)
+        v = np.empty(1, dtype=self.dtype)
+        check(lib.jets_buf_read(self._h, off, v.ctypes.data_as(C.c_void_p), 1))
+        return np.conj(v[0]) if cj else v[0]
+
+    def __setitem__(self, I, val):
+        """x[i] = v (scalar setindex!, :826-832; mirrored positions store conj(v), :470-478)."""
+        off, cj = self._elem_offset(I)
+        v = np.array([np.conj(val) if cj else val], dtype=self.dtype)
+        check(lib.jets_buf_write(self._h, off, v.ctypes.data_as(C.c_void_p), 1))
+
     def from_host(self, x):
         x = np.asarray(x)
+        if isinstance(self.space, JetSSpace) and x.shape == self.space.n and self.space.n != self.space.M:
+            x = x[tuple(slice(0, m) for m in self.space.M)]   # keep the stored part of a full array
         if x.ndim > 1:
             x = x.reshape(-1, order="F")
         x = np.ascontiguousarray(x, dtype=self.dtype)
@@ -216,13 +346,14 @@ class DeviceArray:
         if isinstance(xblock, DeviceArray):
             check(lib.jets_buf_copy(blk._h, xblock._h))
         elif np.isscalar(xblock):
-            check(lib.jets_buf_fill(blk._h, float(xblock)))
+            blk.fill_(xblock)
         else:
             blk.from_host(xblock)
         return blk
 
     def fill_(self, a):
-        check(lib.jets_buf_fill(self._h, float(a)))
+        a = complex(a)
+        check(lib.jets_buf_fill_c(self._h, a.real, a.imag))
         return self
 
     def assign(self, src):
@@ -260,7 +391,7 @@ class DeviceArray:
 
     def __mul__(self, o):
         if np.isscalar(o):
-            return self._lin([(float(o), self)])
+            return self._lin([(o, self)])
         out = similar(self)
         check(lib.jets_hadamard(out._h, self._h, _as_dev(o, self)._h))
         return out
@@ -269,8 +400,11 @@ class DeviceArray:
 
     def __truediv__(self, o):
         if np.isscalar(o):
-            return self._lin([(1.0 / float(o), self)])
+            return self._lin([(1.0 / o, self)])
         return NotImplemented
+
+    def __abs__(self):
+        return abs_(self)
 
 
 def _as_dev(o, like: DeviceArray) -> DeviceArray:
@@ -400,10 +534,32 @@ def lincomb_(out: DeviceArray, terms):
         if not first:
             chunk = [(1.0, out)] + chunk
         n = len(chunk)
-        cs = (C.c_double * n)(*[float(c) for c, _ in chunk])
         xs = (C.c_void_p * n)(*[x._h for _, x in chunk])
-        check(lib.jets_lincomb(out._h, n, cs, xs))
+        if any(isinstance(c, complex) or np.iscomplexobj(c) for c, _ in chunk):
+            flat = []
+            for c, _ in chunk:
+                c = complex(c)
+                flat += [c.real, c.imag]
+            check(lib.jets_lincomb_c(out._h, n, (C.c_double * (2 * n))(*flat), xs))
+        else:
+            cs = (C.c_double * n)(*[float(c) for c, _ in chunk])
+            check(lib.jets_lincomb(out._h, n, cs, xs))
         first = False
+    return out
+
+
+def abs_(x: DeviceArray) -> DeviceArray:
+    """abs.(x) for a complex vector: a real vector on the same block structure (test/runtests.jl:545-547)."""
+    R = x.space
+    T = _REAL[np.dtype(x.dtype)]
+    if isinstance(R, JetBSpace):
+        Rr = JetBSpace([JetSpace(T, *s.n) for s in R.spaces])
+    elif isinstance(R, JetSSpace):
+        Rr = JetSpace(T, *R.M)
+    else:
+        Rr = JetSpace(T, *R.n)
+    out = _alloc(Rr)
+    check(lib.jets_abs(out._h, x._h))
     return out
 
 
@@ -413,15 +569,31 @@ def hadamard_(out, x, y):
 
 
 def dot(x: DeviceArray, y: DeviceArray):
+    """dot(x, y) (src/Jets.jl:850-856); conj on the first argument for complex eltypes."""
+    if _iscomplex(x.dtype):
+        r = (C.c_double * 2)()
+        check(lib.jets_dot_c(x._h, y._h, r))
+        return x.dtype.type(complex(r[0], r[1]))
     r = C.c_double()
     check(lib.jets_dot(x._h, y._h, C.byref(r)))
     return x.dtype.type(r.value)
 
 
+def _sym_weights(R: JetSSpace) -> DeviceArray:
+    if R._weights is None:
+        w = R.multiplicity()
+        R._weights = _alloc(JetSpace(np.float64, w.size)).from_host(w)
+    return R._weights
+
+
 def norm(x: DeviceArray, p=2):
     r = C.c_double()
-    check(lib.jets_norm(x._h, float(p), C.byref(r)))
-    return x.dtype.type(r.value)
+    if isinstance(x.space, JetSSpace):
+        # norm over the logical array: every stored element counts once per position it stands for
+        check(lib.jets_norm_weighted(x._h, _sym_weights(x.space)._h, float(p), C.byref(r)))
+    else:
+        check(lib.jets_norm(x._h, float(p), C.byref(r)))
+    return _REAL.get(np.dtype(x.dtype), np.dtype(x.dtype)).type(r.value)
 
 
 def extrema(x: DeviceArray):
@@ -638,7 +810,8 @@ def JopDiagonal(w):
 
 def JopScale(T, n, a):
     sp = JetSpace(T, *((n,) if np.isscalar(n) else tuple(n)))
-    return JopLn(_newop(lib.jets_op_scale, _dt(T), len(sp), float(a)), sp, sp, {"a": a})
+    a_ = complex(a)
+    return JopLn(_newop(lib.jets_op_scale_c, _dt(T), len(sp), a_.real, a_.imag), sp, sp, {"a": a})
 
 
 def JopPointwise(T, n, fn="square", p=0.0):
@@ -730,7 +903,8 @@ def op_sum(A2, A1, sign):
 
 def scalar_mul(a, A):
     """a*A (src/Jets.jl:1161-1164)."""
-    h = _newop(lib.jets_op_scalar_mul, float(a), A._h.h)
+    a_ = complex(a)
+    h = _newop(lib.jets_op_scalar_mul_c, a_.real, a_.imag, A._h.h)
     cls = JopLn if _is_lin(A) else JopNl
     return cls(h, domain(A), range_(A), {})
 

@@ -44,7 +44,10 @@ static jets_buf make_buf(int dt, std::shared_ptr<Storage> st, int64_t off, int32
 
 static void check_buf(jets_buf x) { JETS_CHECK(x && x->refs > 0, JETS_ERR_INVALID, "null or destroyed buffer handle"); }
 static void check_op(jets_op a) { JETS_CHECK(a && a->refs > 0, JETS_ERR_INVALID, "null or destroyed operator handle"); }
-static void check_dt(int dt) { JETS_CHECK(dt == JETS_F32 || dt == JETS_F64, JETS_ERR_DTYPE, "unsupported dtype %d", dt); }
+static void check_dt(int dt) { JETS_CHECK(dt >= JETS_F32 && dt <= JETS_C128, JETS_ERR_DTYPE, "unsupported dtype %d", dt); }
+static void check_real(int dt, const char* what) {
+  JETS_CHECK(!is_cplx(dt), JETS_ERR_UNSUPPORTED, "%s is not implemented for complex eltypes", what);
+}
 
 static void buf_release(jets_buf x) {
   if (x && --x->refs == 0) delete x;
@@ -144,6 +147,7 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
     a->plans[key] = plan;
   }
   if (coef) {
+    check_real(a->dtype, "jets_apply_axpby");
     // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...
     if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef)) return;
     // ... else through a temporary owned by the operator (dense / staged plans)
@@ -438,6 +442,21 @@ int jets_buf_download(jets_buf x, int32_t b, void* h, int64_t n) { return guard(
 int jets_buf_upload_async(jets_buf x, int32_t b, const void* h, int64_t n) { return guard([&] { xfer(x, b, const_cast<void*>(h), n, true, true); }); }
 int jets_buf_download_async(jets_buf x, int32_t b, void* h, int64_t n) { return guard([&] { xfer(x, b, h, n, false, true); }); }
 
+// x[first .. first+count) <-> host: scalar getindex/setindex! and SymmetricArray element access
+static void xfer_range(jets_buf x, int64_t first, void* host, int64_t count, bool up) {
+  require_ready(); check_buf(x);
+  JETS_CHECK(host || count == 0, JETS_ERR_INVALID, "null host pointer");
+  JETS_CHECK(first >= 0 && count >= 0 && first + count <= x->length(), JETS_ERR_SHAPE,
+             "range [%lld, %lld) outside a vector of %lld elements", (long long)first, (long long)(first + count), (long long)x->length());
+  const size_t w = dsize(x->dtype);
+  char* p = x->ptr() + (size_t)first * w;
+  if (up) CUDA_TRY(cudaMemcpyAsync(p, host, (size_t)count * w, cudaMemcpyHostToDevice, ctx().stream));
+  else CUDA_TRY(cudaMemcpyAsync(host, p, (size_t)count * w, cudaMemcpyDeviceToHost, ctx().stream));
+  CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+}
+int jets_buf_write(jets_buf x, int64_t first, const void* h, int64_t n) { return guard([&] { xfer_range(x, first, const_cast<void*>(h), n, true); }); }
+int jets_buf_read(jets_buf x, int64_t first, void* h, int64_t n) { return guard([&] { xfer_range(x, first, h, n, false); }); }
+
 int jets_buf_copy(jets_buf dst, jets_buf src) {
   return guard([&] {
     require_ready(); check_buf(dst); check_buf(src);
@@ -446,14 +465,34 @@ int jets_buf_copy(jets_buf dst, jets_buf src) {
     CUDA_TRY(cudaMemcpyAsync(dst->ptr(), src->ptr(), (size_t)dst->length() * dsize(dst->dtype), cudaMemcpyDeviceToDevice, ctx().stream));
   });
 }
-int jets_buf_fill(jets_buf x, double a) {
-  return guard([&] { require_ready(); check_buf(x); vec_fill(x->dtype, x->ptr(), x->length(), a, ctx().stream); });
+int jets_buf_fill(jets_buf x, double a) { return jets_buf_fill_c(x, a, 0.0); }
+int jets_buf_fill_c(jets_buf x, double re, double im) {
+  return guard([&] {
+    require_ready(); check_buf(x);
+    if (is_cplx(x->dtype)) cvec_fill(x->dtype, x->ptr(), x->length(), re, im, ctx().stream);
+    else {
+      JETS_CHECK(im == 0.0, JETS_ERR_DTYPE, "complex fill value for a real vector");
+      vec_fill(x->dtype, x->ptr(), x->length(), re, ctx().stream);
+    }
+  });
 }
 int jets_buf_rand(jets_buf x, uint64_t seed, uint64_t off, int dist) {
   return guard([&] {
     require_ready(); check_buf(x);
     JETS_CHECK(dist == 0 || dist == 1, JETS_ERR_INVALID, "dist must be 0 (uniform) or 1 (normal)");
-    vec_rand(x->dtype, x->ptr(), x->length(), seed, off, dist, ctx().stream);
+    if (is_cplx(x->dtype)) {
+      // rand(ComplexF64): both parts U[0,1); randn: both parts N(0, 1/2).  Part k of element i draws
+      // from counter 2i+k, so any partition of the logical vector sees the same numbers.
+      const int rdt = real_of(x->dtype);
+      vec_rand(rdt, x->ptr(), 2 * x->length(), seed, 2 * off, dist, ctx().stream);
+      if (dist == 1) {
+        const double c = 0.70710678118654752440;
+        const void* px = x->ptr();
+        vec_lincomb(rdt, x->ptr(), 2 * x->length(), 1, &c, &px, ctx().stream);
+      }
+    } else {
+      vec_rand(x->dtype, x->ptr(), x->length(), seed, off, dist, ctx().stream);
+    }
   });
 }
 
@@ -478,22 +517,71 @@ static void norm_to(jets_buf x, double p, double* dev_out) {
   else if (std::isinf(p) && p > 0) kind = 4;
   else if (std::isinf(p) && p < 0) kind = 5;
   else kind = 6;
+  if (is_cplx(x->dtype)) {
+    // |z| replaces |x|; kinds 1..6 of vec_reduce map onto 2..7 of cvec_reduce
+    const int finish = kind == 1 ? 1 : kind == 6 ? 2 : 0;
+    cvec_reduce(x->dtype, kind + 1, x->ptr(), nullptr, nullptr, x->length(), p, finish, dev_out, ctx().stream);
+    return;
+  }
   vec_reduce(x->dtype, kind, x->ptr(), nullptr, x->length(), p, dev_out, ctx().stream);
 }
 int jets_dot(jets_buf x, jets_buf y, double* out) {
   return guard([&] {
     require_ready(); check_pair(x, y);
-    vec_reduce(x->dtype, 0, x->ptr(), y->ptr(), x->length(), 0, result_slot(0), ctx().stream);
+    if (is_cplx(x->dtype)) cvec_reduce(x->dtype, 0, x->ptr(), y->ptr(), nullptr, x->length(), 0, 0, result_slot(0), ctx().stream);
+    else vec_reduce(x->dtype, 0, x->ptr(), y->ptr(), x->length(), 0, result_slot(0), ctx().stream);
     fetch(1, out);
+  });
+}
+int jets_dot_c(jets_buf x, jets_buf y, double* out_re_im) {
+  return guard([&] {
+    require_ready(); check_pair(x, y);
+    JETS_CHECK(out_re_im, JETS_ERR_INVALID, "null out");
+    if (is_cplx(x->dtype)) {
+      cvec_reduce(x->dtype, 0, x->ptr(), y->ptr(), nullptr, x->length(), 0, 0, result_slot(0), ctx().stream);
+      cvec_reduce(x->dtype, 1, x->ptr(), y->ptr(), nullptr, x->length(), 0, 0, result_slot(1), ctx().stream);
+      fetch(2, out_re_im);
+    } else {
+      vec_reduce(x->dtype, 0, x->ptr(), y->ptr(), x->length(), 0, result_slot(0), ctx().stream);
+      fetch(1, out_re_im);
+      out_re_im[1] = 0.0;
+    }
   });
 }
 int jets_norm(jets_buf x, double p, double* out) {
   return guard([&] { require_ready(); check_buf(x); norm_to(x, p, result_slot(0)); fetch(1, out); });
 }
+int jets_norm_weighted(jets_buf x, jets_buf w, double p, double* out) {
+  return guard([&] {
+    require_ready(); check_buf(x); check_buf(w);
+    JETS_CHECK(is_cplx(x->dtype), JETS_ERR_UNSUPPORTED, "weighted norms are implemented for the complex eltypes (JetSSpace)");
+    JETS_CHECK(w->dtype == JETS_F64 && w->length() == x->length(), JETS_ERR_SHAPE, "weights must be Float64, one per element");
+    const double* wp = reinterpret_cast<const double*>(w->ptr());
+    int kind, finish = 0;
+    if (p == 2.0) { kind = 2; finish = 1; }
+    else if (p == 1.0) kind = 3;
+    else if (p == 0.0) kind = 4;
+    else if (std::isinf(p) && p > 0) kind = 5;
+    else if (std::isinf(p) && p < 0) kind = 6;
+    else { kind = 7; finish = 2; }
+    cvec_reduce(x->dtype, kind, x->ptr(), nullptr, wp, x->length(), p, finish, result_slot(0), ctx().stream);
+    fetch(1, out);
+  });
+}
+int jets_abs(jets_buf out, jets_buf x) {
+  return guard([&] {
+    require_ready(); check_buf(out); check_buf(x);
+    JETS_CHECK(is_cplx(x->dtype) && out->dtype == real_of(x->dtype), JETS_ERR_DTYPE,
+               "abs.(x): x must be complex and out its real eltype");
+    JETS_CHECK(out->length() == x->length(), JETS_ERR_SHAPE, "length mismatch");
+    cvec_abs(x->dtype, out->ptr(), x->ptr(), x->length(), ctx().stream);
+  });
+}
 int jets_extrema(jets_buf x, double* mn, double* mx) {
   return guard([&] {
     require_ready(); check_buf(x);
     JETS_CHECK(x->length() > 0, JETS_ERR_SHAPE, "extrema of an empty vector");
+    check_real(x->dtype, "extrema (complex numbers are not ordered)");
     vec_reduce(x->dtype, 7, x->ptr(), nullptr, x->length(), 0, result_slot(0), ctx().stream);
     vec_reduce(x->dtype, 8, x->ptr(), nullptr, x->length(), 0, result_slot(1), ctx().stream);
     double r[2];
@@ -507,13 +595,25 @@ int jets_lincomb(jets_buf out, int32_t n, const double* c, const jets_buf* x) {
     JETS_CHECK(n >= 1 && n <= 4 && c && x, JETS_ERR_INVALID, "lincomb takes 1..4 terms");
     const void* px[4];
     for (int i = 0; i < n; ++i) { check_pair(out, x[i]); px[i] = x[i]->ptr(); }
-    vec_lincomb(out->dtype, out->ptr(), out->length(), n, c, px, ctx().stream);
+    if (is_cplx(out->dtype)) vec_lincomb(real_of(out->dtype), out->ptr(), 2 * out->length(), n, c, px, ctx().stream);
+    else vec_lincomb(out->dtype, out->ptr(), out->length(), n, c, px, ctx().stream);
+  });
+}
+int jets_lincomb_c(jets_buf out, int32_t n, const double* c_re_im, const jets_buf* x) {
+  return guard([&] {
+    require_ready(); check_buf(out);
+    JETS_CHECK(n >= 1 && n <= 4 && c_re_im && x, JETS_ERR_INVALID, "lincomb takes 1..4 terms");
+    JETS_CHECK(is_cplx(out->dtype), JETS_ERR_DTYPE, "complex coefficients need a complex vector");
+    const void* px[4];
+    for (int i = 0; i < n; ++i) { check_pair(out, x[i]); px[i] = x[i]->ptr(); }
+    cvec_lincomb(out->dtype, out->ptr(), out->length(), n, c_re_im, px, ctx().stream);
   });
 }
 int jets_hadamard(jets_buf out, jets_buf x, jets_buf y) {
   return guard([&] {
     require_ready(); check_pair(out, x); check_pair(out, y);
-    vec_hadamard(out->dtype, out->ptr(), x->ptr(), y->ptr(), out->length(), ctx().stream);
+    if (is_cplx(out->dtype)) cvec_hadamard(out->dtype, out->ptr(), x->ptr(), y->ptr(), out->length(), 0, ctx().stream);
+    else vec_hadamard(out->dtype, out->ptr(), x->ptr(), y->ptr(), out->length(), ctx().stream);
   });
 }
 
@@ -549,6 +649,7 @@ int jets_scalar_get(jets_scalar s, double* v) {
 int jets_dot_dev(jets_buf x, jets_buf y, jets_scalar out) {
   return guard([&] {
     require_ready(); check_pair(x, y); JETS_CHECK(out, JETS_ERR_INVALID, "null scalar");
+    check_real(x->dtype, "jets_dot_dev");
     vec_reduce(x->dtype, 0, x->ptr(), y->ptr(), x->length(), 0, out->dev, ctx().stream);
   });
 }
@@ -566,6 +667,7 @@ int jets_axpby_dev(jets_buf out, jets_scalar sa, double ca, int af, jets_buf x, 
   return guard([&] {
     require_ready(); check_pair(out, x);
     if (y) check_pair(out, y);
+    check_real(out->dtype, "jets_axpby_dev");
     vec_axpby_dev(out->dtype, out->ptr(), out->length(), sa ? sa->dev : nullptr, ca, af, x->ptr(),
                   sb ? sb->dev : nullptr, cb, bf, y ? y->ptr() : nullptr, ctx().stream);
   });
@@ -607,12 +709,14 @@ int jets_op_diag(jets_buf w, jets_op* out) {
     *out = a;
   });
 }
-int jets_op_scale(jets_dtype dt, int64_t n, double s, jets_op* out) {
+int jets_op_scale(jets_dtype dt, int64_t n, double s, jets_op* out) { return jets_op_scale_c(dt, n, s, 0.0, out); }
+int jets_op_scale_c(jets_dtype dt, int64_t n, double re, double im, jets_op* out) {
   return guard([&] {
     check_dt(dt); JETS_CHECK(out && n >= 0, JETS_ERR_INVALID, "bad arguments");
+    JETS_CHECK(im == 0.0 || is_cplx(dt), JETS_ERR_DTYPE, "complex scalar on a real space");
     jets_op a = new_op(K_SCALE, dt);
     a->dom = a->rng = space1(n);
-    a->a = s;
+    a->a = re; a->ai = im;
     *out = a;
   });
 }
@@ -620,6 +724,7 @@ int jets_op_pointwise(jets_dtype dt, int64_t n, int fn, double p, jets_op* out) 
   return guard([&] {
     check_dt(dt); JETS_CHECK(out && n >= 0, JETS_ERR_INVALID, "bad arguments");
     JETS_CHECK(fn >= JETS_PW_SQUARE && fn <= JETS_PW_TANH, JETS_ERR_UNSUPPORTED, "pointwise function %d is not in the registry", fn);
+    JETS_CHECK(!is_cplx(dt) || fn == JETS_PW_SQUARE, JETS_ERR_UNSUPPORTED, "complex pointwise operators: only x^2 is in the registry");
     jets_op a = new_op(K_PW, dt);
     a->dom = a->rng = space1(n);
     a->fn = fn; a->p = p; a->linear = false;
@@ -642,6 +747,7 @@ int jets_op_dense(jets_buf A, int64_t rows, int64_t cols, int64_t nrhs, jets_op*
     JETS_CHECK(A->length() == rows * cols, JETS_ERR_SHAPE, "matrix buffer has %lld elements, expected %lld x %lld",
                (long long)A->length(), (long long)rows, (long long)cols);
     JETS_CHECK(rows < (1LL << 31) && cols < (1LL << 31), JETS_ERR_UNSUPPORTED, "matrix dimension too large");
+    check_real(A->dtype, "dense matrix operators");
     jets_op a = new_op(K_DENSE, A->dtype);
     a->dom = space1(cols * nrhs);
     a->rng = space1(rows * nrhs);
@@ -795,11 +901,12 @@ int jets_op_block(int32_t R, int32_t C, const jets_op* ops, int dadom, jets_op* 
   });
 }
 
-int jets_op_scalar_mul(double s, jets_op A, jets_op* out) {
+int jets_op_scalar_mul(double s, jets_op A, jets_op* out) { return jets_op_scalar_mul_c(s, 0.0, A, out); }
+int jets_op_scalar_mul_c(double s, double s_im, jets_op A, jets_op* out) {
   return guard([&] {
     check_op(A); JETS_CHECK(out, JETS_ERR_INVALID, "null out");
     jets_op sc = nullptr;
-    JETS_CHECK(jets_op_scale((jets_dtype)A->dtype, A->rng.total(), s, &sc) == JETS_OK, JETS_ERR_INVALID, "scale");
+    { const int rc = jets_op_scale_c((jets_dtype)A->dtype, A->rng.total(), s, s_im, &sc); if (rc != JETS_OK) throw Fail{rc}; }
     jets_op pair[2] = {sc, A};
     jets_op res = nullptr;
     const int rc = jets_op_compose(2, pair, &res);

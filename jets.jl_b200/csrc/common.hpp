@@ -81,7 +81,9 @@ struct Context {
 };
 Context& ctx();
 void require_ready();
-inline size_t dsize(int dt) { return dt == JETS_F32 ? 4 : 8; }
+inline size_t dsize(int dt) { return dt == JETS_F32 ? 4 : dt == JETS_C128 ? 16 : 8; }
+inline bool is_cplx(int dt) { return dt == JETS_C64 || dt == JETS_C128; }
+inline int real_of(int dt) { return dt == JETS_C64 ? JETS_F32 : dt == JETS_C128 ? JETS_F64 : dt; }
 
 // ------------------------------------------------------------------ storage --------------
 constexpr size_t kGuardBytes = 256;  // readable slack before/after every owned allocation
@@ -147,6 +149,7 @@ struct jets_op_s {
   // leaf state
   jets_buf w = nullptr;      // diagonal / dense matrix (retained)
   double a = 0, p = 0;       // scale constant / pointwise parameter
+  double ai = 0;             // imaginary part of the scale constant (complex spaces)
   int fn = 0;                // pointwise fn or stencil kind
   int64_t rows = 0, cols = 0, nrhs = 1;
   jets_buf mo = nullptr;     // linearization point of a pointwise leaf (retained, by reference)
@@ -175,7 +178,9 @@ enum StageOp : int {
   S_BDIFF = 5,   // adjoint of FDIFF: v[p] = (p>=1 ? v[p-1] : 0) - (p+1<n ? v[p] : 0)
   S_LAP = 6,     // v[p] = ((p>=1?v[p-1]:0) - 2 v[p]) + (p+1<n?v[p+1]:0)
   S_NEG = 7,     // v = -v
-  S_ZERO = 8     // v = 0
+  S_ZERO = 8,    // v = 0
+  S_CSCALE = 9,  // complex spaces: v *= (c0 + i*c0 of the S_CIMAG stage that follows)
+  S_CIMAG = 10   // carries the imaginary part of the preceding S_CSCALE; no operation
 };
 
 struct FStage {      // 32 bytes
@@ -424,6 +429,17 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
                    const void* x, const double* sb, double cb, int bf, const void* y,
                    cudaStream_t s);
 void scalar_finish_norm(double* v, double p, cudaStream_t s);
+
+// kernels_cplx.cu: the same vector-space kernels for the complex eltypes (n counts complex elements)
+void cvec_fill(int dtype, void* p, int64_t n, double re, double im, cudaStream_t s);
+void cvec_lincomb(int dtype, void* out, int64_t n, int k, const double* c_re_im, const void* const* x,
+                  cudaStream_t s);
+void cvec_hadamard(int dtype, void* out, const void* x, const void* y, int64_t n, int conj_x, cudaStream_t s);
+void cvec_abs(int dtype, void* out_real, const void* x, int64_t n, cudaStream_t s);
+// kind: 0 Re<x,y>, 1 Im<x,y> (<x,y> = sum conj(x) y), 2 sum w|x|^2, 3 sum w|x|, 4 sum w[x!=0],
+// 5 max|x|, 6 min|x|, 7 sum w|x|^p.  w (f64 weights, one per element) may be null; finish as vec_reduce.
+void cvec_reduce(int dtype, int kind, const void* x, const void* y, const double* w, int64_t n, double p,
+                 int finish, double* dev_out, cudaStream_t s);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
 

@@ -5,35 +5,45 @@
 // the device result is bit-identical to oracle/jets_oracle.py on these paths.
 #pragma once
 #include "common.hpp"
+#include "cplx.cuh"
 
 namespace jets {
 
 template <typename T> struct VecOf;
 template <> struct VecOf<float>  { using type = float4;  static constexpr int V = 4; };
 template <> struct VecOf<double> { using type = double2; static constexpr int V = 2; };
+// complex spaces (LDG engine only): one 128-bit vector = 2 ComplexF32 or 1 ComplexF64
+template <> struct VecOf<Cx<float>>  { using type = float4;  static constexpr int V = 2; };
+template <> struct VecOf<Cx<double>> { using type = double2; static constexpr int V = 1; };
 
 // HEAVY=false instantiations only know x^2 (the transcendental bodies, double-precision pow in
 // particular, are hundreds of instructions and would evict the streaming loop from the I-cache).
 template <typename T, bool HEAVY>
 __device__ __forceinline__ T pw_phi(int fn, T x, T p) {
-  if (!HEAVY) return x * x;
-  switch (fn) {
-    case JETS_PW_SQUARE: return x * x;
-    case JETS_PW_POWER:  return pow(x, p);
-    case JETS_PW_EXP:    return exp(x);
-    case JETS_PW_SIN:    return sin(x);
-    default:             return tanh(x);
+  if constexpr (!HEAVY) {
+    return x * x;
+  } else {
+    switch (fn) {
+      case JETS_PW_SQUARE: return x * x;
+      case JETS_PW_POWER:  return pow(x, p);
+      case JETS_PW_EXP:    return exp(x);
+      case JETS_PW_SIN:    return sin(x);
+      default:             return tanh(x);
+    }
   }
 }
 template <typename T, bool HEAVY>
 __device__ __forceinline__ T pw_dphi(int fn, T x, T p) {
-  if (!HEAVY) return T(2) * x;
-  switch (fn) {
-    case JETS_PW_SQUARE: return T(2) * x;
-    case JETS_PW_POWER:  return p * pow(x, p - T(1));
-    case JETS_PW_EXP:    return exp(x);
-    case JETS_PW_SIN:    return cos(x);
-    default: { T t = tanh(x); return T(1) - t * t; }
+  if constexpr (!HEAVY) {
+    return T(2) * x;
+  } else {
+    switch (fn) {
+      case JETS_PW_SQUARE: return T(2) * x;
+      case JETS_PW_POWER:  return p * pow(x, p - T(1));
+      case JETS_PW_EXP:    return exp(x);
+      case JETS_PW_SIN:    return cos(x);
+      default: { T t = tanh(x); return T(1) - t * t; }
+    }
   }
 }
 
@@ -61,17 +71,32 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
     const CStage st = load_stage(stages + s);
     switch (st.op) {
       case S_SCALE: {
-        const T c = (T)st.c0;
+        if constexpr (IsCx<T>::value) {   // real a times a complex vector scales both parts
+          using R = typename IsCx<T>::real;
+          const R c = (R)st.c0;
 #pragma unroll
-        for (int i = 0; i < NV; ++i)
+          for (int i = 0; i < NV; ++i)
 #pragma unroll
-          for (int w = 0; w < W; ++w) val[i][w] = c * val[i][w];
+            for (int w = 0; w < W; ++w) val[i][w] = mulr(c, val[i][w]);
+        } else {
+          const T c = (T)st.c0;
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int w = 0; w < W; ++w) val[i][w] = c * val[i][w];
+        }
       } break;
       case S_DIAG: {
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
           T b[W];
           ld(sidx, i, b);
+          if constexpr (IsCx<T>::value) {
+            if (st.fn & kConjFlag) {
+#pragma unroll
+              for (int w = 0; w < W; ++w) b[w] = conj(b[w]);
+            }
+          }
 #pragma unroll
           for (int w = 0; w < W; ++w) val[i][w] = b[w] * val[i][w];
         }
@@ -90,8 +115,17 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
         for (int i = 0; i < NV; ++i) {
           T b[W];
           ld(sidx, i, b);
+          if constexpr (IsCx<T>::value) {   // adjoint of the Jacobian: conj(phi'(mo)) .* d
 #pragma unroll
-          for (int w = 0; w < W; ++w) val[i][w] = pw_dphi<T, HEAVY>(st.fn, b[w], p) * val[i][w];
+            for (int w = 0; w < W; ++w) {
+              T j = pw_dphi<T, HEAVY>(st.fn & ~kConjFlag, b[w], p);
+              if (st.fn & kConjFlag) j = conj(j);
+              val[i][w] = j * val[i][w];
+            }
+          } else {
+#pragma unroll
+            for (int w = 0; w < W; ++w) val[i][w] = pw_dphi<T, HEAVY>(st.fn, b[w], p) * val[i][w];
+          }
         }
         ++sidx;
       } break;
@@ -140,6 +174,17 @@ __device__ __forceinline__ void eval_term(const CStage* __restrict__ stages, int
 #pragma unroll
           for (int w = 0; w < W; ++w) val[i][w] = -val[i][w];
       } break;
+      case S_CSCALE: {  // complex a: (c0 of this stage) + i (c0 of the S_CIMAG stage that follows)
+        if constexpr (IsCx<T>::value) {
+          using R = typename IsCx<T>::real;
+          const T c((R)st.c0, (R)load_stage(stages + s + 1).c0);
+#pragma unroll
+          for (int i = 0; i < NV; ++i)
+#pragma unroll
+            for (int w = 0; w < W; ++w) val[i][w] = c * val[i][w];
+        }
+      } break;
+      case S_CIMAG: break;
       default: {  // S_ZERO
 #pragma unroll
         for (int i = 0; i < NV; ++i)

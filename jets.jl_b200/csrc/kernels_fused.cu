@@ -142,6 +142,16 @@ struct SmemLoader {
   }
 };
 
+template <typename T> __device__ __forceinline__ T ldg1(const T* p) { return __ldg(p); }
+template <> __device__ __forceinline__ Cx<float> ldg1(const Cx<float>* p) {
+  const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+  return Cx<float>(v.x, v.y);
+}
+template <> __device__ __forceinline__ Cx<double> ldg1(const Cx<double>* p) {
+  const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+  return Cx<double>(v.x, v.y);
+}
+
 template <typename T, int HL, int HR, int NV>
 struct GlobalLoader {
   using Vec = typename VecOf<T>::type;
@@ -160,17 +170,17 @@ struct GlobalLoader {
       for (int j = 0; j < V; ++j) out[HL + j] = vs[j];
     } else {
 #pragma unroll
-      for (int j = 0; j < V; ++j) out[HL + j] = (p + j < len) ? __ldg(base + p + j) : T(0);
+      for (int j = 0; j < V; ++j) out[HL + j] = (p + j < len) ? ldg1(base + p + j) : T(0);
     }
 #pragma unroll
     for (int j = 0; j < HL; ++j) {
       const int64_t q = p - HL + j;
-      out[j] = (q >= 0 && q < len) ? __ldg(base + q) : T(0);
+      out[j] = (q >= 0 && q < len) ? ldg1(base + q) : T(0);
     }
 #pragma unroll
     for (int j = 0; j < HR; ++j) {
       const int64_t q = p + V + j;
-      out[HL + V + j] = (q < len) ? __ldg(base + q) : T(0);
+      out[HL + V + j] = (q < len) ? ldg1(base + q) : T(0);
     }
   }
 };
@@ -485,6 +495,26 @@ void launch_one(const DevFused& f, const FusedParams& P, cudaStream_t s) {
   count_launch();
 }
 
+// Complex spaces run on the LDG engine only (the TMA engines are not instantiated for them).
+template <typename T, int HL, int HR>
+void launch_ldg_only(const FusedParams& P, cudaStream_t s) {
+  const int64_t Q = P.nitems * P.S;
+  int64_t grid = (int64_t)ctx().sm_count * 8;
+  if (grid > Q) grid = Q > 0 ? Q : 1;
+  jets_fused_ldg_kernel<T, HL, HR, false><<<(unsigned)grid, kLdgThreads, 0, s>>>(P);
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
+template <typename T>
+void launch_halo_cplx(const DevFused& f, const FusedParams& P, cudaStream_t s) {
+  JETS_CHECK(!f.use_tma && !f.heavy, JETS_ERR_UNSUPPORTED, "internal: complex plans run on the LDG engine");
+  if (f.hl == 0 && f.hr == 0) launch_ldg_only<T, 0, 0>(P, s);
+  else if (f.hl == 0 && f.hr == 1) launch_ldg_only<T, 0, 1>(P, s);
+  else if (f.hl == 1 && f.hr == 0) launch_ldg_only<T, 1, 0>(P, s);
+  else if (f.hl == 1 && f.hr == 1) launch_ldg_only<T, 1, 1>(P, s);
+  else JETS_FAIL(JETS_ERR_UNSUPPORTED, "fused halo (%d,%d) not instantiated", f.hl, f.hr);
+}
+
 template <typename T, bool HEAVY>
 void launch_halo(const DevFused& f, const FusedParams& P, cudaStream_t s) {
   if (f.hl == 0 && f.hr == 0) launch_one<T, 0, 0, HEAVY>(f, P, s);
@@ -511,7 +541,9 @@ void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaS
   P.order = f.order;
   P.nsegs = f.nsegs; P.nslots = fused_nslots(f.slot_streams); P.slot_streams = f.slot_streams;
   P.S = f.S; P.nitems = f.nitems; P.in = in; P.out = out;
-  if (dtype == JETS_F32) {
+  if (dtype == JETS_C64) launch_halo_cplx<Cx<float>>(f, P, s);
+  else if (dtype == JETS_C128) launch_halo_cplx<Cx<double>>(f, P, s);
+  else if (dtype == JETS_F32) {
     if (f.heavy) launch_halo<float, true>(f, P, s); else launch_halo<float, false>(f, P, s);
   } else {
     if (f.heavy) launch_halo<double, true>(f, P, s); else launch_halo<double, false>(f, P, s);

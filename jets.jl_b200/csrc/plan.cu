@@ -9,6 +9,7 @@
 //     reference evaluates it (zeros(range(op)) per composite stage, :525-539).
 #include <algorithm>
 #include "common.hpp"
+#include "cplx.cuh"
 
 namespace jets {
 
@@ -49,6 +50,7 @@ int chain_streams(const std::vector<FStage>& ch) {
 
 bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp);
 thread_local size_t g_esz = 8;  // element size of the plan being built
+thread_local bool g_cplx = false;  // complex eltype: adjoint stages conjugate their operand stream
 
 bool has_stencil(const Entry& e) {
   for (auto& s : e.chain)
@@ -162,13 +164,19 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
   switch (a->kind) {
     case K_DIAG: {
       Entry e;
-      e.chain.push_back(mk(S_DIAG, 0, a->w->ptr()));
+      // df'!: m .= conj(w) .* d (fixture JopFoo, test/runtests.jl:4); conj is the identity on reals
+      e.chain.push_back(mk(S_DIAG, (g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0, a->w->ptr()));
       out.push_back(e);
       return true;
     }
     case K_SCALE: {
       Entry e;
-      e.chain.push_back(mk(S_SCALE, 0, nullptr, a->a));
+      if (g_cplx && a->ai != 0.0) {   // _constdiag_df'!: m .= conj(a) .* d (src/Jets.jl:1160)
+        e.chain.push_back(mk(S_CSCALE, 0, nullptr, a->a));
+        e.chain.push_back(mk(S_CIMAG, 0, nullptr, mode == JETS_MODE_DFT ? -a->ai : a->ai));
+      } else {
+        e.chain.push_back(mk(S_SCALE, 0, nullptr, a->a));
+      }
       out.push_back(e);
       return true;
     }
@@ -180,7 +188,7 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
       } else {
         JETS_CHECK(a->mo != nullptr, JETS_ERR_NO_POINT,
                    "Jacobian of a pointwise operator applied before point!/jacobian set mo");
-        e.chain.push_back(mk(S_PW_J, a->fn, a->mo->ptr(), a->p));
+        e.chain.push_back(mk(S_PW_J, a->fn | ((g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0), a->mo->ptr(), a->p));
       }
       out.push_back(e);
       return true;
@@ -353,7 +361,7 @@ struct Builder {
       for (size_t r = 0; r < out_sp.len.size(); ++r)
         if (((dst.off + oo[r]) * esz) % 16) tma = false;
     }
-    if (engine == 2) tma = false;
+    if (engine == 2 || is_cplx(dtype)) tma = false;   // complex spaces: LDG engine (generic interpreter)
     all_fast = all_fast && tma;
     // Fast-kernel shape (measured on B200, profiles/README.md): 16 consumer warps x 2 vectors per
     // thread (16 KB tiles) amortises the per-slot work best -- 81% of HBM peak on config 5, 98% on
@@ -395,7 +403,7 @@ struct Builder {
         for (const FStage& s : e.chain) {
           t.stages.push_back(s);
           if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
-          if ((s.op == S_PW_F || s.op == S_PW_J) && s.fn != JETS_PW_SQUARE) heavy = true;
+          if ((s.op == S_PW_F || s.op == S_PW_J) && (s.fn & ~kConjFlag) != JETS_PW_SQUARE) heavy = true;
         }
         tm.stage_end = (int32_t)t.stages.size();
         tm.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
@@ -437,6 +445,7 @@ struct Builder {
       t.rows.push_back(row);
     }
     if ((all_fast ? fast_nslots(variant, t.max_streams) : fused_nslots(t.max_streams)) < 2) tma = false;
+    if (is_cplx(dtype)) tma = false;
     t.tma_ok = tma;
     bool use_tma = tma;
     if (engine == 2) use_tma = false;
@@ -1036,6 +1045,7 @@ Plan::~Plan() {
 std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok, int engine) {
   auto plan = std::make_shared<Plan>();
   g_esz = dsize(a->dtype);
+  g_cplx = is_cplx(a->dtype);
   Builder b{*plan, a->dtype, io_ok, engine};
   int acc = ACC_SET;
   if (accumulate) {
@@ -1079,7 +1089,8 @@ void run_plan(Plan& p, int dtype, char* in, char* out) {
       case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;
       case ST_GEMM_TC: launch_gemm_tc(st, base(st.src), base(st.dst), c.stream); break;
       case ST_FILL0:
-        vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);
+        if (is_cplx(dtype)) cvec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, 0.0, c.stream);
+        else vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);
         break;
     }
   }

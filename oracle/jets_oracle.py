@@ -43,7 +43,7 @@ __all__ = [
     "dot", "norm", "extrema", "fill_", "to_array", "to_matrix", "dot_product_test",
     "linearity_test", "linearization_test", "zeros", "ones", "rand", "randn", "Array", "vec",
     "close", "perfstat", "JopDiagonal", "JopPointwise", "JopStencil", "JopDense", "JopScale",
-    "bmap", "PW_FUNCS",
+    "bmap", "PW_FUNCS", "JetSSpace", "SymmetricArray", "symspace",
 ]
 
 
@@ -268,8 +268,112 @@ def bmap(f: Callable, *args):
     return BlockArray(out, ref.indices)
 
 
+# --------------------------------------------------------------------------------------
+# Symmetric spaces / arrays                                         src/Jets.jl:405-516
+# --------------------------------------------------------------------------------------
+class JetSSpace(JetAbstractSpace):
+    """``JetSSpace(T, n, M, map)`` (:408-441): logical size n, stored parent of size M; ``map``
+    takes the (1-based) index tuple of a position beyond the parent and returns the index of the
+    stored element whose conjugate it is."""
+
+    def __init__(self, T, n, M, map):
+        self.T = np.dtype(T)
+        self.n = tuple(int(k) for k in n)
+        self.M = tuple(int(k) for k in M)
+        self.map = map
+
+    def __eq__(self, o):
+        return isinstance(o, JetSSpace) and self.T == o.T and self.n == o.n and self.M == o.M and self.map is o.map
+
+    def __hash__(self):
+        return hash((self.T, self.n, self.M))
+
+    eltype = property(lambda s: s.T)
+    ndims = property(lambda s: len(s.n))
+
+    def size(self, i=None):  # :437
+        return self.n if i is None else self.n[i - 1]
+
+    def __len__(self):
+        return int(np.prod(self.n, dtype=np.int64))
+
+    def similar(self, *dims):  # :441-442
+        if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+            dims = tuple(dims[0])
+        return JetSSpace(self.T, dims, self.M, self.map)
+
+
+def symspace():  # :443
+    return None
+
+
+class SymmetricArray:
+    """``SymmetricArray`` (:445-484): parent ``A`` (size M), logical size ``n``; 1-based indexing;
+    ``x[I]`` beyond the parent in any dimension is ``conj(A[map(I)])`` (:455-462) and assignment
+    there stores ``conj(v)`` (:470-478).  Linear indices are column-major over ``n`` (:465-468)."""
+
+    def __init__(self, A, n, map):
+        self.A = A
+        self.n = tuple(n)
+        self.map = map
+
+    dtype = property(lambda s: s.A.dtype)
+    shape = property(lambda s: s.n)
+
+    def parent(self):  # :449
+        return self.A
+
+    def _cart(self, I):
+        if isinstance(I, tuple):
+            return tuple(int(k) for k in I)
+        return tuple(int(k) + 1 for k in np.unravel_index(int(I) - 1, self.n, order="F"))
+
+    def __getitem__(self, I):
+        I = self._cart(I)
+        for d in range(len(self.n)):
+            if I[d] > self.A.shape[d]:
+                J = self.map(I)
+                return np.conj(self.A[tuple(j - 1 for j in J)])
+        return self.A[tuple(i - 1 for i in I)]
+
+    def __setitem__(self, I, v):
+        I = self._cart(I)
+        for d in range(len(self.n)):
+            if I[d] > self.A.shape[d]:
+                J = self.map(I)
+                self.A[tuple(j - 1 for j in J)] = np.conj(v)
+                return
+        self.A[tuple(i - 1 for i in I)] = v
+
+    def full(self):
+        """collect(x): every logical entry through getindex."""
+        out = np.empty(self.n, dtype=self.dtype, order="F")
+        for I in np.ndindex(*self.n):
+            out[I] = self[tuple(i + 1 for i in I)]
+        return out
+
+    # broadcast acts on the parents (:486-508)
+    def _b(self, o, f):
+        return SymmetricArray(f(self.A, o.A if isinstance(o, SymmetricArray) else o), self.n, self.map)
+
+    def __add__(self, o): return self._b(o, lambda a, b: a + b)
+    __radd__ = __add__
+    def __sub__(self, o): return self._b(o, lambda a, b: a - b)
+    def __mul__(self, o): return self._b(o, lambda a, b: a * b)
+    __rmul__ = __mul__
+
+    def assign(self, o):  # copyto!(dest::SymmetricArray, bc) :503-507
+        self.A[...] = o.A if isinstance(o, SymmetricArray) else o
+        return self
+
+    def similar(self):  # :480-482
+        return SymmetricArray(np.empty_like(self.A), self.n, self.map)
+
+
 def space(x, iblock=None):
     """space(x::AbstractArray) :126; space(x::BlockArray) :814; space(R, iblock) :799."""
+    if isinstance(x, SymmetricArray):  # :447
+        return JetSSpace(x.dtype, x.n, x.A.shape, x.map)
     if isinstance(x, JetBSpace):
         return x.spaces[iblock - 1]
     if isinstance(x, BlockArray):
@@ -281,6 +385,8 @@ def _factory(kind):
     def make(R, rng=None):
         if isinstance(R, JetBSpace):  # :922-924
             return BlockArray([make(s, rng) for s in R.spaces], R.indices)
+        if isinstance(R, JetSSpace):  # :510-513: the factory acts on the parent shape M
+            return SymmetricArray(make(JetSpace(R.T, *R.M), rng), R.n, R.map)
         shp = R.n
         if kind == "zeros":
             return np.zeros(shp, dtype=R.T, order="F")
@@ -328,7 +434,10 @@ def setblock_(x, iblock, xblock):  # :916, :920
 
 
 def norm(x, p=2):
-    """norm(x::BlockArray, p) (:834-848): per-block stdlib norm, combined per p."""
+    """norm(x::BlockArray, p) (:834-848): per-block stdlib norm, combined per p.  A SymmetricArray
+    has no norm method of its own: the generic AbstractArray norm iterates the logical array."""
+    if isinstance(x, SymmetricArray):
+        return _norm1(x.full(), p)
     if not isinstance(x, BlockArray):
         return _norm1(x, p)
     if p == math.inf:

@@ -67,3 +67,37 @@ def test_block_space_indices_match_reference_rule():
         assert mk.indices(R, 2) == (3, 6) and mk.space(R, 3) == mk.JetSpace(np.float64, 2, 3)
         assert R == mk.JetBSpace([mk.JetSpace(np.float64, 2), mk.JetSpace(np.float64, 2, 2), mk.JetSpace(np.float64, 2, 3)])
         assert R.similar((0,)) == mk.JetSpace(np.float64, (0,))
+
+
+def _indexmap(I):  # test/runtests.jl:219-225
+    return tuple(I) if I[0] < 5 else (I[0] - 4, I[1])
+
+
+def test_symmetric_space_bookkeeping_matches_the_oracle():
+    """JetSSpace host logic (src/Jets.jl:408-484): storage offset / conjugation of every logical
+    index and the multiplicity table behind norm() agree with the oracle's SymmetricArray."""
+    import jets_b200 as B
+    from oracle import jets_oracle as J
+    Rb = B.JetSSpace(np.complex128, (8, 4), (4, 4), _indexmap)
+    Ro = J.JetSSpace(np.complex128, (8, 4), (4, 4), _indexmap)
+    assert Rb.size() == (8, 4) and len(Rb) == 32 and Rb._block_lens() == [16] and Rb.eltype == np.complex128
+    assert Rb.similar((0, 0)).n == (0, 0) and Rb.similar((0, 0)).M == Rb.M
+    g = np.random.default_rng(3)
+    x = J.rand(Ro, g)
+    P = x.A.reshape(-1, order="F")
+    for i1 in range(1, 9):
+        for i2 in range(1, 5):
+            off, cj = Rb._parent_linear((i1, i2))
+            assert (np.conj(P[off]) if cj else P[off]) == x[(i1, i2)]
+    w = Rb.multiplicity()
+    assert w.shape == (16,) and np.all(w == 2.0)
+    for p in (1, 2, 3.5):
+        assert np.isclose(np.sum(w * np.abs(P) ** p) ** (1 / p), J.norm(x, p), rtol=1e-14)
+
+
+def test_complex_eltypes_are_in_the_abi():
+    import jets_b200 as B
+    from jets_b200 import _lib as L
+    assert (L.F32, L.F64, L.C64, L.C128) == (0, 1, 2, 3)
+    src = open(HEADER).read()
+    assert "JETS_C64 = 2" in src and "JETS_C128 = 3" in src

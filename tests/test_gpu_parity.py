@@ -651,8 +651,12 @@ def test_shape_and_dtype_errors(D):
     assert e.value.code == 3
     with pytest.raises(B.JetsError):
         B.compose(A, B.JopDiagonal(np.ones(9)))
-    with pytest.raises(B.JetsError):
-        B.JetSpace(np.complex128, 4) and B.zeros(B.JetSpace(np.complex128, 4))
+    with pytest.raises(B.JetsError) as e:
+        B.zeros(B.JetSpace(np.int32, 4))          # eltypes outside Float32/64, ComplexF32/64
+    assert e.value.code == 3
+    with pytest.raises(B.JetsError) as e:         # a complex vector through a real operator
+        B.mul_(B.zeros(B.JetSpace(np.complex128, 8)), A, B.ones(B.JetSpace(np.complex128, 8)))
+    assert e.value.code == 3
 
 
 def test_device_rand_is_partition_invariant(D):

@@ -458,6 +458,51 @@ def test_dot_product_linearity_linearization(g):  # :901-930
     assert np.isclose(muobs.max(), muexp.max(), rtol=1e-6)
 
 
+# ---- symmetric spaces: runtests.jl:219-282 ---------------------------------------------------
+def indexmap(I):  # runtests.jl:219-225 (1-based index tuple in, index tuple out)
+    if I[0] < 5:
+        return tuple(I)
+    return (I[0] - 4, I[1])
+
+
+def test_symmetric_space(g):  # :227-258
+    R = J.JetSSpace(np.complex128, (8, 4), (4, 4), indexmap)
+    assert R.size() == (8, 4) and R.eltype == np.complex128
+    assert np.array_equal(J.ones(R).full().real, np.ones((8, 4))) and np.array_equal(J.ones(R).full().imag, np.zeros((8, 4)))
+    assert np.array_equal(J.zeros(R).full(), np.zeros((8, 4)))
+    assert J.rand(R, g).shape == (8, 4) and J.Array(R).shape == (8, 4) and J.Array(R).dtype == np.complex128
+    x = J.rand(R, g)
+    z = x.similar()
+    assert isinstance(z, J.SymmetricArray) and z.shape == (8, 4)
+    y = x.A
+    assert np.isclose(J.norm(x), math.sqrt(2 * np.linalg.norm(y) ** 2), rtol=1e-14)
+    assert np.isclose(J.norm(x, 2), J.norm(x), rtol=1e-15)
+    assert np.isclose(J.norm(x, 1), 2 * np.sum(np.abs(y)), rtol=1e-14)
+    assert np.isclose(J.norm(x, math.inf), np.max(np.abs(y)), rtol=1e-15)
+    x[1, 1] = 0
+    x[6, 1] = 0
+    assert J.norm(x, 0) == 2 * np.count_nonzero(y)
+    assert J.space(J.rand(R, g)) == R
+    assert R.similar((0, 0)).n == (0, 0) and R.similar((0, 0)).M == R.M
+    for i in range(1, 33):   # linear indices, column-major over the logical size (:252-257)
+        x[i] = i + 1j * i
+        assert x[i] == i + 1j * i
+    # a mirrored position stores the conjugate in the parent (:470-478)
+    x[(7, 2)] = 3 + 4j
+    assert x.A[2, 1] == 3 - 4j and x[(7, 2)] == 3 + 4j and x[(3, 2)] == 3 - 4j
+
+
+def test_symmetric_space_broadcast(g):  # :260-282
+    R = J.JetSSpace(np.complex128, (8, 4), (4, 4), indexmap)
+    u, v, w = J.rand(R, g), J.rand(R, g), J.rand(R, g)
+    a, b, c = g.random(3)
+    x = a * u + b * v + c * w
+    assert isinstance(x, J.SymmetricArray)
+    assert np.array_equal(x.A, a * u.A + b * v.A + c * w.A)
+    y = J.zeros(R).assign(x)
+    assert np.array_equal(y.A, x.A)
+
+
 # ---- the build's own primitives, pinned the way SURVEY §8c prescribes for the stencil -------
 @pytest.mark.parametrize("kind", ["fdiff", "lap"])
 @pytest.mark.parametrize("T", [np.float32, np.float64])
