@@ -31,6 +31,7 @@
 // boxes and each thread gathers its row with conflict-free 4-byte loads; A'*Y stages [col][32 k]
 // boxes (128B swizzle) and each thread reads its own 128-byte row.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <algorithm>
 #include <map>
 #include "common.hpp"
@@ -40,8 +41,8 @@ namespace {
 
 constexpr int BM = 128;            // output rows per tile (= TMEM lanes)
 constexpr int BK = 32;             // k per stage
-constexpr int kAStages = 8;        // matrix ring (HBM latency: 128 KB in flight per SM)
-constexpr int kXStages = 4;        // right-hand-side ring (measured: 6 matrix + 8 right-hand-side stages is 9% slower)
+// Ring depths are template parameters of the kernel (kAStages matrix stages, kXStages right-hand-side
+// stages; both 16 KB).  Measured: 6 + 8 is 9% slower than 8 + 4 -- the matrix ring is what hides HBM latency.
 constexpr int kTStages = 4;        // TMEM operand ring (hi|lo slots of 64 columns), own barriers
 constexpr int kABytes = BM * BK * 4;           // 16 KB
 constexpr int kXBytes = 128 * BK * 4;          // 2*NP rows of 128 B, NP <= 64
@@ -50,7 +51,7 @@ constexpr int kThreads = 512;      // 16 warps: 0-3 epilogue, 4-7 + 12-15 split,
 constexpr int kTmemCols = 512;     // [0,256): 2 accumulator buffers x (main | correction) x 64; [256,512): kTStages A slots x (hi | lo) x 32
 constexpr int kBufCols = 128;
 constexpr int kASlotCol = 256;
-constexpr int kSmemBytes = 1024 /*align slack*/ + kAStages * kABytes + kXStages * kXBytes + 512;
+constexpr int smem_bytes(int a_stages, int x_stages) { return 1024 /*align slack*/ + a_stages * kABytes + x_stages * kXBytes + 1024; }
 
 struct TcParams {
   const DBlock* blocks;
@@ -64,6 +65,7 @@ struct TcParams {
   int32_t trans, acc;
   float* out;
   int32_t expt;               // JETS_B200_TC_EXPT: 1 = skip the a_lo MMAs, 2 = skip all MMAs (timing experiments only)
+  int32_t mixed;              // 1: correction terms on kind::f16 (bf16 operands), see umma_stage_corr_bf16; 0: all three terms tf32
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -136,6 +138,78 @@ __device__ __forceinline__ void umma_stage_tf32(uint32_t d_main, uint32_t d_corr
       "}" ::"r"(d_main), "r"(d_corr), "r"(a_hi), "r"(a_lo), "l"(xdesc), "r"(idesc_main), "r"(idesc_corr), "r"(accumulate)
       : "memory");
 }
+// The same k-stage with the two correction terms evaluated on bf16 operands (kind::f16, K = 16 per
+// MMA): a*x = a_hi*x_hi + bf(a)*bf(x_lo) + bf(a_lo)*bf(x) + O(2^-19 |a x|) with round-to-nearest bf16
+// conversions (zero-mean errors of <= 2^-9 on terms that are <= 2^-10 of the product).  The main term
+// stays tf32 with N = np; the corrections are 4 bf16 MMAs of N = np instead of the tf32 path's
+// 4 x (N = np extra columns) + 4 x (N = np): 256 tensor-pipe cycles per stage instead of 384, and a
+// third less operand traffic out of shared memory.
+//   TMEM operand slot (64 columns): [0,32) a_hi tf32 k 0..31 | [32,40) bf(a_lo) k 0..15 | [40,48) bf(a) k 0..15
+//                                   | [48,56) bf(a_lo) k 16..31 | [56,64) bf(a) k 16..31     (two bf16 per column)
+//   X slot rows [np,2np) (128 B each): bf(x) k 0..31 | bf(x_lo) k 0..31
+__device__ __forceinline__ void umma_stage_main_tf32(uint32_t d_main, uint32_t a_slot, uint64_t xdesc, uint32_t idesc_tf32,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .b64 x1, x2, x3;\n\t"
+      ".reg .b32 h1, h2, h3;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\t"
+      "setp.ne.b32 p1, %3, 0;\n\t"          // always true
+      "add.s64 x1, %2, 2;\n\t"
+      "add.s64 x2, %2, 4;\n\t"
+      "add.s64 x3, %2, 6;\n\t"
+      "add.u32 h1, %1, 8;\n\t"
+      "add.u32 h2, %1, 16;\n\t"
+      "add.u32 h3, %1, 24;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h1], x1, %3, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h2], x2, %3, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [h3], x3, %3, p1;\n\t"
+      "}" ::"r"(d_main), "r"(a_slot), "l"(xdesc), "r"(idesc_tf32), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_stage_corr_bf16(uint32_t d_corr, uint32_t a_slot, uint64_t xbdesc, uint32_t idesc_bf16,
+                                                     uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p0, p1;\n\t"
+      ".reg .b64 b1, b2, b3;\n\t"
+      ".reg .b32 c0, c1, c2, c3;\n\t"
+      "setp.ne.b32 p0, %4, 0;\n\t"
+      "setp.ne.b32 p1, %3, 0;\n\t"          // always true
+      "add.s64 b1, %2, 4;\n\t"              // bf(x_lo) k 0..15   (+64 B)
+      "add.s64 b2, %2, 2;\n\t"              // bf(x)    k 16..31  (+32 B)
+      "add.s64 b3, %2, 6;\n\t"              // bf(x_lo) k 16..31  (+96 B)
+      "add.u32 c0, %1, 32;\n\t"
+      "add.u32 c1, %1, 40;\n\t"
+      "add.u32 c2, %1, 48;\n\t"
+      "add.u32 c3, %1, 56;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [c0], %2, %3, p0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [c1], b1, %3, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [c2], b2, %3, p1;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [c3], b3, %3, p1;\n\t"
+      "}" ::"r"(d_corr), "r"(a_slot), "l"(xbdesc), "r"(idesc_bf16), "r"(accumulate)
+      : "memory");
+}
+// One lane of a fully converged warp (CUTLASS's elect_one_sync): the compiler knows the branch it
+// guards runs in a single thread and predicates the uniform-datapath instructions directly.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xFFFFFFFF;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}" : "=r"(pred));
+  return pred != 0;
+}
+// two floats -> packed bf16x2, round to nearest even; `lo` lands in bits [0,16) (the lower k index)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -173,6 +247,11 @@ __device__ __forceinline__ uint32_t make_idesc(int n) {
   return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 }
 
+// The same for kind::f16 with bf16 operands: A = B = BF16 (format code 1).
+__device__ __forceinline__ uint32_t make_idesc_bf16(int n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+}
+
 __device__ __forceinline__ int find_group(const int32_t* tile_ptr, int ngroups, int tile) {
   int lo = 0, hi = ngroups - 1;
   while (lo < hi) {
@@ -182,18 +261,21 @@ __device__ __forceinline__ int find_group(const int32_t* tile_ptr, int ngroups, 
   return lo;
 }
 
+template <int kAStages, int kXStages>
 __global__ void __launch_bounds__(kThreads, 1)
 jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) {
+  static_assert(kAStages <= 16 && kXStages <= 16, "barrier arrays hold 16 stages");
   extern __shared__ unsigned char smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;           // 128B-swizzle atoms need 1024-byte alignment
   unsigned char* sbase = smem_raw + (base - raw);
   const uint32_t a0 = base, x0 = base + kAStages * kABytes;
   const uint32_t bars = x0 + kXStages * kXBytes;
-  const uint32_t a_full0 = bars, a_empty0 = bars + 64, x_full0 = bars + 128, x_empty0 = bars + 192, t_ready0 = bars + 256,
-                 mma_done0 = bars + 288, acc_full0 = bars + 320, acc_empty0 = bars + 336;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAStages * kABytes + kXStages * kXBytes + 384);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t a_full0 = bars, a_empty0 = bars + 128, x_full0 = bars + 256, x_empty0 = bars + 384, t_ready0 = bars + 512,
+                 mma_done0 = bars + 544, acc_full0 = bars + 576, acc_empty0 = bars + 592;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(sbase + kAStages * kABytes + kXStages * kXBytes + 640);
+  // warp-uniform by construction (shuffle from lane 0), so that everything the MMA issuers derive from it can live in uniform registers
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kAStages; ++s) {
@@ -202,14 +284,14 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
     }
     for (int s = 0; s < kXStages; ++s) {
       mbar_init(x_full0 + 8 * s, 1);
-      mbar_init(x_empty0 + 8 * s, 1);
+      mbar_init(x_empty0 + 8 * s, 2);     // both MMA issuers commit
     }
     for (int s = 0; s < kTStages; ++s) {
       mbar_init(t_ready0 + 8 * s, 8);
-      mbar_init(mma_done0 + 8 * s, 1);
+      mbar_init(mma_done0 + 8 * s, 2);
     }
     for (int b = 0; b < 2; ++b) {
-      mbar_init(acc_full0 + 8 * b, 1);
+      mbar_init(acc_full0 + 8 * b, 2);
       mbar_init(acc_empty0 + 8 * b, 4);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -221,7 +303,7 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
   const int np = P.np;
 
   if (warp == 8) {
@@ -278,11 +360,23 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         }
       }
     }
-  } else if (warp == 10) {
-    // =============================== MMA issuer =================================
+  } else if (warp == 10 || warp == 11) {
+    // =============================== MMA issuers ================================
+    // Two warps run the same control flow and issue disjoint accumulator chains: warp 10 the main
+    // term (columns [0,np) of the buffer; in the all-tf32 mode the whole stage), warp 11 the bf16
+    // corrections (columns [np,2np)).  ncu showed ONE issuing lane as the kernel's narrowest point
+    // (~150 dependent single-lane instructions per k-stage, ~1100 cycles, against 256 tensor-pipe
+    // cycles and ~700 cycles of HBM time); two issuers, an elect.sync leader (no per-instruction
+    // "any thread left?" loop around the uniform-datapath MMAs) and hoisted descriptors cut that.
+    // Ring slots and accumulator chunks are committed by both warps (their barriers count 2).
+    const bool corr_warp = warp == 11;
     const uint32_t idesc_main = make_idesc(2 * np);   // a_hi x [x_hi | x_lo]
-    const uint32_t idesc_corr = make_idesc(np);       // a_lo x x_hi
+    const uint32_t idesc_corr = make_idesc(np);       // a_lo x x_hi, or the N = np main term of the mixed mode
+    const uint32_t idesc_bf16 = make_idesc_bf16(np);  // mixed mode: bf16 corrections
     const uint64_t xdesc0 = make_desc_k128(x0);       // X slot s: start-address field += s * kXBytes / 16
+    const uint64_t xb_off = (uint64_t)((np * 128) >> 4);   // rows [np, 2np) of an X slot
+    const bool leader = elect_one();
+    const int mixed = P.mixed, expt = P.expt;
     uint32_t it = 0, cn = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
       const int g = find_group(P.tile_ptr, P.ngroups, tile);
@@ -295,22 +389,30 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
           const int buf = cn & 1;
           mbar_wait(acc_empty0 + 8 * buf, ((cn >> 1) & 1) ^ 1);
           // columns [0,np): a_hi*x_hi (the main term, ONE truncating accumulate per k-step);
-          // columns [np,2np): a_hi*x_lo + a_lo*x_hi (2^-11 smaller, so its rounding does not matter)
+          // columns [np,2np): the two correction terms (2^-11 smaller, so their rounding does not matter)
           const uint32_t d_tmem = tmem_base + buf * kBufCols;
           for (int kc = c0; kc < c1; ++kc, ++it) {
             const int s = it % kXStages, t = it % kTStages;
             mbar_wait(x_full0 + 8 * s, (it / kXStages) & 1);
             mbar_wait(t_ready0 + 8 * t, (it / kTStages) & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (lane == 0) {
+            if (leader) {
               const uint32_t a_hi = tmem_base + kASlotCol + t * 64;
-              if (P.expt == 0)
-                umma_stage_tf32(d_tmem, d_tmem + np, a_hi, a_hi + 32, xdesc0 + (uint64_t)(s * (kXBytes >> 4)), idesc_main, idesc_corr,
-                                kc > c0 ? 1u : 0u);
-              else if (P.expt == 1) {
+              const uint64_t xd = xdesc0 + (uint64_t)(s * (kXBytes >> 4));
+              const uint32_t accf = kc > c0 ? 1u : 0u;
+              if (expt == 0) {
+                if (mixed) {
+                  if (!corr_warp) umma_stage_main_tf32(d_tmem, a_hi, xd, idesc_corr, accf);
+                  else umma_stage_corr_bf16(d_tmem + np, a_hi, xd + xb_off, idesc_bf16, accf);
+                } else if (!corr_warp) {
+                  umma_stage_tf32(d_tmem, d_tmem + np, a_hi, a_hi + 32, xd, idesc_main, idesc_corr, accf);
+                }
+              } else if (expt == 3 && !corr_warp) {   // timing experiment: only the four N = np tf32 main MMAs
+                umma_stage_main_tf32(d_tmem, a_hi, xd, idesc_corr, accf);
+              } else if (expt == 1 && !corr_warp) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
-                  umma_tf32_ts(d_tmem, a_hi + ks * 8, xdesc0 + (uint64_t)(s * (kXBytes >> 4) + 2 * ks), idesc_main, (kc > c0 || ks > 0) ? 1u : 0u);
+                  umma_tf32_ts(d_tmem, a_hi + ks * 8, xd + (uint64_t)(2 * ks), idesc_main, (kc > c0 || ks > 0) ? 1u : 0u);
               }
               umma_commit(x_empty0 + 8 * s);                       // right-hand-side slot free once the MMAs retire
               umma_commit(mma_done0 + 8 * t);                      // TMEM operand slot likewise
@@ -321,7 +423,7 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         }
       }
     }
-  } else if (warp >= 4 && warp != 11) {
+  } else if (warp >= 4) {
     // =============================== split A into TMEM (warps 4-7 and 12-15) =====
     // Two warps per TMEM lane quarter: warps 4-7 take k columns [0,16) of the stage, warps 12-15
     // columns [16,32) -- one warp per quarter could not split a stage as fast as HBM delivers it.
@@ -354,11 +456,23 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
 #pragma unroll
             for (int k = 0; k < 16; ++k) hi[k] = col[k * 32];
           }
+          if (P.mixed) {
+            // lo[0,8) = bf(a_lo) pairs, lo[8,16) = bf(a) pairs of this thread's 16 k
 #pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const uint32_t a = hi[k];
-            hi[k] = a & 0xFFFFE000u;
-            lo[k] = __float_as_uint(__uint_as_float(a) - __uint_as_float(hi[k])) & 0xFFFFE000u;
+            for (int k = 0; k < 16; k += 2) {
+              const float a0 = __uint_as_float(hi[k]), a1 = __uint_as_float(hi[k + 1]);
+              const uint32_t h0 = hi[k] & 0xFFFFE000u, h1 = hi[k + 1] & 0xFFFFE000u;
+              lo[k >> 1] = pack_bf16x2(a0 - __uint_as_float(h0), a1 - __uint_as_float(h1));
+              lo[8 + (k >> 1)] = pack_bf16x2(a0, a1);
+              hi[k] = h0; hi[k + 1] = h1;
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+              const uint32_t a = hi[k];
+              hi[k] = a & 0xFFFFE000u;
+              lo[k] = __float_as_uint(__uint_as_float(a) - __uint_as_float(hi[k])) & 0xFFFFE000u;
+            }
           }
           __syncwarp();
           if (lane == 0) mbar_arrive(a_empty0 + 8 * sa);            // the shared-memory slot can be refilled
@@ -374,8 +488,6 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
         }
       }
     }
-  } else if (warp == 11) {
-    // idle
   } else {
     // =============================== epilogue (warps 0-3) =======================
     float acc[64];
@@ -442,7 +554,7 @@ jets_gemm_tc_kernel(const TcParams P, const __grid_constant__ CUtensorMap xmap) 
 // Right-hand sides -> the split buffer: xs[n][koff + k] = hi(x[k + n*kdim]), xs[np + n][...] = lo.
 struct SplitSeg { int64_t in_off; int32_t kdim, koff; };
 __global__ void split_rhs_kernel(const float* __restrict__ in, float* __restrict__ xs, const SplitSeg* __restrict__ segs,
-                                 int nsegs, int64_t kp, int np, int nrhs, int n0, int nrhs_total) {
+                                 int nsegs, int64_t kp, int np, int nrhs, int n0, int nrhs_total, int mixed) {
   const int seg = blockIdx.y;
   const SplitSeg sg = segs[seg];
   const int64_t total = (int64_t)sg.kdim * nrhs;
@@ -453,7 +565,14 @@ __global__ void split_rhs_kernel(const float* __restrict__ in, float* __restrict
     const uint32_t h = __float_as_uint(x) & 0xFFFFE000u;
     const uint32_t l = __float_as_uint(x - __uint_as_float(h)) & 0xFFFFE000u;
     xs[(int64_t)n * kp + sg.koff + k] = __uint_as_float(h);
-    xs[(int64_t)(np + n) * kp + sg.koff + k] = __uint_as_float(l);
+    if (mixed) {
+      // row np+n holds, per 32-deep k-stage (128 bytes): bf(x) k 0..31 | bf(x_lo) k 0..31
+      __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(xs + (int64_t)(np + n) * kp + sg.koff + (k & ~31));
+      row[k & 31] = __float2bfloat16_rn(x);
+      row[32 + (k & 31)] = __float2bfloat16_rn(x - __uint_as_float(h));
+    } else {
+      xs[(int64_t)(np + n) * kp + sg.koff + k] = __uint_as_float(l);
+    }
   }
   (void)nsegs; (void)nrhs_total;
 }
@@ -569,13 +688,34 @@ void gemm_tc_prepare(Step& st, Plan& plan) {
   st.tc_segs = blob + o_segs;
 }
 
-void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
-  if (st.n_out_rows == 0 || st.gemv_tiles == 0) return;
+// JETS_B200_TC_MIXED=0 keeps all three split terms on kind::tf32 (the A/B baseline); default: bf16 corrections.
+static int tc_mixed() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JETS_B200_TC_MIXED"); v = e ? (atoi(e) != 0) : 1; }
+  return v;
+}
+
+// JETS_B200_TC_RING selects the (matrix, right-hand-side) ring depths: 0 = 8+4, 1 = 10+4, 2 = 11+3, 3 = 9+5, 4 = 12+2.
+static int tc_ring() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("JETS_B200_TC_RING"); v = e ? atoi(e) : 0; }
+  return v;
+}
+template <int AS, int XS>
+static void launch_tc(int grid, const TcParams& P, const CUtensorMap& xmap, cudaStream_t s) {
+  constexpr int bytes = smem_bytes(AS, XS);
+  static_assert(bytes <= 227 * 1024, "ring does not fit shared memory");
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(jets_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(jets_gemm_tc_kernel<AS, XS>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
     attr_set = true;
   }
+  jets_gemm_tc_kernel<AS, XS><<<grid, kThreads, bytes, s>>>(P, xmap);
+}
+
+void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
+  if (st.n_out_rows == 0 || st.gemv_tiles == 0) return;
+  const int ring = tc_ring();
   const int nrhs_total = st.dblocks[0].nrhs;
   int maxk = 1;
   for (const DBlock& b : st.dblocks) maxk = std::max(maxk, st.dblocks[0].trans ? b.rows : b.cols);
@@ -586,7 +726,7 @@ void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
       dim3 grid((unsigned)std::min<int64_t>((work + 255) / 256, 64), (unsigned)st.tc_nsegs);
       split_rhs_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float*>(in), reinterpret_cast<float*>(st.tc_xs),
                                             reinterpret_cast<const SplitSeg*>(st.tc_segs), st.tc_nsegs, st.tc_kp, st.tc_np, nrhs, n0,
-                                            nrhs_total);
+                                            nrhs_total, tc_mixed());
       CUDA_TRY(cudaGetLastError());
       count_launch();
     }
@@ -605,10 +745,17 @@ void launch_gemm_tc(const Step& st, const char* in, char* out, cudaStream_t s) {
     P.acc = st.acc;
     P.out = reinterpret_cast<float*>(out);
     { const char* e = getenv("JETS_B200_TC_EXPT"); P.expt = e ? atoi(e) : 0; }
+    P.mixed = tc_mixed();
     const int grid = (int)std::min<int64_t>(st.gemv_tiles, ctx().sm_count);
     CUtensorMap xmap;
     memcpy(&xmap, st.tc_xmap, sizeof(xmap));
-    jets_gemm_tc_kernel<<<grid, kThreads, kSmemBytes, s>>>(P, xmap);
+    switch (ring) {
+      case 1: launch_tc<10, 4>(grid, P, xmap, s); break;
+      case 2: launch_tc<11, 3>(grid, P, xmap, s); break;
+      case 3: launch_tc<9, 5>(grid, P, xmap, s); break;
+      case 4: launch_tc<12, 2>(grid, P, xmap, s); break;
+      default: launch_tc<8, 4>(grid, P, xmap, s); break;
+    }
     CUDA_TRY(cudaGetLastError());
     count_launch();
   }
