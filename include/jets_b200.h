@@ -57,7 +57,9 @@ typedef enum {
   JETS_PW_POWER  = 1,  /* x^p       ; phi' = p*x^(p-1)            */
   JETS_PW_EXP    = 2,
   JETS_PW_SIN    = 3,
-  JETS_PW_TANH   = 4
+  JETS_PW_TANH   = 4,
+  JETS_PW_LOG    = 5,  /* log(x)    ; phi' = 1/x                  */
+  JETS_PW_ATAN   = 6   /* atan(x)   ; phi' = 1/(1+x*x)            */
 } jets_pw_fn;
 
 /* stencils (no reference definition: JetPack.jl is un-vendored; semantics in DESIGN.md §4) */
@@ -189,6 +191,12 @@ int jets_op_stencil(jets_dtype dt, int64_t n, int kind, jets_op* out);
  * A is rows x cols, column-major (Julia layout), leading dimension = rows.  nrhs>1 applies A to
  * an (cols x nrhs) column-major matrix of right-hand sides (domain JetSpace(T,cols,nrhs)).     */
 int jets_op_dense(jets_buf A, int64_t rows, int64_t cols, int64_t nrhs, jets_op* out);
+/* Restriction d = m[idx] with adjoint m[idx] = d, zero elsewhere -- the JetPack-style leaf the Jets
+ * documentation composes with (docs/src/index.md:14-19; JetPack.jl itself is un-vendored, so the
+ * definition is this library's: idx0 holds nidx UNIQUE 0-based positions of a length-n domain, copied
+ * to the device).  Changes the length, so it is a fusion barrier with its own gather/scatter kernel;
+ * plan_info bit6.                                                                               */
+int jets_op_restrict(jets_dtype dt, int64_t n, int64_t nidx, const int64_t* idx0, jets_op* out);
 /* JopZeroBlock(dom, rng) (src/Jets.jl:941-951).                                                */
 int jets_op_zero(jets_dtype dt, int64_t ndom, int64_t nrng, jets_op* out);
 
@@ -250,7 +258,8 @@ int jets_apply_axpby(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar
                      jets_scalar so, double co, int o_flags);
 /* Which engine the last plan for (op,mode) used: bit0 TMA-fused, bit1 LDG-fused, bit2 dense
  * GEMV, bit3 tcgen05 GEMM, bit4 staged through HBM temporaries, bit5 TMA-fused with the
- * shared-memory input-tile cache (rows sharing an input block fetch it once).                   */
+ * shared-memory input-tile cache (rows sharing an input block fetch it once).;
+ * bit6 gather/scatter (restriction).                                                          */
 int jets_op_plan_info(jets_op a, int mode, int32_t* engines, int32_t* nlaunches);
 /* Force an engine for A/B measurements: 0 auto, 1 TMA-fused, 2 LDG-fused, 3 TMA-fused without
  * the input-tile cache.                                                                         */

@@ -13,7 +13,7 @@ LIB_PATH = os.path.join(HERE, "libjets_b200.so")
 
 F32, F64, C64, C128 = 0, 1, 2, 3
 MODE_F, MODE_DF, MODE_DFT = 0, 1, 2
-PW = {"square": 0, "power": 1, "exp": 2, "sin": 3, "tanh": 4}
+PW = {"square": 0, "power": 1, "exp": 2, "sin": 3, "tanh": 4, "log": 5, "atan": 6}
 STENCIL = {"fdiff": 0, "lap": 1}
 COEF_NEG, COEF_INV = 1, 2
 
@@ -109,6 +109,7 @@ SIGNATURES = {
     "jets_op_stencil": (_i, [_i, _i64, _i, _pp]),
     "jets_op_dense": (_i, [_p, _i64, _i64, _i64, _pp]),
     "jets_op_zero": (_i, [_i, _i64, _i64, _pp]),
+    "jets_op_restrict": (_i, [_i, _i64, _i64, _pi64, _pp]),
     "jets_op_as_linear": (_i, [_p, _pp]),
     "jets_op_adjoint": (_i, [_p, _pp]),
     "jets_op_compose": (_i, [_i32, _pp, _pp]),

@@ -740,7 +740,56 @@ def size(A, i=None):
 
 
 def state(A, key=None):
-    return A.meta if key is None else A.meta[key]
+    """state(A[, key]) (src/Jets.jl:264-265, :313-314).  For a composition a missing key is looked up
+    in the operands and must be unambiguous (:607-623)."""
+    if key is None:
+        return A.meta
+    if key in A.meta:
+        return A.meta[key]
+    if A.meta.get("kind") == "compose":
+        hits = [o for o in A.meta["ops"] if key in o.meta]
+        if not hits:
+            raise KeyError(f"key {key} does not exist in the state of the composite operator")
+        if len(hits) > 1:
+            raise KeyError(f"ambiguous: key {key} exists in more than one operator in the composition")
+        return state(hits[0], key)
+    raise KeyError(key)
+
+
+def state_(A, s):
+    """state!(A, s) (src/Jets.jl:272, :315): merge ``s`` into the operator's state.  State that lives on
+    the device (a diagonal, a matrix) is updated IN the buffer the kernels read, so the new values take
+    effect on the next mul! exactly as a Jets closure would see its new keyword arguments."""
+    for k, v in dict(s).items():
+        cur = A.meta.get(k)
+        if isinstance(cur, DeviceArray):
+            cur.assign(v)
+        else:
+            A.meta[k] = v
+    return A
+
+
+def perfstat(A):
+    """perfstat(A) (src/Jets.jl:281, :316; composite :597-605): the engine(s) the planner chose for this
+    operator and the number of kernel launches of one apply."""
+    if isinstance(A, JopAdjoint):
+        return perfstat(A.op)
+    return plan_info(A)
+
+
+def close(A):
+    """Base.close(A) (src/Jets.jl:290, :317; composite :591-595): leaves return False, combinators close
+    their operands and return None.  The device handle is released when its last holder goes away."""
+    if isinstance(A, JopAdjoint):
+        return close(A.op)
+    kids = A.meta.get("ops")
+    A.close()
+    if kids is None:
+        return False
+    for o in (kids.ravel() if isinstance(kids, np.ndarray) else kids):
+        if isinstance(o, Jop):
+            close(o)
+    return None
 
 
 def _lin_handle(A: Jop) -> _Handle:
@@ -824,6 +873,16 @@ def JopPointwise(T, n, fn="square", p=0.0):
 def JopStencil(T, n, kind="fdiff"):
     sp = JetSpace(T, int(n))
     return JopLn(_newop(lib.jets_op_stencil, _dt(T), int(n), L.STENCIL[kind]), sp, sp, {"kind": kind})
+
+
+def JopRestriction(T, n, indices):
+    """d = m[indices]; adjoint m .= 0, m[indices] = d (JetPack-style restriction; ``indices`` 1-based and
+    unique, as a Julia caller passes them)."""
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64).reshape(-1) - 1)
+    L.ensure_init()
+    h = C.c_void_p()
+    check(lib.jets_op_restrict(_dt(T), int(n), idx.size, idx.ctypes.data_as(C.POINTER(C.c_int64)), C.byref(h)))
+    return JopLn(_Handle(h), JetSpace(T, int(n)), JetSpace(T, idx.size), {"indices": np.asarray(indices)})
 
 
 def JopDense(A, nrhs=1):
@@ -1045,7 +1104,7 @@ def vec(x):
 def plan_info(A, mode=None):
     e, n = C.c_int32(), C.c_int32()
     check(lib.jets_op_plan_info(A._h.h, A._mode if mode is None else mode, C.byref(e), C.byref(n)))
-    names = [nm for bit, nm in ((1, "tma"), (2, "ldg"), (4, "gemv"), (8, "tcgen05"), (16, "staged")) if e.value & bit]
+    names = [nm for bit, nm in ((1, "tma"), (2, "ldg"), (4, "gemv"), (8, "tcgen05"), (16, "staged"), (64, "gather")) if e.value & bit]
     return {"engines": names, "launches": n.value, "input_cache": bool(e.value & 32)}
 
 

@@ -233,7 +233,8 @@ static jets_op clone_tree(jets_op a) {  // copy(F,false): new nodes, shared (imm
   c->dom = a->dom; c->rng = a->rng; c->linear = a->linear;
   c->w = a->w;
   if (c->w) c->w->refs++;
-  c->a = a->a; c->p = a->p; c->fn = a->fn;
+  c->a = a->a; c->ai = a->ai; c->p = a->p; c->fn = a->fn;
+  c->gidx = a->gidx; c->gidx64 = a->gidx64;
   c->rows = a->rows; c->cols = a->cols; c->nrhs = a->nrhs;
   c->mo = a->mo;
   if (c->mo) c->mo->refs++;
@@ -723,7 +724,7 @@ int jets_op_scale_c(jets_dtype dt, int64_t n, double re, double im, jets_op* out
 int jets_op_pointwise(jets_dtype dt, int64_t n, int fn, double p, jets_op* out) {
   return guard([&] {
     check_dt(dt); JETS_CHECK(out && n >= 0, JETS_ERR_INVALID, "bad arguments");
-    JETS_CHECK(fn >= JETS_PW_SQUARE && fn <= JETS_PW_TANH, JETS_ERR_UNSUPPORTED, "pointwise function %d is not in the registry", fn);
+    JETS_CHECK(fn >= JETS_PW_SQUARE && fn <= JETS_PW_ATAN, JETS_ERR_UNSUPPORTED, "pointwise function %d is not in the registry", fn);
     JETS_CHECK(!is_cplx(dt) || fn == JETS_PW_SQUARE, JETS_ERR_UNSUPPORTED, "complex pointwise operators: only x^2 is in the registry");
     jets_op a = new_op(K_PW, dt);
     a->dom = a->rng = space1(n);
@@ -754,6 +755,35 @@ int jets_op_dense(jets_buf A, int64_t rows, int64_t cols, int64_t nrhs, jets_op*
     a->rows = rows; a->cols = cols; a->nrhs = nrhs;
     A->refs++;
     a->w = A;
+    *out = a;
+  });
+}
+int jets_op_restrict(jets_dtype dt, int64_t n, int64_t nidx, const int64_t* idx0, jets_op* out) {
+  return guard([&] {
+    require_ready();
+    check_dt(dt); JETS_CHECK(out && n >= 0 && nidx >= 0 && (idx0 || nidx == 0), JETS_ERR_INVALID, "bad arguments");
+    std::vector<bool> seen((size_t)n, false);
+    for (int64_t i = 0; i < nidx; ++i) {
+      JETS_CHECK(idx0[i] >= 0 && idx0[i] < n, JETS_ERR_SHAPE, "restriction index %lld outside the domain [0,%lld)", (long long)idx0[i], (long long)n);
+      JETS_CHECK(!seen[(size_t)idx0[i]], JETS_ERR_INVALID, "restriction index %lld appears twice (the adjoint would not be a plain scatter)", (long long)idx0[i]);
+      seen[(size_t)idx0[i]] = true;
+    }
+    jets_op a = new_op(K_RESTRICT, dt);
+    a->dom = space1(n);
+    a->rng = space1(nidx);
+    a->gidx64 = n >= (1LL << 31);
+    const size_t bytes = (size_t)std::max<int64_t>(nidx, 1) * (a->gidx64 ? 8 : 4);
+    void* d = nullptr;
+    CUDA_TRY(cudaMalloc(&d, bytes));
+    a->gidx = std::shared_ptr<void>(d, [](void* p) { cudaFree(p); });
+    if (nidx > 0) {
+      if (a->gidx64) CUDA_TRY(cudaMemcpy(d, idx0, (size_t)nidx * 8, cudaMemcpyHostToDevice));
+      else {
+        std::vector<int32_t> h((size_t)nidx);
+        for (int64_t i = 0; i < nidx; ++i) h[(size_t)i] = (int32_t)idx0[i];
+        CUDA_TRY(cudaMemcpy(d, h.data(), (size_t)nidx * 4, cudaMemcpyHostToDevice));
+      }
+    }
     *out = a;
   });
 }

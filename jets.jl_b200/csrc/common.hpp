@@ -131,7 +131,7 @@ struct Space {
 };
 
 enum Kind : int {
-  K_DIAG, K_SCALE, K_PW, K_STENCIL, K_DENSE, K_ZERO,  // leaves
+  K_DIAG, K_SCALE, K_PW, K_STENCIL, K_DENSE, K_ZERO, K_RESTRICT,  // leaves
   K_LNVIEW, K_ADJ,                                    // wrappers
   K_COMPOSE, K_SUM, K_BLOCK                           // combinators
 };
@@ -153,6 +153,8 @@ struct jets_op_s {
   int fn = 0;                // pointwise fn or stencil kind
   int64_t rows = 0, cols = 0, nrhs = 1;
   jets_buf mo = nullptr;     // linearization point of a pointwise leaf (retained, by reference)
+  std::shared_ptr<void> gidx;  // K_RESTRICT: device index table (int32 when the domain allows, else int64), shared by clones
+  bool gidx64 = false;
   // children
   std::vector<jets_op> kids;  // retained
   std::vector<int> sgn;       // K_SUM
@@ -337,7 +339,7 @@ struct DBlock {
   int32_t pad;
 };
 
-enum StepKind : int { ST_FUSED, ST_GEMV, ST_FILL0, ST_GEMM_TC };
+enum StepKind : int { ST_FUSED, ST_GEMV, ST_FILL0, ST_GEMM_TC, ST_GATHER };
 enum AccMode : int { ACC_SET = 0, ACC_ADD = 1, ACC_SUB = 2 };
 
 struct Ref {           // where a step reads / writes: 0 = apply's `in`, 1 = apply's `out`, >=2 tmp
@@ -356,6 +358,10 @@ struct Step {
   int64_t gemv_tiles = 0;
   int acc = ACC_SET;
   int64_t fill_len = 0;
+  // ST_GATHER: dst[i] (acc)= src[idx[i]] (g_scatter=0) or dst[idx[i]] (acc)= src[i] (g_scatter=1), i < g_n
+  const void* g_idx = nullptr;
+  int64_t g_n = 0;
+  int g_scatter = 0, g_idx64 = 0;
   // ST_GEMM_TC (kernels_gemm_tc.cu): pre-split right-hand sides, tensor maps, tile tables
   int32_t tc_np = 0, tc_nsegs = 0;
   int64_t tc_kp = 0;
@@ -429,6 +435,8 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
                    const void* x, const double* sb, double cb, int bf, const void* y,
                    cudaStream_t s);
 void scalar_finish_norm(double* v, double p, cudaStream_t s);
+// restriction / its adjoint: out[i] (acc)= in[idx[i]]  or  out[idx[i]] (acc)= in[i]   (indices unique)
+void vec_gather(int dtype, void* out, const void* in, const void* idx, int idx64, int64_t n, int scatter, int acc, cudaStream_t s);
 
 // kernels_cplx.cu: the same vector-space kernels for the complex eltypes (n counts complex elements)
 void cvec_fill(int dtype, void* p, int64_t n, double re, double im, cudaStream_t s);

@@ -28,6 +28,8 @@ __device__ __forceinline__ T pw_phi(int fn, T x, T p) {
       case JETS_PW_POWER:  return pow(x, p);
       case JETS_PW_EXP:    return exp(x);
       case JETS_PW_SIN:    return sin(x);
+      case JETS_PW_LOG:    return log(x);
+      case JETS_PW_ATAN:   return atan(x);
       default:             return tanh(x);
     }
   }
@@ -42,6 +44,8 @@ __device__ __forceinline__ T pw_dphi(int fn, T x, T p) {
       case JETS_PW_POWER:  return p * pow(x, p - T(1));
       case JETS_PW_EXP:    return exp(x);
       case JETS_PW_SIN:    return cos(x);
+      case JETS_PW_LOG:    return T(1) / x;
+      case JETS_PW_ATAN:   return T(1) / (T(1) + x * x);
       default: { T t = tanh(x); return T(1) - t * t; }
     }
   }

@@ -13,6 +13,11 @@
 // terms share a second set, and both are folded into per-thread f32 registers with
 // round-to-nearest adds every kDrainStages k-stages: the result does not depend on the length
 // of the reduction.
+// Default ("mixed") mode: the two correction terms run on kind::f16 with bf16 operands, K-concatenated
+// into one chain -- bf(a_lo)*bf(x) + bf(a)*bf(x_lo), round-to-nearest conversions, 2^-19 of the
+// product per term and zero-mean -- which takes 256 tensor-pipe cycles per k-stage instead of 384
+// and a third less operand traffic out of shared memory; measured error 1.3e-6 against Float64
+// (all-tf32: 1.6e-6).  JETS_B200_TC_MIXED=0 keeps all three terms on tf32.
 //
 // The kernel is HBM-bound by design (32 flop/B on the matrix stream), so it is built around the
 // matrix bytes: one CTA per SM, persistent over 128-row output tiles, no split-K, no atomics.
@@ -24,8 +29,15 @@
 //               and write a_hi / a_lo straight into TENSOR MEMORY (tcgen05.st): the MMA takes its A
 //               operand from TMEM, so shared memory carries the matrix bytes exactly twice
 //               (TMA write + this read) instead of ~8x with hi/lo copies in shared memory
-//   warp 10     issues tcgen05.mma.kind::tf32 (A from TMEM, X from shared memory through a K-major
-//               128B-swizzle descriptor), commits ring slots and accumulator chunks to mbarriers
+//   warps 10,11 issue the MMAs (A from TMEM, X from shared memory through a K-major 128B-swizzle
+//               descriptor): warp 10 the tf32 main term, warp 11 the bf16 corrections -- disjoint
+//               accumulator columns, so the two chains need no ordering between them; both commit
+//               ring slots and accumulator chunks to mbarriers.  Everything the issuers touch is
+//               warp-uniform BY CONSTRUCTION (warp index and TMEM base broadcast with shfl), so the
+//               compiler keeps it in uniform registers and emits the UTCHMMAs back to back; with a
+//               lane-derived warp index it wrapped every MMA and commit in an "elect one of the
+//               remaining threads" loop and the single issuing lane (~150 dependent instructions,
+//               ~1100 cycles per k-stage) was the kernel's bottleneck: 1.15 ms -> 0.74 ms on 4 GiB.
 //   warps 0-3   epilogue: tcgen05.ld the accumulator chunk, add into registers, store the tile
 // Both orientations read the matrix from its one column-major layout: A*X stages [k][32 rows]
 // boxes and each thread gathers its row with conflict-free 4-byte loads; A'*Y stages [col][32 k]

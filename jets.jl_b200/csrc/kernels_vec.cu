@@ -3,6 +3,7 @@
 // BlockArray broadcast is a single streaming pass; reductions are two-pass, fixed-order, f64
 // accumulated, warp-shuffle trees -- no atomics, bit-reproducible run to run.
 #include "common.hpp"
+#include "cplx.cuh"
 
 namespace jets {
 namespace {
@@ -499,6 +500,42 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
   } else {
     if (al) axpby_dev_kernel<double, true><<<grid_for(n / 2 + 1, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
     else axpby_dev_kernel<double, false><<<grid_for(n, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
+  }
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
+
+// ------------------------------------------------------------------ restriction ----------
+// d = m[idx] and its adjoint m[idx] = d (zero elsewhere: the caller zero-fills first when it overwrites).
+// Indices are unique (checked when the operator is built), so the scatter needs no atomics and is
+// deterministic.  The index and the dense side stream coalesced; the sparse side goes through the
+// read-only path.  HBM-bound: sizeof(I) + 2*sizeof(T) algorithmic bytes per selected element.
+template <typename T, typename I>
+__global__ void __launch_bounds__(kThreads) gather_kernel(T* __restrict__ out, const T* __restrict__ in,
+                                                          const I* __restrict__ idx, int64_t n, int scatter, int acc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int64_t j = (int64_t)idx[i];
+    const int64_t o = scatter ? j : i, q = scatter ? i : j;
+    const T v = in[q];
+    if (acc == ACC_SET) out[o] = v;
+    else if (acc == ACC_ADD) out[o] = out[o] + v;
+    else out[o] = out[o] - v;
+  }
+}
+template <typename T>
+static void gather_t(void* out, const void* in, const void* idx, int idx64, int64_t n, int scatter, int acc, cudaStream_t s) {
+  const unsigned g = grid_for(n, 4);
+  if (idx64) gather_kernel<T, int64_t><<<g, kThreads, 0, s>>>((T*)out, (const T*)in, (const int64_t*)idx, n, scatter, acc);
+  else gather_kernel<T, int32_t><<<g, kThreads, 0, s>>>((T*)out, (const T*)in, (const int32_t*)idx, n, scatter, acc);
+}
+void vec_gather(int dtype, void* out, const void* in, const void* idx, int idx64, int64_t n, int scatter, int acc, cudaStream_t s) {
+  if (n <= 0) return;
+  switch (dtype) {
+    case JETS_F32: gather_t<float>(out, in, idx, idx64, n, scatter, acc, s); break;
+    case JETS_F64: gather_t<double>(out, in, idx, idx64, n, scatter, acc, s); break;
+    case JETS_C64: gather_t<Cx<float>>(out, in, idx, idx64, n, scatter, acc, s); break;
+    default: gather_t<Cx<double>>(out, in, idx, idx64, n, scatter, acc, s); break;
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();

@@ -202,6 +202,7 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
     }
     case K_ZERO: return true;  // contributes nothing (src/Jets.jl:942, skipped at :1022,:1047)
     case K_DENSE: return false;
+    case K_RESTRICT: return false;   // changes the length: a fusion barrier with its own gather/scatter kernel
     case K_LNVIEW: return expand(a->kids[0], map_mode_lnview(mode), out, isp, osp);
     case K_ADJ: return expand(a->kids[0], map_mode_adj(mode), out, isp, osp);
     case K_COMPOSE: return expand_seq(app_order(a, mode), mode, out, isp, osp);
@@ -926,6 +927,21 @@ struct Builder {
         emit_dense(D, acc, src, dst);
         return;
       }
+      case K_RESTRICT: {
+        // forward d = m[idx]; adjoint m[idx] = d, zero elsewhere (zero-filled here when the apply overwrites)
+        const bool adj = (mode == JETS_MODE_DFT);
+        if (adj && acc == ACC_SET) emit_fill0(dst, a->dom.total());
+        Step st;
+        st.kind = ST_GATHER;
+        st.src = src; st.dst = dst;
+        st.acc = (adj && acc == ACC_SET) ? ACC_ADD : acc;
+        st.g_idx = a->gidx.get(); st.g_idx64 = a->gidx64 ? 1 : 0;
+        st.g_n = a->rng.total();
+        st.g_scatter = adj ? 1 : 0;
+        plan.engines |= 64;
+        plan.steps.push_back(std::move(st));
+        return;
+      }
       case K_COMPOSE: {
         plan.engines |= 16;
         const std::vector<jets_op> seq = app_order(a, mode);
@@ -1088,6 +1104,10 @@ void run_plan(Plan& p, int dtype, char* in, char* out) {
         break;
       case ST_GEMV: launch_gemv(st, dtype, base(st.src), base(st.dst), c.stream); break;
       case ST_GEMM_TC: launch_gemm_tc(st, base(st.src), base(st.dst), c.stream); break;
+      case ST_GATHER:
+        vec_gather(dtype, base(st.dst) + st.dst.off * dsize(dtype), base(st.src) + st.src.off * dsize(dtype), st.g_idx, st.g_idx64,
+                   st.g_n, st.g_scatter, st.acc, c.stream);
+        break;
       case ST_FILL0:
         if (is_cplx(dtype)) cvec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, 0.0, c.stream);
         else vec_fill(dtype, base(st.dst) + st.dst.off * dsize(dtype), st.fill_len, 0.0, c.stream);

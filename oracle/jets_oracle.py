@@ -42,7 +42,7 @@ __all__ = [
     "nblocks", "getblock", "getblock_", "setblock_", "isblockop", "iszero", "indices", "space",
     "dot", "norm", "extrema", "fill_", "to_array", "to_matrix", "dot_product_test",
     "linearity_test", "linearization_test", "zeros", "ones", "rand", "randn", "Array", "vec",
-    "close", "perfstat", "JopDiagonal", "JopPointwise", "JopStencil", "JopDense", "JopScale",
+    "close", "perfstat", "JopDiagonal", "JopPointwise", "JopStencil", "JopDense", "JopScale", "JopRestriction",
     "bmap", "PW_FUNCS", "JetSSpace", "SymmetricArray", "symspace",
 ]
 
@@ -1257,7 +1257,27 @@ PW_FUNCS = {
     "exp": (lambda x, p: np.exp(x), lambda x, p: np.exp(x)),
     "sin": (lambda x, p: np.sin(x), lambda x, p: np.cos(x)),
     "tanh": (lambda x, p: np.tanh(x), lambda x, p: x.dtype.type(1) - np.tanh(x) * np.tanh(x)),
+    "log": (lambda x, p: np.log(x), lambda x, p: x.dtype.type(1) / x),
+    "atan": (lambda x, p: np.arctan(x), lambda x, p: x.dtype.type(1) / (x.dtype.type(1) + x * x)),
 }
+
+
+def JopRestriction(T, n, indices):
+    """d = m[indices]; adjoint m .= 0, m[indices] = d.  JetPack-style restriction (JetPack.jl is
+    un-vendored: the definition is this build's, pinned by dot_product_test and convert(Array, A)).
+    ``indices`` are 1-based and unique, as a Julia caller would pass them."""
+    idx = np.asarray(indices, dtype=np.int64) - 1
+    assert idx.size == np.unique(idx).size and (idx.size == 0 or (idx.min() >= 0 and idx.max() < n))
+
+    def _df(d, m, *, indices, **kw):
+        d[...] = m.reshape(-1, order="F")[idx]
+        return d
+
+    def _dft(m, d, *, indices, **kw):
+        m[...] = 0
+        m.reshape(-1, order="F")[idx] = d
+        return m
+    return JopLn(df=_df, dft=_dft, dom=JetSpace(T, n), rng=JetSpace(T, idx.size), s={"indices": np.asarray(indices)})
 
 
 def JopPointwise(T, n, fn="square", p=0.0):

@@ -239,3 +239,87 @@ def test_symmetric_space_broadcast(D):  # runtests.jl:260-282
     assert np.allclose(x.A, a * u.A + b * v.A + c * w.A, rtol=1e-15, atol=0)
     y = B.zeros(R).assign(x)
     assert y.issymmetric and np.array_equal(y.A, x.A)
+
+
+# ------------------------------------------------------------------ leaves + state (rank 4) --
+@pytest.mark.parametrize("T", [np.float32, np.float64, np.complex128])
+def test_restriction(O, D, T):
+    """d = m[idx], adjoint scatter; alone, inside a composite with fused stages on both sides, and as
+    a block of a JopBlock -- bit-exact against the oracle (pure data movement + elementwise)."""
+    g = np.random.default_rng(31)
+    n, k = 5003, 1777
+    idx = g.permutation(n)[:k] + 1
+    rt = np.dtype(T).type(0).real.dtype
+    mk = (lambda s: crand(g, s, T)) if np.dtype(T).kind == "c" else (lambda s: g.random(s).astype(T))
+    w1, w2, mh, dh = mk(n), mk(k), mk(n), mk(k)
+
+    def build(K, dev):
+        R = K.JopRestriction(T, n, idx)
+        chain = K.compose(K.JopDiagonal(dev(w2)), K.compose(R, K.JopDiagonal(dev(w1))))
+        blk = K.blockop([[R, K.JopDiagonal(dev(w2))], [K.JopStencil(T, n, "fdiff"), K.JopZeroBlock(K.JetSpace(T, k), K.JetSpace(T, n))]])
+        return R, chain, blk
+
+    B, J = D.B, O.J
+    Rd, Cd, Bd = build(B, lambda v: B.to_device(v))
+    Ro, Co, Bo = build(J, lambda v: v)
+    assert bits((Rd * B.to_device(mh)).to_host(), Ro * mh)
+    assert bits((Rd.T * B.to_device(dh)).to_host(), Ro.T * dh)
+    assert "gather" in B.plan_info(Rd)["engines"]
+    if np.dtype(T).kind != "c":       # complex products: numpy's SIMD multiply may contract
+        assert bits((Cd * B.to_device(mh)).to_host(), Co * mh)
+        assert bits((Cd.T * B.to_device(dh)).to_host(), Co.T * dh)
+    else:
+        assert close((Cd * B.to_device(mh)).to_host(), Co * mh, T) and close((Cd.T * B.to_device(dh)).to_host(), Co.T * dh, T)
+    xin = np.concatenate([mh, dh])
+    yin = np.concatenate([dh, mh])
+    f = (Bd * B.to_device(xin, B.domain(Bd))).to_host()
+    t = (Bd.T * B.to_device(yin, B.range_(Bd))).to_host()
+    fo = J.to_array(Bo * J.reshape(xin.copy(), J.domain(Bo)))
+    to = J.to_array(Bo.T * J.reshape(yin.copy(), J.range_(Bo)))
+    tol = 1e-5 if rt == np.float32 else 1e-12
+    assert np.linalg.norm(f - fo) <= tol * np.linalg.norm(fo) and np.linalg.norm(t - to) <= tol * np.linalg.norm(to)
+    lhs, rhs = B.dot_product_test(Bd, B.to_device(xin, B.domain(Bd)), B.to_device(yin, B.range_(Bd)))
+    assert abs(complex(lhs) - complex(rhs)) <= 10 * tol * abs(complex(lhs))
+    with pytest.raises(B.JetsError):
+        B.JopRestriction(T, 10, [1, 2, 2])      # duplicate index
+    with pytest.raises(B.JetsError):
+        B.JopRestriction(T, 10, [1, 11])        # outside the domain
+
+
+@pytest.mark.parametrize("fn", ["log", "atan"])
+def test_new_pointwise_functions(O, D, fn):
+    g = np.random.default_rng(32)
+    n = 3001
+    B, J = D.B, O.J
+    mo, dm = g.random(n) + 0.5, g.random(n)
+    Fd, Fo = B.JopPointwise(np.float64, n, fn), J.JopPointwise(np.float64, n, fn)
+    assert np.allclose((Fd * B.to_device(mo)).to_host(), Fo * mo, rtol=1e-12, atol=0)
+    Jd, Jo = B.jacobian(Fd, B.to_device(mo)), J.jacobian(Fo, mo)
+    assert np.allclose((Jd * B.to_device(dm)).to_host(), Jo * dm, rtol=1e-12, atol=0)
+    assert np.allclose((Jd.T * B.to_device(dm)).to_host(), Jo.T * dm, rtol=1e-12, atol=0)
+    muobs, muexp = B.linearization_test(Fd, B.to_device(mo))
+    assert np.isclose(muobs[-1], muexp[-1], rtol=0.1)
+
+
+def test_state_plumbing(D):  # state/state!/perfstat/close: src/Jets.jl:264-290, :591-623
+    B = D.B
+    g = np.random.default_rng(33)
+    n = 1000
+    w = g.random(n)
+    A = B.JopDiagonal(w)
+    S = B.JopScale(np.float64, n, 2.5)
+    Cmp = B.compose(S, A)
+    assert np.array_equal(B.state(A, "diagonal").to_host(), w) and B.state(S, "a") == 2.5
+    assert np.array_equal(B.state(Cmp, "diagonal").to_host(), w) and B.state(Cmp, "a") == 2.5   # :607-623
+    with pytest.raises(KeyError):
+        B.state(Cmp, "nope")
+    with pytest.raises(KeyError):
+        B.state(B.compose(A, B.JopDiagonal(w)), "diagonal")    # ambiguous
+    m = g.random(n)
+    assert np.array_equal(Cmp * m, 2.5 * (w * m))
+    w2 = g.random(n)
+    B.state_(A, {"diagonal": w2})              # state!: the kernels read the new values
+    assert np.array_equal(Cmp * m, 2.5 * (w2 * m))
+    ps = B.perfstat(Cmp)
+    assert ps["engines"] == ["tma"] and ps["launches"] == 1
+    assert B.close(A) is False and B.close(B.compose(S, B.JopDiagonal(w))) is None

@@ -535,3 +535,34 @@ def test_pointwise_registry_linearization(fn, g):
     Jc = jacobian(F, mo)
     lhs, rhs = J.dot_product_test(Jc, g.random(12), g.random(12))
     assert np.isclose(lhs, rhs, rtol=1e-13)
+
+
+# ---- JetPack-style leaves and state plumbing ----------------------------
+@pytest.mark.parametrize("T", [np.float32, np.float64, np.complex128])
+def test_restriction_adjoint_and_matrix(T, g):
+    n = 23
+    idx = g.permutation(n)[:9] + 1          # 1-based, unique, unsorted
+    R = J.JopRestriction(T, n, idx)
+    m = J.rand(domain(R), g)
+    d = J.rand(range_(R), g)
+    assert np.array_equal(R * m, m[idx - 1])
+    back = R.T * d
+    assert np.array_equal(back[idx - 1], d) and np.count_nonzero(back) <= idx.size
+    lhs, rhs = J.dot_product_test(R, m, d)
+    assert np.isclose(lhs, rhs, rtol=1e-6 if np.dtype(T) == np.float32 else 1e-13)
+    M = J.to_matrix(R)
+    E = np.zeros((idx.size, n))
+    E[np.arange(idx.size), idx - 1] = 1
+    assert np.array_equal(M, E.astype(T))
+
+
+@pytest.mark.parametrize("fn", ["log", "atan"])
+def test_new_pointwise_functions_linearization(fn, g):
+    F = J.JopPointwise(np.float64, 12, fn)
+    mo = g.random(12) + 0.5
+    muobs, muexp = J.linearization_test(F, mo, rng=g)
+    assert np.isclose(muobs[-1], muexp[-1], rtol=0.1)
+    Jm = J.to_matrix(jacobian(F, mo))
+    eps = 1e-6
+    fd = (F * (mo + eps) - F * (mo - eps)) / (2 * eps)
+    assert np.allclose(np.diag(Jm), fd, rtol=1e-6)
