@@ -366,6 +366,42 @@ def run_ours(args):
     e2e_val = 2 * bytes_apply / (e2e_ms * 1e-3) / 1e9
     e2e_check = float(h_out[:1000].double().sum().item())
     pipe = None
+    # What the host link itself delivers for these two buffers (same pinned memory, same sizes): one
+    # direction alone and both at once.  e2e moves h2d+d2h bytes per step, so its floor is the "both" time.
+    link = None
+    if world == 1 and rank == 0:
+        try:
+            s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+            dev_a = torch.empty(nloc, dtype=torch.float32, device="cuda")
+            dev_b = torch.empty(nloc, dtype=torch.float32, device="cuda")
+
+            def timed(up, down):
+                torch.cuda.synchronize()
+                a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a0.record()
+                s1.wait_event(a0); s2.wait_event(a0)
+                if up:
+                    with torch.cuda.stream(s1):
+                        dev_a.copy_(h_in, non_blocking=True)
+                if down:
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(dev_b, non_blocking=True)
+                torch.cuda.current_stream().wait_stream(s1)
+                torch.cuda.current_stream().wait_stream(s2)
+                a1.record()
+                torch.cuda.synchronize()
+                return a0.elapsed_time(a1)
+            timed(True, True)
+            gb = nloc * 4 / 1e9
+            t_up, t_dn, t_both = timed(True, False), timed(False, True), timed(True, True)
+            link = {"h2d_alone_gbs": round(gb / t_up * 1e3, 1), "d2h_alone_gbs": round(gb / t_dn * 1e3, 1),
+                    "both_directions_ms": round(t_both, 1),
+                    "e2e_over_link_floor": round(t_both / e2e_ms, 3),
+                    "what": "cudaMemcpyAsync of the same two pinned buffers: each direction alone, then both at once; "
+                            "e2e_over_link_floor = (time of both copies at once) / (e2e step time)"}
+            del dev_a, dev_b
+        except Exception as ex:  # never let the probe break the bench line
+            link = {"error": str(ex)}
     del h_in, h_out
 
     peak, peak_src = peaks()
@@ -383,7 +419,7 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": bytes_apply // world},
         "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": NBLK * blk * 4,
                 "d2h_bytes_per_step": NBLK * blk * 4, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                "what": e2e_what, "result_probe_sum_first_1000": e2e_check},
+                "what": e2e_what, "result_probe_sum_first_1000": e2e_check, "host_link": link},
         "gpu_launches": int(ln.item()),
         "clocks": clocks,
         "parity": {"dot_product_test_rel": dpt, "tolerance": 1e-5, "checksum": checksum},

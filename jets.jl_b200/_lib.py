@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libjets_b200.so")
+LIB_PATH = os.environ.get("JETS_B200_LIB") or os.path.join(HERE, "libjets_b200.so")   # override: A/B against another build
 
 F32, F64, C64, C128 = 0, 1, 2, 3
 MODE_F, MODE_DF, MODE_DFT = 0, 1, 2

@@ -338,28 +338,38 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
       auto run_terms = [&](auto edge_tag) {
         constexpr bool EDGE = decltype(edge_tag)::value;
+        // per-vector edge information (constant across the terms of the group)
+        bool first[VPT];
+        int last[VPT];
+#pragma unroll
+        for (int i = 0; i < VPT; ++i) {
+          const int e0 = (i * kConsumers + tid) * V;
+          first[i] = EDGE && (flags & F_BLK0) && e0 == 0;
+          last[i] = (EDGE && (flags & F_BLKEND)) ? nvalid - 1 - e0 : (1 << 30);
+        }
         for (int t = 0; t < nterms; ++t) {
           const BTerm gt = M.terms[t];
-          FastIO2<T> io;
-          io.stride = kBufBytes;
           const char* xin = reinterpret_cast<const char*>(xr_p) + (int)gt.xrel * kBufBytes;
           const char* sst = reinterpret_cast<const char*>(sl_p) + (int)gt.sstream0 * kBufBytes;
+          FastIO2<T> io[VPT];
 #pragma unroll
           for (int i = 0; i < VPT; ++i) {
-            const int e0 = (i * kConsumers + tid) * V;
-            const bool first = EDGE && (flags & F_BLK0) && e0 == 0;
-            const int last = (EDGE && (flags & F_BLKEND)) ? nvalid - 1 - e0 : (1 << 30);
-            T val[V];
-            io.bin = xin + i * kConsumers * 16;
-            io.bst = sst + i * kConsumers * 16;
-            eval_fast<T, EDGE>(gt.pattern, io, stages + gt.stage0, first, last, val);
-            if (gt.sign >= 0) {
+            io[i].stride = kBufBytes;
+            io[i].bin = xin + i * kConsumers * 16;
+            io[i].bst = sst + i * kConsumers * 16;
+          }
+          T val[VPT][V];
+          eval_fast_n<T, EDGE, VPT>(gt.pattern, io, stages + gt.stage0, first, last, val);   // one dispatch per term
+          if (gt.sign >= 0) {
 #pragma unroll
-              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[j];
-            } else {
+            for (int i = 0; i < VPT; ++i)
 #pragma unroll
-              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[j];
-            }
+              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] + val[i][j];
+          } else {
+#pragma unroll
+            for (int i = 0; i < VPT; ++i)
+#pragma unroll
+              for (int j = 0; j < V; ++j) acc[i][j] = acc[i][j] - val[i][j];
           }
         }
       };
