@@ -491,11 +491,27 @@ def extra_workloads(B, torch, stream, peak):
     ms_flush = time_steps(torch, stream, step1f, 20, 3, flush)
     lhs, rhs = B.dot_product_test(A, m, B.rand(B.range_(A), seed=1003))
     gbs = 2 * 192e6 / (ms * 1e-3) / 1e9
+    # calibration: what a plain device copy of the SAME traffic (96 MB read + 96 MB write per launch, two
+    # launches per step, the same rotation over 6 buffer pairs) takes -- at 40 us per launch the ramp and
+    # tail of ANY kernel are a visible part of the time, which the long-copy peak does not include
+    cp_src = [torch.empty(96_000_000 // 8, dtype=torch.float64, device="cuda").normal_() for _ in range(NSETS)]
+    cp_dst = [torch.empty(96_000_000 // 8, dtype=torch.float64, device="cuda") for _ in range(NSETS)]
+    ccnt = [0]
+
+    def step1c():
+        i = ccnt[0] % NSETS
+        ccnt[0] += 1
+        cp_dst[i].copy_(cp_src[i])
+        cp_src[i].copy_(cp_dst[(i + 1) % NSETS])
+    ms_copy = time_steps(torch, stream, step1c, 4 * NSETS, 2 * NSETS)
+    del cp_src, cp_dst
     out["config1_blockdiag_4x4_1e6_f64"] = {"ms_per_step": round(ms, 4), "value": round(gbs, 1), "unit": "GB/s",
                                              "frac_of_hbm_peak": round(gbs / peak, 4), "algorithmic_bytes_per_step": 384_000_000,
                                              "dot_product_test_rel": abs(lhs - rhs) / abs(lhs + rhs), "engine": B.plan_info(A),
                                              "l2": f"{NSETS} independent operator/vector sets cycled ({NSETS * 192} MB working set >> 126 MB L2)",
-                                             "ms_per_step_single_set_after_256MB_write_flush": round(ms_flush, 4)}
+                                             "ms_per_step_single_set_after_256MB_write_flush": round(ms_flush, 4),
+                                             "size_matched_device_copy_ms_per_step": round(ms_copy, 4),
+                                             "frac_of_size_matched_copy": round(ms_copy / ms, 4)}
     del A, At, W, m, d, m2, sets
     # config 2: diagonal ∘ fdiff ∘ jacobian(pointwise square), 1e8 elements, Float32
     n = 100_000_000
