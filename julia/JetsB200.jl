@@ -31,6 +31,8 @@ end
 init(device::Integer = 0) = check(ccall((:jets_init, LIB), Cint, (Cint,), device))
 dtype_code(::Type{Float32}) = Cint(0)
 dtype_code(::Type{Float64}) = Cint(1)
+dtype_code(::Type{ComplexF32}) = Cint(2)      # JETS_C64: interleaved (re, im), Julia's own layout
+dtype_code(::Type{ComplexF64}) = Cint(3)      # JETS_C128
 
 # ------------------------------------------------------------------ device storage --------
 mutable struct B200Array{T} <: AbstractVector{T}
@@ -79,12 +81,37 @@ function LinearAlgebra.dot(x::B200Array{T}, y::B200Array{T}) where {T}
     check(ccall((:jets_dot, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}), x.h, y.h, r))
     T(r[])
 end
+# complex eltypes: dot conjugates its first argument (:853) and returns a complex number
+function LinearAlgebra.dot(x::B200Array{T}, y::B200Array{T}) where {T<:Complex}
+    r = zeros(Cdouble, 2)
+    check(ccall((:jets_dot_c, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cdouble}), x.h, y.h, r))
+    T(r[1], r[2])
+end
 function LinearAlgebra.norm(x::B200Array{T}, p::Real = 2) where {T}
     r = Ref{Cdouble}(0)
     check(ccall((:jets_norm, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cdouble}), x.h, p, r))
-    T(r[])
+    real(T)(r[])
 end
-Base.fill!(x::B200Array, a) = (check(ccall((:jets_buf_fill, LIB), Cint, (Ptr{Cvoid}, Cdouble), x.h, a)); x)
+# norm of a SymmetricArray whose parent lives on the device (src/Jets.jl:443-462): `w` holds, per stored
+# element, 1 + the number of mirrored positions that map onto it (computed once per JetSSpace on the host)
+function symmetric_norm(parent::B200Array{T}, w::B200Array{Float64}, p::Real = 2) where {T<:Complex}
+    r = Ref{Cdouble}(0)
+    check(ccall((:jets_norm_weighted, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Ptr{Cdouble}), parent.h, w.h, p, r))
+    real(T)(r[])
+end
+# abs.(x) of a complex vector: a real vector on the same block structure (test/runtests.jl:545-547)
+function absb200!(out::B200Array{R}, x::B200Array{Complex{R}}) where {R}
+    check(ccall((:jets_abs, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), out.h, x.h)); out
+end
+Base.fill!(x::B200Array, a) = (check(ccall((:jets_buf_fill_c, LIB), Cint, (Ptr{Cvoid}, Cdouble, Cdouble), x.h, real(a), imag(a))); x)
+# scalar getindex / setindex! (src/Jets.jl:819-832): one element over the host link, 1-based
+function Base.getindex(x::B200Array{T}, i::Integer) where {T}
+    v = Vector{T}(undef, 1)
+    check(ccall((:jets_buf_read, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{T}, Int64), x.h, i - 1, v, 1)); v[1]
+end
+function Base.setindex!(x::B200Array{T}, a, i::Integer) where {T}
+    check(ccall((:jets_buf_write, LIB), Cint, (Ptr{Cvoid}, Int64, Ptr{T}, Int64), x.h, i - 1, T[a], 1)); a
+end
 function Base.extrema(x::B200Array{T}) where {T}
     mn = Ref{Cdouble}(0); mx = Ref{Cdouble}(0)
     check(ccall((:jets_extrema, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}, Ptr{Cdouble}), x.h, mn, mx))
@@ -123,6 +150,16 @@ function JopDiagonalB200(w::B200Array{T}) where {T}
     oh = OpHandle(h[])
     sp = JetSpace(T, length(w))
     JopLn(dom = sp, rng = sp, s = (b200 = oh, w = w),
+          df! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 1, m),
+          df′! = (m, d; b200, kw...) -> leaf_apply!(m, b200, 2, d))
+end
+# d = m[indices], adjoint m .= 0; m[indices] = d -- the JetPack-style restriction (indices 1-based, unique)
+function JopRestrictionB200(::Type{T}, n::Integer, indices::AbstractVector{<:Integer}) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    idx0 = Int64.(indices) .- 1
+    check(ccall((:jets_op_restrict, LIB), Cint, (Cint, Int64, Int64, Ptr{Int64}, Ptr{Ptr{Cvoid}}), dtype_code(T), n, length(idx0), idx0, h))
+    oh = OpHandle(h[])
+    JopLn(dom = JetSpace(T, n), rng = JetSpace(T, length(idx0)), s = (b200 = oh, indices = indices),
           df! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 1, m),
           df′! = (m, d; b200, kw...) -> leaf_apply!(m, b200, 2, d))
 end
