@@ -332,10 +332,30 @@ def run_ours(args):
     h_in.uniform_(0, 1)
     e2e_steps = max(1, min(args.steps, 4))
 
-    if world == 1:
-        # block-row chunks pipelined over three streams: upload k | forward k-1, adjoint k-2 | download k-2
+    pipelined = world == 1 or os.environ.get("JETS_BENCH_E2E_PIPELINE", "1") != "0"
+    e2e_same = None
+    if world > 1:
+        def e2e_step_seq(dst):
+            B.check(lib.jets_buf_upload_async(S["x_own"]._h, -1, C.c_void_p(h_in.data_ptr()), nloc))
+            fwd()
+            adj()
+            B.check(lib.jets_buf_download_async(S["m_own"]._h, -1, C.c_void_p(dst.data_ptr()), nloc))
+    if pipelined:
+        # block-row chunks pipelined over three streams: upload k | forward k-1, adjoint k-2 | download k-2.
+        # At N > 1 the chunks that touch a neighbouring rank (first / last) wait for the halo exchange, which
+        # itself waits for every rank's upload; all other chunks stream (pipeline.compute_schedule).
         pipe = B.pipeline.ChunkedBandedApply(B, torch, part, S["make_block"], S["zero_block"], S["xext"], S["d"], S["mext"],
-                                             nchunks=int(os.environ.get("JETS_BENCH_E2E_CHUNKS", "32")))
+                                             nchunks=int(os.environ.get("JETS_BENCH_E2E_CHUNKS", "32")), comm=comm)
+        if world > 1:   # the pipelined result must be bit-identical to upload -> apply -> apply -> download
+            h_ref = torch.empty(nloc, dtype=torch.float32, pin_memory=True)
+            e2e_step_seq(h_ref)
+            barrier()
+            pipe.step(h_in, h_out, stream)
+            barrier()
+            same = torch.tensor([1 if torch.equal(h_ref, h_out) else 0], dtype=torch.int32, device="cuda")
+            dist.all_reduce(same, op=dist.ReduceOp.MIN)
+            e2e_same = bool(same.item())
+            del h_ref
         pipe.step(h_in, h_out, stream)
         barrier()
         e0 = pipe.start_event(stream)
@@ -345,17 +365,12 @@ def run_ours(args):
         e2e_what = ("pinned host m -> H2D -> d=A*m -> m'=A'*d -> D2H m' through jets_buf_upload_async/jets_apply/"
                     f"jets_buf_download_async, {len(pipe.chunks)} block-row chunks pipelined on 3 streams (jets.jl_b200/pipeline.py)")
     else:
-        def e2e_step():
-            B.check(lib.jets_buf_upload_async(S["x_own"]._h, -1, C.c_void_p(h_in.data_ptr()), nloc))
-            fwd()
-            adj()
-            B.check(lib.jets_buf_download_async(S["m_own"]._h, -1, C.c_void_p(h_out.data_ptr()), nloc))
-        e2e_step()
+        e2e_step_seq(h_out)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(e2e_steps):
-            e2e_step()
+            e2e_step_seq(h_out)
         e1.record(stream)
         barrier()
         e2e_what = "pinned host m -> H2D -> d=A*m -> m'=A'*d -> D2H m' through jets_buf_upload/jets_apply/jets_buf_download"
@@ -419,7 +434,8 @@ def run_ours(args):
                      "algorithmic_bytes_per_launch": bytes_apply // world},
         "e2e": {"value": round(e2e_val, 2), "unit": "GB/s", "h2d_bytes_per_step": NBLK * blk * 4,
                 "d2h_bytes_per_step": NBLK * blk * 4, "ms_per_step": round(e2e_ms, 3), "steps": e2e_steps,
-                "what": e2e_what, "result_probe_sum_first_1000": e2e_check, "host_link": link},
+                "what": e2e_what, "result_probe_sum_first_1000": e2e_check, "host_link": link,
+                "pipelined_equals_sequential": e2e_same},
         "gpu_launches": int(ln.item()),
         "clocks": clocks,
         "parity": {"dot_product_test_rel": dpt, "tolerance": 1e-5, "checksum": checksum},
