@@ -84,7 +84,12 @@ void load_nccl() {
       JETS_FAIL(JETS_ERR_NCCL, "NCCL error %s at %s:%d", dist().n.GetErrorString(r__), __FILE__, __LINE__); \
   } while (0)
 
-int nccl_type(int dt) { return dt == JETS_F32 ? ncclFloat32 : ncclFloat64; }
+int nccl_type(int dt) {
+  // the multi-GPU exchange paths are built and measured for the real eltypes (complex vectors would need
+  // their element counts doubled for NCCL and for the rank-ordered adds): fail loudly instead of mis-sizing
+  JETS_CHECK(!is_cplx(dt), JETS_ERR_UNSUPPORTED, "jets_dist_*: complex eltypes are not implemented on the multi-GPU path");
+  return dt == JETS_F32 ? ncclFloat32 : ncclFloat64;
+}
 void need_dist() { JETS_CHECK(dist().ready, JETS_ERR_NCCL, "jets_dist_init() has not been called"); }
 
 // x[0:n] += y[0:n]
@@ -95,6 +100,7 @@ __global__ void add_inplace_kernel(T* __restrict__ x, const T* __restrict__ y, i
 }
 void add_inplace(int dt, void* x, const void* y, int64_t n, cudaStream_t s) {
   if (n <= 0) return;
+  JETS_CHECK(!is_cplx(dt), JETS_ERR_UNSUPPORTED, "jets_dist_*: complex eltypes are not implemented on the multi-GPU path");
   int64_t g = (n + 1023) / 1024;
   const int64_t cap = (int64_t)ctx().sm_count * 16;
   if (g > cap) g = cap;
