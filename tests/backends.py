@@ -13,7 +13,7 @@ class OracleBackend:
                   "JopDense", "JopZeroBlock", "blockop", "compose", "adjoint", "jacobian", "jacobian_",
                   "mul_", "dot", "norm", "extrema", "dot_product_test", "linearity_test", "to_matrix",
                   "getblock", "nblocks", "domain", "range_", "zeros", "ones", "iszero", "isblockop",
-                  "size", "shape", "setblock_", "getblock_", "fill_"):
+                  "size", "shape", "setblock_", "getblock_", "fill_", "JopRestriction"):
             setattr(self, k, getattr(J, k))
 
     def arr(self, x, R):
@@ -58,7 +58,7 @@ class DeviceBackend:
                   "JopDense", "JopZeroBlock", "blockop", "compose", "adjoint", "jacobian", "jacobian_",
                   "mul_", "dot", "norm", "extrema", "dot_product_test", "linearity_test", "to_matrix",
                   "getblock", "nblocks", "domain", "range_", "zeros", "ones", "iszero", "isblockop",
-                  "size", "shape", "setblock_", "getblock_", "fill_"):
+                  "size", "shape", "setblock_", "getblock_", "fill_", "JopRestriction"):
             setattr(self, k, getattr(B, k))
 
     def arr(self, x, R):
