@@ -672,6 +672,59 @@ def extra_workloads(B, torch, stream, peak):
     except B.JetsError as e:  # e.g. not enough free memory on a shared box
         out.setdefault("config3a_dense_64x64_2048_f32_gemv", {"error": str(e)})
         out.setdefault("config3b_dense_64x64_2048_f32_64rhs_tcgen05", {"error": str(e)})
+    try:
+        out["reference_suite_shapes_latency"] = small_op_latency(B, torch, stream)
+    except Exception as e:  # a diagnostic section must never cost the bench line
+        out["reference_suite_shapes_latency"] = {"error": str(e)}
+    return out
+
+
+def small_op_latency(B, torch, stream):
+    """The shapes of the reference's own PkgBenchmark suite (benchmark/benchmarks.jl:39-157: n = 100
+    elements, a 4-stage composition, a 2x3 block operator) through the device path.  At this size a call is
+    pure launch latency -- microseconds per call, where the CPU reference spends a fraction of one -- so this
+    section documents the fixed cost per call of the device path; it is not a throughput claim."""
+    import numpy as np
+    n = 100
+    g = np.random.default_rng(7)
+    T = np.float64
+
+    def per_call_us(fn, reps=2000):
+        for _ in range(50):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        a.record(stream)
+        for _ in range(reps):
+            fn()
+        b.record(stream)
+        t_host = (time.perf_counter() - t0) / reps * 1e6
+        torch.cuda.synchronize()
+        return {"device_us": round(a.elapsed_time(b) / reps * 1e3, 2), "host_issue_us": round(t_host, 2)}
+    A = B.JopDiagonal(g.random(n))                       # JopFoo, benchmarks.jl:36-47
+    F = B.JopPointwise(T, n, "square")                   # JopBar, :49-67
+    m, d = B.rand(B.domain(A), seed=1), B.zeros(B.range_(A))
+    out = {"what": "per-call cost at the reference suite's n=100 shapes (benchmark/benchmarks.jl); launch-latency bound"}
+    out["JopLn mul!"] = per_call_us(lambda: B.mul_(d, A, m))
+    At = A.T
+    out["JopLn mul! adjoint"] = per_call_us(lambda: B.mul_(m, At, d))
+    out["JopNl mul!"] = per_call_us(lambda: B.mul_(d, F, m))
+    G = F @ A @ F @ A                                     # Composition, :69-82
+    out["Composition mul!"] = per_call_us(lambda: B.mul_(d, G, m))
+    J = B.jacobian(G, m)
+    Jt = J.T
+    out["Composition jacobian mul! adjoint"] = per_call_us(lambda: B.mul_(m, Jt, d))
+    Fb = B.blockop([[B.JopPointwise(T, n, "square") for _ in range(3)] for _ in range(2)])   # Block, homogeneous, :84-124
+    mb, db, eb = B.rand(B.domain(Fb), seed=2), B.zeros(B.range_(Fb)), B.rand(B.range_(Fb), seed=3)
+    out["Block 2x3 mul!"] = per_call_us(lambda: B.mul_(db, Fb, mb))
+    Jb = B.jacobian(Fb, mb)
+    Jbt = Jb.T
+    out["Block 2x3 jacobian mul! adjoint"] = per_call_us(lambda: B.mul_(mb, Jbt, db))
+    fb = B.zeros(B.range_(Fb))
+    out["BlockArray broadcast f .= d .+ e"] = per_call_us(lambda: B.lincomb_(fb, [(1.0, db), (1.0, eb)]))
+    out["BlockArray dot (host result)"] = per_call_us(lambda: B.dot(db, eb), reps=500)
+    out["BlockArray norm (host result)"] = per_call_us(lambda: B.norm(db), reps=500)
     return out
 
 
