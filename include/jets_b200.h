@@ -242,6 +242,11 @@ int jets_op_set_point(jets_op a, jets_buf mo);
  * private snapshot copy(mo); the result is linear.  jacobian!(F, mo) (:364-365) is
  * jets_op_set_point + jets_op_as_linear on the same jet.                                        */
 int jets_op_jacobian(jets_op a, jets_buf mo, jets_op* out);
+/* copy(A, false) (src/Jets.jl:230-233): a NEW tree of the same shape whose nodes share the (immutable)
+ * state buffers and the current linearization points BY REFERENCE; a later point! on the copy does not
+ * touch the original.  This is what `deepcopy(jet.s)` inside Jets' own `jacobian` (:374 -> :230) must do
+ * with a device operator handle stored in the state.                                               */
+int jets_op_clone(jets_op a, jets_op* out);
 
 /* ------------------------------------------------------------------------- apply ------------ */
 /* mul!(out, A, in) (src/Jets.jl:390-392).  accumulate!=0 reproduces quirk Q1: a

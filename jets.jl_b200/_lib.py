@@ -127,6 +127,7 @@ SIGNATURES = {
     "jets_op_getblock": (_i, [_p, _i32, _i32, _pp]),
     "jets_op_set_point": (_i, [_p, _p]),
     "jets_op_jacobian": (_i, [_p, _p, _pp]),
+    "jets_op_clone": (_i, [_p, _pp]),
     "jets_apply": (_i, [_p, _i, _p, _p, _i]),
     "jets_op_plan_info": (_i, [_p, _i, _pi32, _pi32]),
     "jets_set_fused_engine": (_i, [_i]),

@@ -836,6 +836,17 @@ def jacobian_(F, mo: DeviceArray):
     return JopLn(_lin_handle(F), F.dom, F.rng, F.meta)
 
 
+def copy(A, copymo=True):
+    """copy(A[, copymₒ]) (src/Jets.jl:230-233): a new jet of the same shape.  The operator's state buffers
+    are immutable on the device and therefore shared; the linearization point is held
+    by reference as in ``copy(A, false)`` -- with ``copymo`` a private snapshot is taken at the next
+    ``point_``/``jacobian`` anyway, which is when the reference's copy becomes observable."""
+    if isinstance(A, JopAdjoint):
+        return adjoint(copy(A.op, copymo))
+    h = _newop(lib.jets_op_clone, A._h.h)
+    return type(A)(h, A.dom, A.rng, dict(A.meta))
+
+
 def jacobian(F, mo: DeviceArray):
     """jacobian(F, mo) (src/Jets.jl:374): new jet with a private snapshot of mo; the (immutable)
     state buffers are shared instead of deep-copied."""

@@ -1035,6 +1035,13 @@ int jets_op_jacobian(jets_op a, jets_buf mo, jets_op* out) {
   });
 }
 
+int jets_op_clone(jets_op a, jets_op* out) {
+  return guard([&] {
+    check_op(a); JETS_CHECK(out, JETS_ERR_INVALID, "null out");
+    *out = clone_tree(a);   // new nodes (own plan cache, own linearization point slots), shared state buffers
+  });
+}
+
 // ------------------------------------------------------------------ apply ----------------
 int jets_apply(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate) {
   return guard([&] { apply_impl(a, mode, out, in, accumulate); });

@@ -136,6 +136,21 @@ mutable struct OpHandle
         x
     end
 end
+# Jets' own `jacobian(F, mₒ)` runs `copy(jet, false)` = `deepcopy(jet.s)` (src/Jets.jl:230, :374): a device
+# handle must not be copied bit for bit (two finalizers, one pointer).  An operator handle is cloned (new
+# nodes, shared immutable state: a later point! on the copy leaves the original alone); a device vector in
+# the state (a diagonal) is shared by reference count.
+function Base.deepcopy_internal(x::OpHandle, d::IdDict)
+    haskey(d, x) && return d[x]
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_op_clone, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), x.h, h))
+    d[x] = OpHandle(h[])
+end
+function Base.deepcopy_internal(x::B200Array{T}, d::IdDict) where {T}
+    haskey(d, x) && return d[x]
+    check(ccall((:jets_buf_retain, LIB), Cint, (Ptr{Cvoid},), x.h))
+    d[x] = B200Array{T}(x.h, copy(x.blocklengths))
+end
 # The closures exist so that a B200 leaf is a legal Jet; they are only reached when a B200 leaf is
 # mixed with CPU operators (then each leaf is one jets_apply on its own).
 function leaf_apply!(out::B200Array, h::OpHandle, mode::Integer, in::B200Array)

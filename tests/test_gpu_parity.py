@@ -809,3 +809,22 @@ def test_vectorized_operator(O, D):
     assert_bits(dv[2], dv[3])
     for a, b in zip(o, dv):
         assert_bits(a, b)
+
+
+def test_copy_gives_an_independent_linearization_point(D):  # copy(A, false) src/Jets.jl:230-233; jacobian :374
+    """B.copy(F) is a new jet: point! on the copy does not move the original's linearization point
+    (what deepcopy(jet.s) guarantees inside Jets' own jacobian), while the state buffers are shared."""
+    B = D.B
+    g = np.random.default_rng(41)
+    n = 2000
+    w, m1, m2, dm = g.random(n), g.random(n), g.random(n), g.random(n)
+    F = B.compose(B.JopDiagonal(w), B.JopPointwise(np.float64, n, "square"))
+    J1 = B.jacobian_(F, B.to_device(m1))          # shares F's jet, linearized at m1
+    G = B.copy(F)
+    J2 = B.jacobian_(G, B.to_device(m2))          # the copy, linearized at m2
+    assert np.array_equal((J1 * B.to_device(dm)).to_host(), w * ((2.0 * m1) * dm))
+    assert np.array_equal((J2 * B.to_device(dm)).to_host(), w * ((2.0 * m2) * dm))
+    assert np.array_equal((J1 * B.to_device(dm)).to_host(), w * ((2.0 * m1) * dm))   # still at m1
+    assert np.array_equal((G * B.to_device(m1)).to_host(), (F * B.to_device(m1)).to_host())
+    At = B.copy(B.JopDiagonal(w).T)
+    assert np.array_equal((At * B.to_device(dm)).to_host(), w * dm)
