@@ -56,6 +56,22 @@ function b200zeros(R::Jets.JetAbstractSpace{T}) where {T}
                 dtype_code(T), length(bl), bl, h))
     B200Array{T}(h[], bl)
 end
+# similar / copy / zeros on the device: Jets' own `jacobian` runs copy(mₒ) (:374) and `A*m` runs
+# zeros(range(A)) (:399); neither may fall back to AbstractArray's element-by-element generics.
+function Base.similar(x::B200Array{T}) where {T}
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    check(ccall((:jets_buf_create, LIB), Cint, (Cint, Int32, Ptr{Int64}, Ptr{Ptr{Cvoid}}),
+                dtype_code(T), length(x.blocklengths), x.blocklengths, h))
+    B200Array{T}(h[], copy(x.blocklengths))
+end
+function Base.copyto!(dst::B200Array{T}, src::B200Array{T}) where {T}
+    check(ccall((:jets_buf_copy, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), dst.h, src.h)); dst
+end
+Base.copy(x::B200Array) = copyto!(similar(x), x)
+function b200rand(R::Jets.JetAbstractSpace, seed::Integer = rand(UInt64) >> 1)
+    x = b200zeros(R)
+    check(ccall((:jets_buf_rand, LIB), Cint, (Ptr{Cvoid}, UInt64, UInt64, Cint), x.h, seed, 0, 0)); x
+end
 # host <-> device: setblock!/getblock!/convert(Array,x)               src/Jets.jl:862-868, :915-916
 function Base.copyto!(x::B200Array{T}, a::Array{T}) where {T}
     check(ccall((:jets_buf_upload, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{T}, Int64), x.h, -1, a, length(a)))
