@@ -111,6 +111,46 @@ def cpu_arm(steps, warmup):
     return cb, ms2
 
 
+def cpu_secondary():
+    """The C restatement timed on configs 1 and 2 as well (bounded: config 1 at full size is only 192 MB per
+    apply; config 2 on a 1/10 sample), in the three modes of cpu_arm: the reference's passes on ONE thread (what
+    Jets does), the same passes threaded, and a fused threaded rewrite.  GB/s of algorithmic bytes."""
+    import numpy as np
+    from oracle import c_oracle as CO
+    out = {"cores": CO.num_threads()}
+    g = np.random.default_rng(1)
+
+    def best_ms(fn, reps):
+        fn()
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append((time.perf_counter() - t0) * 1e3)
+        return min(ts)
+    # config 1: 4x4 diagonal blocks, 1e6 elements, Float64 -- full size
+    n = 1_000_000
+    W = [[g.random(n) for _ in range(4)] for _ in range(4)]
+    A = CO.BlockOp([[("diag", W[r][c]) for c in range(4)] for r in range(4)], [n] * 4, [n] * 4, np.float64)
+    m, d = g.random(4 * n), g.random(4 * n)
+    o1, o2 = np.empty(4 * n), np.empty(4 * n)
+    c1 = {}
+    for name, mode, reps in (("single_thread_as_in_jets", 0, 3), ("reference_passes_threaded", 2, 8), ("fused_openmp_rewrite", 1, 8)):
+        ms = best_ms(lambda: (A.apply(m, False, mode, o1), A.apply(d, True, mode, o2)), reps)
+        c1[name] = {"ms_per_fwd_adj": round(ms, 3), "gbs": round(384e6 / ms / 1e6, 2)}
+    out["config1_blockdiag_4x4_1e6_f64"] = c1
+    # config 2: diagonal ∘ fdiff ∘ jacobian(x^2), Float32 -- 1e7 elements (1/10 of the GPU workload)
+    n = 10_000_000
+    w, mo, x = (g.random(n).astype(np.float32) for _ in range(3))
+    o = np.empty(n, dtype=np.float32)
+    c2 = {"sample": "1e7 elements (1/10 of the GPU workload)"}
+    for name, mode, reps in (("single_thread_as_in_jets", 0, 3), ("reference_passes_threaded", 2, 8), ("fused_openmp_rewrite", 1, 8)):
+        ms = best_ms(lambda: (CO.chain_apply(w, mo, x, False, mode, o), CO.chain_apply(w, mo, x, True, mode, o)), reps)
+        c2[name] = {"ms_per_fwd_adj": round(ms, 3), "gbs": round(2 * 16.0 * n / ms / 1e6, 2)}
+    out["config2_chain_f32"] = c2
+    return out
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -443,6 +483,10 @@ def run_ours(args):
     }
     if rank == 0 and world == 1 and not args.no_cpu:
         line["cpu_baseline"], _ = cpu_arm(2, 1)
+        try:
+            line["cpu_baseline"]["other_configs"] = cpu_secondary()
+        except Exception as ex:  # a diagnostic leg must never cost the bench line
+            line["cpu_baseline"]["other_configs"] = {"error": str(ex)}
     if rank == 0 and world == 1 and not args.no_extra:
         del S, A, At
         import gc
