@@ -4,6 +4,7 @@ stores no golden vectors and uses unseeded ``rand``; each testset is restated on
 ``≈`` in the reference is Julia's norm-wise isapprox with rtol=sqrt(eps); we assert tighter.
 """
 import math
+import os
 
 import numpy as np
 import pytest
@@ -566,3 +567,59 @@ def test_new_pointwise_functions_linearization(fn, g):
     eps = 1e-6
     fd = (F * (mo + eps) - F * (mo - eps)) / (2 * eps)
     assert np.allclose(np.diag(Jm), fd, rtol=1e-6)
+
+
+# ---- close / perfstat / blockop keyword arguments: runtests.jl:697-702, :840-899 -----------
+def JopClose(diag, files):  # :11-18 -- a leaf that owns a resource (a file) released by close
+    import tempfile
+    fd, path = tempfile.mkstemp()
+    os.close(fd)
+    files.append(path)
+
+    def df(d, m, *, diagonal, **kw):
+        d[...] = diagonal * m
+        return d
+    spc = JetSpace(np.float64, diag.size)
+    return JopLn(df=df, dom=spc, rng=spc,
+                 s={"diagonal": diag, "file": path, "_close": lambda j: os.remove(j.s["file"])})
+
+
+def test_close_releases_leaf_resources_through_every_combinator(g):  # :840-886
+    files = []
+    A = JopClose(g.random(2), files)
+    assert os.path.isfile(state(A)["file"])
+    J.close(A)
+    assert not os.path.isfile(state(A)["file"])
+    # block operator :847-860
+    blocks = [[JopClose(g.random(2), files) for _ in range(2)] for _ in range(2)]
+    A = J.blockop(blocks)
+    parts = [J.getblock(A, i, j) for i in (1, 2) for j in (1, 2)]
+    assert all(os.path.isfile(state(B)["file"]) for B in parts)
+    J.close(A)
+    assert not any(os.path.isfile(state(B)["file"]) for B in parts)
+    # composition :862-873 and linear combination :875-886
+    for combine in (lambda a2, a1: compose(a2, a1), lambda a2, a1: a2 + a1):
+        A1, A2 = JopClose(g.random(2), files), JopClose(g.random(2), files)
+        A = combine(A2, A1)
+        assert os.path.isfile(state(A1)["file"]) and os.path.isfile(state(A2)["file"])
+        J.close(A)
+        assert not os.path.isfile(state(A1)["file"]) and not os.path.isfile(state(A2)["file"])
+    assert not any(os.path.exists(f) for f in files)
+
+
+def test_perfstat_is_looked_up_through_compositions_and_sums(g):  # :888-899
+    A1 = JopFoo(g.random(2))
+    state(A1)["_perfstat"] = lambda j: math.pi      # Jets.perfstat(::Jet{..JopFoo_df!}) = π, :9
+    A2 = JopBar(2)
+    A = compose(A2, A1)
+    assert J.perfstat(A1) == math.pi
+    assert J.perfstat(A2) is None
+    assert J.perfstat(A) == math.pi
+    assert J.perfstat(A2 + A1) == math.pi
+
+
+def test_blockop_accepts_keyword_arguments(g):  # :697-702
+    x = J.JopBlock(np.array([[JopBaz(g.random((2, 2)))], [JopBaz(g.random((2, 2)))]], dtype=object), foo=3)
+    assert isinstance(x, J.Jop)
+    x = J.JopBlock(np.array([[JopBaz(g.random((2, 2)))], [JopBaz(g.random((2, 2)))]], dtype=object), foo=3, bar=4)
+    assert isinstance(x, J.Jop) and state(x)["foo"] == 3 and state(x)["bar"] == 4
