@@ -29,6 +29,7 @@ extern "C" {
 typedef struct jets_buf_s* jets_buf;   /* device vector: flat storage + block offset table   */
 typedef struct jets_op_s*  jets_op;    /* operator tree node (a "Jet", src/Jets.jl:133-142)  */
 typedef struct jets_scalar_s* jets_scalar; /* device-resident scalar (graph-capturable loops) */
+typedef struct jets_dist_op_s* jets_dist_op; /* rank-local part of an operator partitioned over GPUs */
 
 typedef enum {
   JETS_OK = 0,
@@ -275,6 +276,13 @@ int jets_set_fused_engine(int which);
  * ncclUniqueId produced on rank 0 and broadcast by the host (torch.distributed / MPI / file).  */
 int jets_dist_unique_id(char id[128]);
 int jets_dist_init(int rank, int nranks, const char id[128]);
+/* Host bootstrap, instead of or in addition to NCCL: `allgather(user, mine, all, bytes)` must gather `bytes`
+ * bytes from every rank into all[rank*bytes ..] (MPI_Allgather, torch.distributed gloo, a shared file ...) and
+ * return 0.  It carries only set-up records (CUDA IPC handles, layouts) and host scalars; the payload of the
+ * jets_dist_op_* banded path moves through peer memory, so that path needs no NCCL at all.  The callback must
+ * stay valid until jets_dist_shutdown.                                                                    */
+typedef int (*jets_allgather_fn)(void* user, const void* mine, void* all, int64_t bytes);
+int jets_dist_init_host(int rank, int nranks, jets_allgather_fn allgather, void* user);
 int jets_dist_shutdown(void);
 int jets_dist_rank(void);
 int jets_dist_size(void);
@@ -303,6 +311,48 @@ int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi);
 /* Dense-structure exchange: all-gather domain shards / reduce-scatter partial domains.         */
 int jets_dist_allgather(jets_buf shard, jets_buf full);
 int jets_dist_reduce_scatter(jets_buf full, jets_buf shard);
+
+
+/* ------------------------------------------ distributed operators: ONE call per apply ---------- */
+/* mul!(d, A, m) / mul!(m, A', d) (src/Jets.jl:390-392) for a JopBlock whose block rows are partitioned over
+ * the ranks (one process per GPU).  The reference applies a block row as d_r = sum_c A_rc m_c
+ * (src/Jets.jl:1015-1030) and a block column of the adjoint as m_c = sum_r A_rc' d_r (:1039-1055); here each
+ * rank holds its rows and the matching shards of the vectors, and every exchange the sums need happens
+ * INSIDE the call.
+ *
+ * Block-banded operator (A_rc == JopZeroBlock for |r-c| > halo): A_loc is the rank's nloc x (nloc+2*halo)
+ * JopBlock over the halo-extended domain [halo blocks of rank-1 | nloc own blocks | halo blocks of rank+1]
+ * (blocks outside the global operator are JopZeroBlock).  Collective: every rank creates its part in the same
+ * order; neighbouring ranks map each other's exchange arena (CUDA IPC, same node).  Without jets_dist_init
+ * (or halo == 0) the operator is purely local -- the same calls then serve one GPU.  The handle retains A_loc. */
+int jets_dist_op_create(jets_op A_loc, int32_t halo, jets_dist_op* out);
+/* Dense block structure: A_loc is the rank's nloc x ncol_total JopBlock over the WHOLE domain, which is
+ * sharded over the ranks in equal contiguous pieces (domain length / nranks elements each).  Forward:
+ * ncclAllGather of the shards, then the local rows; adjoint: local partial sums for the whole domain, then
+ * ncclReduceScatter.  Needs jets_dist_init.                                                             */
+int jets_dist_op_create_dense(jets_op A_loc, jets_dist_op* out);
+int jets_dist_op_destroy(jets_dist_op A);
+/* mode F/DF: out = rank-local rows of A*in, `in` = this rank's domain shard (its nloc own blocks; banded) or
+ * domain/nranks elements (dense), `out` = its range blocks.  mode DFT: out = this rank's shard of A'*in,
+ * `in` = its range blocks.  Banded operators: ONE kernel launch per rank per call -- the halo blocks are
+ * written into the neighbours' arenas by the first work units of the launch (peer stores over NVLink), the
+ * work units that need a neighbour's data run last and wait for its flag word; the adjoint's partial sums
+ * are added in rank order (previous rank first), which for halo == 1 is bit-identical to the single-GPU
+ * apply.  Asynchronous on the context stream; every rank must issue the same sequence of applies.        */
+int jets_dist_apply(jets_dist_op A, int mode, jets_buf out, jets_buf in);
+/* Host-buffer pipeline: host_out = A' * (A * host_in) for this rank's shards (nloc own blocks each, pinned
+ * host memory), cut into `nchunks` block-row chunks (<= 0: default) pipelined on three internal streams:
+ * upload k | forward k-1, adjoint k-2 | download k-2.  Bit-identical to upload, jets_dist_apply x2,
+ * download.  Asynchronous: ordered after the context stream at call time; consecutive calls overlap (the
+ * next upload runs under the previous download).  jets_dist_op_join makes the context stream wait for
+ * everything issued so far (then jets_sync / events on the context stream see the results).              */
+int jets_dist_apply_normal_host(jets_dist_op A, void* host_out, const void* host_in, int32_t nchunks);
+int jets_dist_op_join(jets_dist_op A);
+/* what: 0 local block rows, 1 halo, 2 neighbours (bit0 previous, bit1 next), 3 chunks of the host pipeline,
+ * 4 kernel launches of one jets_dist_apply, 5 kind (0 banded, 1 dense), 6 number of work units that gave up
+ * waiting for a neighbour's flag (JETS_B200_GATE_TIMEOUT_MS, default 30 s; synchronises; results are invalid
+ * when it is not 0 -- a rank that never issued the matching apply).                                       */
+int32_t jets_dist_op_info(jets_dist_op A, int32_t what);
 
 #ifdef __cplusplus
 }

@@ -133,6 +133,7 @@ SIGNATURES = {
     "jets_set_fused_engine": (_i, [_i]),
     "jets_dist_unique_id": (_i, [C.c_char_p]),
     "jets_dist_init": (_i, [_i, _i, C.c_char_p]),
+    "jets_dist_init_host": (_i, [_i, _i, _p, _p]),
     "jets_dist_shutdown": (_i, []),
     "jets_dist_rank": (_i, []),
     "jets_dist_size": (_i, []),
@@ -146,6 +147,13 @@ SIGNATURES = {
     "jets_dist_halo_reduce_end": (_i, [_p, _i32, _i32]),
     "jets_dist_allgather": (_i, [_p, _p]),
     "jets_dist_reduce_scatter": (_i, [_p, _p]),
+    "jets_dist_op_create": (_i, [_p, _i32, _pp]),
+    "jets_dist_op_create_dense": (_i, [_p, _pp]),
+    "jets_dist_op_destroy": (_i, [_p]),
+    "jets_dist_apply": (_i, [_p, _i, _p, _p]),
+    "jets_dist_apply_normal_host": (_i, [_p, _p, _p, _i32]),
+    "jets_dist_op_join": (_i, [_p]),
+    "jets_dist_op_info": (_i32, [_p, _i32]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

@@ -29,6 +29,7 @@ SOURCES = {
     "kernels_dense.cu": [],
     "kernels_gemm_tc.cu": [],
     "dist.cu": [],
+    "dist_op.cu": [],
 }
 
 

@@ -232,7 +232,9 @@ enum Pattern : int {
   PAT_LAP_SCALE, PAT_FDIFF_SCALE, PAT_BDIFF_SCALE,   // c .* S(x)   (config 4: B - c*S)
   PAT_J2,             // 2 mo .* x                   (Jacobian of x^2)
   PAT_SQUARE,         // x .* x
-  PAT_SCALE_LAP, PAT_SCALE_FDIFF, PAT_SCALE_BDIFF    // S(c .* x)   (adjoint of c*S: config 4's A')
+  PAT_SCALE_LAP, PAT_SCALE_FDIFF, PAT_SCALE_BDIFF,   // S(c .* x)   (adjoint of c*S: config 4's A')
+  PAT_LAP_DIAG, PAT_FDIFF_DIAG, PAT_BDIFF_DIAG,      // w .* S(x)   (weighted derivative blocks)
+  PAT_DIAG_LAP, PAT_DIAG_FDIFF, PAT_DIAG_BDIFF       // S(w .* x)   (their adjoints)
 };
 struct GTerm {       // 8 bytes
   uint8_t stage0, nstages;   // into the group's stage pool
@@ -251,7 +253,14 @@ struct GroupRec {    // 272 bytes
 // at the same tile position, and every input tile lives in a shared-memory ring ("x ring") from
 // its first to its last use, so a block-tridiagonal row costs 2 tile loads instead of 4.
 enum : int { XF_LOAD = 1, XF_RELEASE = 2 };
-enum : int { BG_ROW_FIRST = 1, BG_ROW_LAST = 2, BG_ACC = 4 };
+// BGroupRec::flags: bits 4-5 select the output base (0 = the apply's `out`, k = GateLaunch::out_alt[k-1]);
+// bits 8-11 (only on the LAST group of a unit) name the cross-rank signals the finished unit counts towards.
+enum : int { BG_ROW_FIRST = 1, BG_ROW_LAST = 2, BG_ACC = 4, BG_OUT_ALT_SHIFT = 4, BG_SIG_SHIFT = 8 };
+// BGroupRec::xrel_mask: bit t = input of term t is an offset from a base pointer; bits 8+2t..9+2t select
+// that base (0 = the apply's `in`, k = GateLaunch::in_alt[k-1]).
+constexpr int kXAltShift = 8;
+constexpr int kGateFlags = 4;     // cross-rank flag words a launch may wait on / signals it may raise
+constexpr int kGateFlagStride = 32;  // 32-bit words between two flag words (one 128-byte line each)
 struct BTerm {       // 8 bytes
   uint8_t stage0, nstages;   // into the group's stage pool
   uint8_t sstream0;          // first STATE stream of the term inside the state slot
@@ -277,7 +286,9 @@ struct BundleRec {   // 32 bytes: consecutive output rows of equal length walked
   int64_t unit_begin;          // first (bundle, position) unit of this bundle in the launch-wide enumeration
   int64_t len;                 // row length (elements)
   int32_t group_begin, ngroups;
-  int32_t nx, pad;             // x-ring allocations per unit
+  int32_t nx;                  // x-ring allocations per unit
+  int32_t gate;                // bits 0-3: flag words the producer waits for before the unit's first load;
+                               // bits 4-7: signals a finished unit of this bundle counts towards
 };
 
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
@@ -325,6 +336,12 @@ struct DevFused {   // device copy + launch geometry
   int32_t chunk = 1;
   bool covers_out = false;    // the launch writes every element of the apply's `out`
   void* blob = nullptr;
+  // cross-rank gating (distributed banded apply, dist.cu): units per signal, the signals this launch must
+  // raise even when no unit feeds them, and the completion counters (in the plan blob)
+  int32_t sig_total[kGateFlags] = {0, 0, 0, 0};
+  int32_t sig_owned = 0;
+  int32_t* sig_done = nullptr;
+  bool gated = false;
 };
 
 // Dense block table entry: out[out_off + i] (+)= sum_j A[i + j*lda] * in[in_off + j]  (trans=0)
@@ -384,6 +401,20 @@ struct Plan {
 };
 
 // plan.cu
+// Distributed block-banded apply (dist.cu): which rows of the rank-local operator one launch covers.
+// Flag words a launch may wait on (in THIS rank's arena) ...
+enum : int { GF_LO_READY = 0, GF_HI_READY = 1, GF_PREV_DONE = 2, GF_NEXT_DONE = 3 };
+// ... and the signals it may raise (flag words in the NEIGHBOURS' arenas): previous rank's HI_READY, next
+// rank's LO_READY, previous rank's NEXT_DONE, next rank's PREV_DONE.
+enum : int { GS_PREV_HI_READY = 0, GS_NEXT_LO_READY = 1, GS_PREV_NEXT_DONE = 2, GS_NEXT_PREV_DONE = 3 };
+struct BandedSel {
+  int mode = JETS_MODE_DF;
+  int row_begin = 0, row_end = 0;               // forward: local block rows; adjoint: own block columns
+  bool send_prev = false, send_next = false;    // include the push rows (forward) / partial-sum rows (adjoint)
+  bool has_prev = false, has_next = false;
+  int owned = 0;                                // signals this launch must raise even if no unit feeds them
+};
+std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel& sel);
 std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
 void run_plan(Plan& p, int dtype, char* in, char* out);
 struct ApplyCoef;
@@ -405,8 +436,24 @@ struct ApplyCoef {
   const double* a_ptr = nullptr; double a_const = 1.0; int a_flags = 0;
   const double* o_ptr = nullptr; double o_const = 0.0; int o_flags = 0;
 };
+// Per-launch cross-rank wiring of a gated bundle launch: flag words in THIS rank's exchange arena that
+// neighbours raise (a unit whose bundle names flag k starts only once flags[k*stride] >= wait_val[k]),
+// flag words in the NEIGHBOURS' arenas this launch raises to sig_val[k] once every unit feeding signal k
+// has been stored, and the alternative input / output bases (halo and staging buffers, local or peer).
+struct GateLaunch {
+  const uint32_t* flags = nullptr;
+  uint32_t wait_val[kGateFlags] = {0, 0, 0, 0};
+  uint32_t* sig_addr[kGateFlags] = {nullptr, nullptr, nullptr, nullptr};
+  uint32_t sig_val[kGateFlags] = {0, 0, 0, 0};
+  const char* in_alt[3] = {nullptr, nullptr, nullptr};
+  char* out_alt[3] = {nullptr, nullptr, nullptr};
+  // escape hatch: a wait that lasts longer than timeout_ns (0 = forever) bumps *err and proceeds with whatever is
+  // in the buffer -- a missing neighbour must never hang the GPU; the host turns err != 0 into an error
+  uint32_t* err = nullptr;
+  uint64_t timeout_ns = 0;
+};
 void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s,
-                         const ApplyCoef* coef = nullptr);
+                         const ApplyCoef* coef = nullptr, const GateLaunch* gate = nullptr);
 
 // kernels_dense.cu
 void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStream_t s);

@@ -3,53 +3,14 @@
 // and (b) inside a process that already loaded torch's bundled libnccl.so.2 the same copy is
 // reused (two NCCL copies in one process would each build their own transport state).
 #include <dlfcn.h>
-#include <map>
-#include "common.hpp"
+#include "dist.hpp"
 
 namespace jets {
-namespace {
-
-typedef struct ncclComm* ncclComm_t;
-typedef struct { char internal[128]; } ncclUniqueId;
-enum { ncclSuccess = 0 };
-enum { ncclFloat32 = 7, ncclFloat64 = 8 };
-enum { ncclSum = 0 };
-
-struct Nccl {
-  void* lib = nullptr;
-  int (*GetUniqueId)(ncclUniqueId*) = nullptr;
-  int (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
-  int (*CommDestroy)(ncclComm_t) = nullptr;
-  int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*ReduceScatter)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
-  int (*GroupStart)() = nullptr;
-  int (*GroupEnd)() = nullptr;
-  const char* (*GetErrorString)(int) = nullptr;
-};
-
-struct Dist {
-  Nccl n;
-  ncclComm_t comm = nullptr;
-  int rank = 0, size = 1;
-  bool ready = false;
-  double* dev_gather = nullptr;  // [size] doubles
-  char* halo_tmp = nullptr;      // receive staging for halo_reduce
-  size_t halo_tmp_bytes = 0;
-  // peer memory (CUDA IPC): base pointers of the neighbours' copies of registered allocations
-  struct Peer { void* prev = nullptr; void* next = nullptr; size_t bytes = 0; };
-  std::map<const void*, Peer> peers;   // keyed by the local allocation base
-  cudaStream_t copy[2] = {nullptr, nullptr};          // copy-engine streams (pull from prev / next)
-  cudaEvent_t ev_begin = nullptr, ev_copy[2] = {nullptr, nullptr};
-  float* dev_flag = nullptr;     // 2 floats for the barrier all-reduce
-  bool pending_nccl = false;     // begin() used the NCCL fallback on an auxiliary stream
-};
 Dist& dist() {
   static Dist d;
   return d;
 }
+namespace {
 
 void load_nccl() {
   Nccl& n = dist().n;
@@ -77,20 +38,12 @@ void load_nccl() {
 #undef SYM
 }
 
-#define NCCL_TRY(expr)                                                                      \
-  do {                                                                                      \
-    int r__ = (expr);                                                                       \
-    if (r__ != ncclSuccess)                                                                 \
-      JETS_FAIL(JETS_ERR_NCCL, "NCCL error %s at %s:%d", dist().n.GetErrorString(r__), __FILE__, __LINE__); \
-  } while (0)
-
 int nccl_type(int dt) {
   // the multi-GPU exchange paths are built and measured for the real eltypes (complex vectors would need
   // their element counts doubled for NCCL and for the rank-ordered adds): fail loudly instead of mis-sizing
   JETS_CHECK(!is_cplx(dt), JETS_ERR_UNSUPPORTED, "jets_dist_*: complex eltypes are not implemented on the multi-GPU path");
   return dt == JETS_F32 ? ncclFloat32 : ncclFloat64;
 }
-void need_dist() { JETS_CHECK(dist().ready, JETS_ERR_NCCL, "jets_dist_init() has not been called"); }
 
 // x[0:n] += y[0:n]
 template <typename T>
@@ -168,6 +121,30 @@ void pull_end() {
 }
 
 }  // namespace
+
+void need_dist() { JETS_CHECK(dist().ready, JETS_ERR_NCCL, "jets_dist_init() has not been called"); }
+void need_nccl() {
+  JETS_CHECK(dist().ready && dist().comm, JETS_ERR_NCCL, "this call needs the NCCL communicator: jets_dist_init() has not been called");
+}
+
+void dist_allgather_host(const void* mine, void* all, size_t bytes) {
+  Dist& d = dist();
+  if (d.host_ag) {
+    const int rc = d.host_ag(d.host_ag_user, mine, all, (int64_t)bytes);
+    JETS_CHECK(rc == 0, JETS_ERR_NCCL, "the host bootstrap's all-gather callback failed with code %d", rc);
+    return;
+  }
+  need_nccl();
+  char* dev = nullptr;
+  CUDA_TRY(cudaMalloc(&dev, (size_t)(d.size + 1) * bytes));
+  try {
+    CUDA_TRY(cudaMemcpyAsync(dev + (size_t)d.size * bytes, mine, bytes, cudaMemcpyHostToDevice, ctx().stream));
+    NCCL_TRY(d.n.AllGather(dev + (size_t)d.size * bytes, dev, bytes, ncclInt8, d.comm, ctx().stream));
+    CUDA_TRY(cudaMemcpyAsync(all, dev, (size_t)d.size * bytes, cudaMemcpyDeviceToHost, ctx().stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx().stream));
+  } catch (...) { cudaFree(dev); throw; }
+  cudaFree(dev);
+}
 }  // namespace jets
 
 using namespace jets;
@@ -188,8 +165,9 @@ int jets_dist_init(int rank, int nranks, const char id[128]) {
     require_ready();
     load_nccl();
     Dist& d = dist();
-    JETS_CHECK(!d.ready, JETS_ERR_NCCL, "jets_dist_init called twice");
+    JETS_CHECK(!d.comm, JETS_ERR_NCCL, "jets_dist_init called twice");
     JETS_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, JETS_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    JETS_CHECK(!d.ready || (d.rank == rank && d.size == nranks), JETS_ERR_INVALID, "jets_dist_init after jets_dist_init_host with another rank/size");
     ncclUniqueId u;
     memcpy(u.internal, id, 128);
     NCCL_TRY(d.n.CommInitRank(&d.comm, nranks, u, rank));
@@ -200,13 +178,31 @@ int jets_dist_init(int rank, int nranks, const char id[128]) {
   });
 }
 
+int jets_dist_init_host(int rank, int nranks, jets_allgather_fn allgather, void* user) {
+  return guard([&] {
+    require_ready();
+    Dist& d = dist();
+    JETS_CHECK(allgather, JETS_ERR_INVALID, "null all-gather callback");
+    JETS_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, JETS_ERR_INVALID, "bad rank %d of %d", rank, nranks);
+    JETS_CHECK(!d.ready || (d.rank == rank && d.size == nranks), JETS_ERR_INVALID, "jets_dist_init_host after jets_dist_init with another rank/size");
+    d.host_ag = allgather;
+    d.host_ag_user = user;
+    d.rank = rank;
+    d.size = nranks;
+    d.ready = true;
+  });
+}
+
 int jets_dist_shutdown(void) {
   return guard([&] {
     Dist& d = dist();
     if (!d.ready) return;
     cudaStreamSynchronize(ctx().stream);
-    d.n.CommDestroy(d.comm);
-    cudaFree(d.dev_gather);
+    dist_ops_shutdown();
+    if (d.comm) d.n.CommDestroy(d.comm);
+    if (d.dev_gather) cudaFree(d.dev_gather);
+    d.dev_gather = nullptr;
+    d.host_ag = nullptr; d.host_ag_user = nullptr;
     if (d.halo_tmp) cudaFree(d.halo_tmp);
     for (auto& kv : d.peers) {
       if (kv.second.prev) cudaIpcCloseMemHandle(kv.second.prev);
@@ -225,6 +221,15 @@ int jets_dist_sum_scalar(double* inout) {
     require_ready(); need_dist();
     Dist& d = dist();
     Context& c = ctx();
+    if (d.host_ag) {   // rank order on the host: bit-stable
+      std::vector<double> all(d.size);
+      dist_allgather_host(inout, all.data(), sizeof(double));
+      double s = 0.0;
+      for (double v : all) s += v;
+      *inout = s;
+      return;
+    }
+    need_nccl();
     c.host_scratch[40] = *inout;
     double* mine = d.dev_gather + d.size;
     CUDA_TRY(cudaMemcpyAsync(mine, &c.host_scratch[40], sizeof(double), cudaMemcpyHostToDevice, c.stream));
@@ -239,7 +244,7 @@ int jets_dist_sum_scalar(double* inout) {
 
 int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     Context& c = ctx();
     const int nb = x->nblocks();
@@ -302,7 +307,7 @@ void halo_reduce_add(jets_buf x, int32_t nlo, int32_t nhi) {   // previous rank 
 
 int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     halo_reduce_xfer(x, nlo, lo, nhi, hi);
     halo_reduce_add(x, nlo, nhi);
   });
@@ -310,7 +315,7 @@ int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jet
 // ---- peer-memory registration (CUDA IPC) ------------------------------------------------------
 int jets_dist_register(jets_buf x) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     JETS_CHECK(x && x->st && x->st->alloc, JETS_ERR_INVALID, "jets_dist_register needs a library-owned buffer");
     const void* base = alloc_base(x);
@@ -337,7 +342,7 @@ int jets_dist_register(jets_buf x) {
 // ---- forward halo gather, split so that it overlaps the interior rows ---------------------------
 int jets_dist_halo_exchange_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     Context& c = ctx();
     const int nb = x->nblocks();
@@ -382,7 +387,7 @@ int jets_dist_halo_exchange_end(void) {
 
 int jets_dist_halo_reduce_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     Context& c = ctx();
     d.pending_nccl = false;
@@ -436,7 +441,7 @@ int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi) {
 
 int jets_dist_allgather(jets_buf shard, jets_buf full) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     JETS_CHECK(full->length() == shard->length() * d.size, JETS_ERR_SHAPE, "allgather: full must be nranks x shard");
     NCCL_TRY(d.n.AllGather(shard->ptr(), full->ptr(), (size_t)shard->length(), nccl_type(shard->dtype), d.comm, ctx().stream));
@@ -445,7 +450,7 @@ int jets_dist_allgather(jets_buf shard, jets_buf full) {
 
 int jets_dist_reduce_scatter(jets_buf full, jets_buf shard) {
   return guard([&] {
-    require_ready(); need_dist();
+    require_ready(); need_nccl();
     Dist& d = dist();
     JETS_CHECK(full->length() == shard->length() * d.size, JETS_ERR_SHAPE, "reduce_scatter: full must be nranks x shard");
     NCCL_TRY(d.n.ReduceScatter(full->ptr(), shard->ptr(), (size_t)shard->length(), nccl_type(full->dtype), ncclSum, d.comm, ctx().stream));

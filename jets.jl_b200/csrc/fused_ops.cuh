@@ -329,6 +329,26 @@ __device__ __forceinline__ bool eval_fast(int pattern, const IO& io, const CStag
       else st_bdiff<T, EDGE>(y, c * io.at(0, -1), first, last, o);
       return true;
     }
+    case PAT_LAP_DIAG: case PAT_FDIFF_DIAG: case PAT_BDIFF_DIAG: {  // streams: x, w
+      T w[V], s[V];
+      io.vec(0, x); io.vec(1, w);
+      if (pattern == PAT_LAP_DIAG) st_lap<T, EDGE>(x, io.at(0, -1), io.at(0, V), first, last, s);
+      else if (pattern == PAT_FDIFF_DIAG) st_fdiff<T, EDGE>(x, io.at(0, V), last, s);
+      else st_bdiff<T, EDGE>(x, io.at(0, -1), first, last, s);
+#pragma unroll
+      for (int j = 0; j < V; ++j) o[j] = w[j] * s[j];
+      return true;
+    }
+    case PAT_DIAG_LAP: case PAT_DIAG_FDIFF: case PAT_DIAG_BDIFF: {  // streams: x, w
+      T w[V], y[V];
+      io.vec(0, x); io.vec(1, w);
+#pragma unroll
+      for (int j = 0; j < V; ++j) y[j] = w[j] * x[j];
+      if (pattern == PAT_DIAG_LAP) st_lap<T, EDGE>(y, io.at(1, -1) * io.at(0, -1), io.at(1, V) * io.at(0, V), first, last, o);
+      else if (pattern == PAT_DIAG_FDIFF) st_fdiff<T, EDGE>(y, io.at(1, V) * io.at(0, V), last, o);
+      else st_bdiff<T, EDGE>(y, io.at(1, -1) * io.at(0, -1), first, last, o);
+      return true;
+    }
     case PAT_J2: {
       T m[V];
       io.vec(0, x); io.vec(1, m);
@@ -400,6 +420,12 @@ __device__ __forceinline__ bool eval_fast_n(int pattern, const IO (&io)[NV], con
     case PAT_SCALE_LAP: JETS_PAT_BODY(PAT_SCALE_LAP)
     case PAT_SCALE_FDIFF: JETS_PAT_BODY(PAT_SCALE_FDIFF)
     case PAT_SCALE_BDIFF: JETS_PAT_BODY(PAT_SCALE_BDIFF)
+    case PAT_LAP_DIAG: JETS_PAT_BODY(PAT_LAP_DIAG)
+    case PAT_FDIFF_DIAG: JETS_PAT_BODY(PAT_FDIFF_DIAG)
+    case PAT_BDIFF_DIAG: JETS_PAT_BODY(PAT_BDIFF_DIAG)
+    case PAT_DIAG_LAP: JETS_PAT_BODY(PAT_DIAG_LAP)
+    case PAT_DIAG_FDIFF: JETS_PAT_BODY(PAT_DIAG_FDIFF)
+    case PAT_DIAG_BDIFF: JETS_PAT_BODY(PAT_DIAG_BDIFF)
     default: return false;
   }
 #undef JETS_PAT_BODY

@@ -59,6 +59,11 @@ struct BundleParams {
   int32_t hl, hr;
   int32_t axpby;              // store epilogue out = cA*acc + cO*out_old (coefficients below)
   ApplyCoef coef;
+  // cross-rank gating of the distributed banded apply (dist.cu); gate.flags == nullptr: plain launch
+  GateLaunch gate;
+  int32_t sig_total[kGateFlags];
+  int32_t sig_owned;
+  int32_t* sig_done;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -81,6 +86,16 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(bar), "r"(parity) : "memory");
+}
+// Cross-rank flag words (distributed banded apply): written by a neighbouring GPU over NVLink into this
+// rank's exchange arena, polled here; epochs only grow, so "flag >= value" is a signed difference.
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
@@ -121,6 +136,15 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   BundleRec B = P.bundles[0];
   asm volatile("griddepcontrol.wait;" ::: "memory");
   __syncthreads();
+  if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
+    // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
+#pragma unroll
+    for (int k = 0; k < kGateFlags; ++k)
+      if (((P.sig_owned >> k) & 1) && P.sig_total[k] == 0 && P.gate.sig_addr[k] != nullptr) {
+        __threadfence_system();
+        st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
+      }
+  }
 
   if (tid >= kConsumers) {
     // =============================== producer warp ===============================
@@ -132,6 +156,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     uint32_t par = 0;
     uint32_t xbase = 0;            // x-ring allocations made by this CTA so far
     int b = 0;
+    int waited = 0;                // gate flags this CTA has already seen raised (epochs only grow)
     int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
 
     // One lane issues one term group of unit `q` into state slot `my`.
@@ -171,11 +196,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
       }
       BMeta& M = meta[my];
-      M.out_tile = P.out + (out_off + tile_start) * (int64_t)sizeof(T);
+      const int oalt = (gflags >> BG_OUT_ALT_SHIFT) & 3;
+      char* obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
+      M.out_tile = obase + (out_off + tile_start) * (int64_t)sizeof(T);
       M.rec = rec;
       const int fl = (tile_start == 0 ? F_BLK0 : 0) | (rem <= te ? F_BLKEND : 0) |
                      ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
-                     ((gflags & BG_ACC) ? F_ACC : 0);
+                     ((gflags & BG_ACC) ? F_ACC : 0) | (gflags & (0xF << BG_SIG_SHIFT));
       *reinterpret_cast<int4*>(&M.nvalid) = make_int4(nvalid, fl, nterms, xrelease);
       *reinterpret_cast<uint4*>(&M.terms[0]) = *reinterpret_cast<uint4*>(&tt[0]);
       *reinterpret_cast<uint4*>(&M.terms[2]) = *reinterpret_cast<uint4*>(&tt[2]);
@@ -188,7 +215,9 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       for (int t = 0; t < kGroupTerms; ++t) {
         if (t < nterms && (tt[t].xflags & XF_LOAD)) {
           const int64_t px = __ldg(&rec->xptr[t]);
-          const char* src = ((xrel_mask >> t) & 1) ? P.in + px : reinterpret_cast<const char*>(px);
+          const int ialt = (xrel_mask >> (kXAltShift + 2 * t)) & 3;
+          const char* ibase = ialt == 0 ? P.in : ialt == 1 ? P.gate.in_alt[0] : ialt == 2 ? P.gate.in_alt[1] : P.gate.in_alt[2];
+          const char* src = ((xrel_mask >> t) & 1) ? ibase + px : reinterpret_cast<const char*>(px);
           bulk_g2s(xring0 + tt[t].xrel * kBufBytes + (kPad - lpad), src + goff, bytes, sfull0 + 8 * my);
         }
       }
@@ -235,6 +264,31 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         b = lo;
         B = P.bundles[b];
         unit_end = B.unit_begin + (B.len + te - 1) / te;
+      }
+      if ((B.gate & 15) & ~waited) {
+        // the unit reads (or overwrites) memory a neighbouring rank fills (or is still reading): wait for
+        // its flag word.  Gated bundles are enumerated so that the waits are normally satisfied already.
+        if (lane == 0) {
+          int m = (B.gate & 15) & ~waited;
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            const uint32_t* fp = P.gate.flags + k * kGateFlagStride;
+            uint64_t t0 = 0;
+            while ((int32_t)(ld_acquire_sys(fp) - P.gate.wait_val[k]) < 0) {
+              __nanosleep(100);
+              if (P.gate.timeout_ns) {
+                uint64_t now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0) t0 = now;
+                else if (now - t0 > P.gate.timeout_ns) { atomicAdd(P.gate.err, 1u); break; }
+              }
+            }
+          }
+          asm volatile("fence.proxy.async;" ::: "memory");   // the data arrived through the generic proxy; TMA reads it
+        }
+        waited |= B.gate & 15;
+        __syncwarp();
       }
       // Short bundles: several units of the bundle are issued side by side, one lane per group, as
       // long as the batch needs no x buffer that one of its own groups has to release first.
@@ -410,6 +464,25 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       }
+      if (flags & (0xF << BG_SIG_SHIFT)) {
+        // last row of a unit whose bundle feeds cross-rank signals: once every consumer warp has stored its
+        // part, count the unit; the CTA that completes a signal's last unit raises the neighbour's flag word
+        // (data and flag may both live in peer memory: fence.sys orders them for the observer's acquire).
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+        if (tid == 0) {
+          __threadfence_system();
+          int m = (flags >> BG_SIG_SHIFT) & 15;
+          while (m) {
+            const int k = __ffs(m) - 1;
+            m &= m - 1;
+            if (atomicAdd(P.sig_done + k, 1) == P.sig_total[k] - 1) {
+              P.sig_done[k] = 0;               // re-armed for the next launch of this plan
+              __threadfence_system();
+              if (P.gate.sig_addr[k] != nullptr) st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
+            }
+          }
+        }
+      }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
@@ -466,11 +539,17 @@ int bundle_buf_bytes(int variant) {
 }
 int bundle_smem_budget() { return kSmemLimit - kHdrAligned; }
 
-void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s, const ApplyCoef* coef) {
+void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s, const ApplyCoef* coef,
+                         const GateLaunch* gate) {
   if (f.nbundles == 0 || f.nunits == 0) return;
+  JETS_CHECK(!f.gated || (gate && gate->flags), JETS_ERR_INVALID, "internal: gated plan launched without its flag words");
   BundleParams P;
   P.axpby = coef ? 1 : 0;
   if (coef) P.coef = *coef;
+  if (gate) P.gate = *gate;
+  for (int k = 0; k < kGateFlags; ++k) P.sig_total[k] = f.sig_total[k];
+  P.sig_owned = f.sig_owned;
+  P.sig_done = f.sig_done;
   P.groups = f.bgroups; P.bundles = f.bundles;
   P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
   P.tile_elems = f.tile_elems; P.nunits = f.nunits;

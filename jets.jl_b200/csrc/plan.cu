@@ -37,11 +37,15 @@ int map_mode_adj(int mode) { return mode == JETS_MODE_DFT ? JETS_MODE_DF : JETS_
 const Space& out_space(jets_op a, int mode) { return mode == JETS_MODE_DFT ? a->dom : a->rng; }
 const Space& in_space(jets_op a, int mode) { return mode == JETS_MODE_DFT ? a->rng : a->dom; }
 
-FStage mk(int op, int fn = 0, const void* ptr = nullptr, double c0 = 0) {
+// c1 != 0 marks an operand stream that lives in caller-owned memory WITHOUT the 256-byte guard of library
+// allocations (jets_buf_wrap): the TMA engines fetch 16 bytes before a tile (stencil halo) and round its
+// tail up, so such streams are only ever read by the guarded-load (LDG) engine.
+FStage mk(int op, int fn = 0, const void* ptr = nullptr, double c0 = 0, bool guarded = true) {
   FStage s;
-  s.op = op; s.fn = fn; s.ptr = ptr; s.c0 = c0; s.c1 = 0;
+  s.op = op; s.fn = fn; s.ptr = ptr; s.c0 = c0; s.c1 = guarded ? 0.0 : 1.0;
   return s;
 }
+bool stream_tma_ok(const FStage& s) { return !s.ptr || ((reinterpret_cast<uintptr_t>(s.ptr) & 15) == 0 && s.c1 == 0.0); }
 
 int chain_streams(const std::vector<FStage>& ch) {
   int n = 1;
@@ -166,7 +170,7 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
     case K_DIAG: {
       Entry e;
       // df'!: m .= conj(w) .* d (fixture JopFoo, test/runtests.jl:4); conj is the identity on reals
-      e.chain.push_back(mk(S_DIAG, (g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0, a->w->ptr()));
+      e.chain.push_back(mk(S_DIAG, (g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0, a->w->ptr(), 0, a->w->guarded()));
       out.push_back(e);
       return true;
     }
@@ -189,7 +193,7 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
       } else {
         JETS_CHECK(a->mo != nullptr, JETS_ERR_NO_POINT,
                    "Jacobian of a pointwise operator applied before point!/jacobian set mo");
-        e.chain.push_back(mk(S_PW_J, a->fn | ((g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0), a->mo->ptr(), a->p));
+        e.chain.push_back(mk(S_PW_J, a->fn | ((g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0), a->mo->ptr(), a->p, a->mo->guarded()));
       }
       out.push_back(e);
       return true;
@@ -291,6 +295,17 @@ int classify(const std::vector<FStage>& ch) {
     if (is(1, S_FDIFF)) return PAT_SCALE_FDIFF;
     if (is(1, S_BDIFF)) return PAT_SCALE_BDIFF;
   }
+  auto plain_diag = [&](size_t i) { return is(i, S_DIAG) && ch[i].fn == 0; };   // real diagonal (no conjugation flag)
+  if (n == 2 && plain_diag(1)) {
+    if (is(0, S_LAP)) return PAT_LAP_DIAG;
+    if (is(0, S_FDIFF)) return PAT_FDIFF_DIAG;
+    if (is(0, S_BDIFF)) return PAT_BDIFF_DIAG;
+  }
+  if (n == 2 && plain_diag(0)) {
+    if (is(1, S_LAP)) return PAT_DIAG_LAP;
+    if (is(1, S_FDIFF)) return PAT_DIAG_FDIFF;
+    if (is(1, S_BDIFF)) return PAT_DIAG_BDIFF;
+  }
   if (n == 3 && j2(0) && is(1, S_FDIFF) && is(2, S_DIAG)) return PAT_J2_FDIFF_DIAG;
   if (n == 3 && is(0, S_DIAG) && is(1, S_BDIFF) && j2(2)) return PAT_DIAG_BDIFF_J2;
   return PAT_GENERIC;
@@ -353,7 +368,7 @@ struct Builder {
       for (const Entry& e : es) {
         if (classify(e.chain) == PAT_GENERIC) all_fast = false;
         for (const FStage& s : e.chain)
-          if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
+          if (!stream_tma_ok(s)) tma = false;
         if (((src.off + io[e.c]) * esz) % 16 || ((dst.off + oo[e.r]) * esz) % 16) tma = false;
         run = (e.r == prev_r) ? run + 1 : 1;
         prev_r = e.r;
@@ -404,7 +419,7 @@ struct Builder {
         tm.stage_begin = (int32_t)t.stages.size();
         for (const FStage& s : e.chain) {
           t.stages.push_back(s);
-          if (s.ptr && (reinterpret_cast<uintptr_t>(s.ptr) & 15)) tma = false;
+          if (!stream_tma_ok(s)) tma = false;
           if ((s.op == S_PW_F || s.op == S_PW_J) && (s.fn & ~kConjFlag) != JETS_PW_SQUARE) heavy = true;
         }
         tm.stage_end = (int32_t)t.stages.size();
@@ -527,12 +542,15 @@ struct Builder {
   // term is the tile's first use (the producer loads it) and/or its last use (consumers release it).
   struct PTerm {
     int pattern = 0, sign = 1;
-    int64_t key = 0;                 // input block: byte offset from the apply's `in`
+    int64_t key = 0;                 // input block: byte offset from its base pointer
+    int in_alt = 0;                  // base: 0 = the apply's `in`, k = GateLaunch::in_alt[k-1]
     std::vector<int64_t> sptr;       // state streams
     std::vector<CStage> stages;
   };
   struct PRow {
-    int64_t out_off = 0, len = 0;
+    int64_t out_off = 0, len = 0;    // out_off: element offset from the row's output base
+    int out_alt = 0;                 // base: 0 = the apply's `out`, k = GateLaunch::out_alt[k-1]
+    int wait = 0, sig = 0;           // cross-rank gate: flag words to wait for / signals the finished row feeds
     std::vector<PTerm> terms;
   };
   struct BundleSim {
@@ -541,12 +559,14 @@ struct Builder {
     int maxdist = 0, sstreams = 0, max_rows = 1;
   };
 
+  static int64_t xkey(const PTerm& t) { return t.key | ((int64_t)t.in_alt << 56); }   // identity of an input tile stream
   static void simulate_bundles(const std::vector<PRow>& rows, int NX, int Bmax, bool accflag, BundleSim& o) {
     o = BundleSim{};
     size_t ri = 0;
     while (ri < rows.size()) {
       BundleRec B{};
       B.len = rows[ri].len;
+      B.gate = rows[ri].wait | (rows[ri].sig << 4);
       B.group_begin = (int32_t)o.groups.size();
       std::map<int64_t, int> where;                      // input key -> latest allocation
       std::vector<std::pair<int, int>> last_use;         // per allocation: (group index, term index)
@@ -555,7 +575,8 @@ struct Builder {
         auto it = where.find(key);
         return (it != where.end() && next_alloc - it->second <= NX) ? it->second : -1;
       };
-      while (ri < rows.size() && nrows < Bmax && rows[ri].len == B.len && next_alloc < 60000) {
+      while (ri < rows.size() && nrows < Bmax && rows[ri].len == B.len && next_alloc < 60000 &&
+             (rows[ri].wait | (rows[ri].sig << 4)) == B.gate) {
         const PRow& row = rows[ri];
         // A row joins the bundle when it shares an input tile with it.  Rows WITHOUT terms (zero-filled
         // output blocks, e.g. the halo columns of a rank-local adjoint) ride along with whatever bundle
@@ -564,7 +585,7 @@ struct Builder {
         // (measured at config 5: 8.7 ms -> 7.7 ms).
         if (nrows > 0 && next_alloc > 0 && !row.terms.empty()) {
           bool share = false;
-          for (const PTerm& t : row.terms) share = share || resident(t.key) >= 0;
+          for (const PTerm& t : row.terms) share = share || resident(xkey(t)) >= 0;
           if (!share) break;
         }
         BGroupRec cur{};
@@ -572,7 +593,8 @@ struct Builder {
         bool first = true;
         auto flush = [&](bool row_last) {
           cur.out_off = row.out_off;
-          cur.flags = (first ? BG_ROW_FIRST : 0) | (row_last ? BG_ROW_LAST : 0) | (accflag ? BG_ACC : 0);
+          cur.flags = (first ? BG_ROW_FIRST : 0) | (row_last ? BG_ROW_LAST : 0) | (accflag ? BG_ACC : 0) |
+                      (row.out_alt << BG_OUT_ALT_SHIFT);
           o.sstreams = std::max(o.sstreams, (int)cur.nsstreams);
           o.groups.push_back(cur);
           cur = BGroupRec{};
@@ -584,7 +606,7 @@ struct Builder {
                                  nst + (int)t.stages.size() > kGroupStages))
             flush(false);
           int gi = (int)o.groups.size();
-          int a = resident(t.key);
+          int a = resident(xkey(t));
           uint8_t xf = 0;
           if (a >= 0) {
             o.maxdist = std::max(o.maxdist, next_alloc - a);
@@ -596,7 +618,7 @@ struct Builder {
               gi = (int)o.groups.size();
             }
             ++next_alloc;
-            where[t.key] = a;
+            where[xkey(t)] = a;
             last_use.emplace_back(gi, 0);
             xf = XF_LOAD;
           }
@@ -611,7 +633,7 @@ struct Builder {
           bt.xflags = xf;
           bt.xrel = (uint16_t)a;
           cur.xptr[ti] = t.key;
-          cur.xrel_mask |= 1 << ti;
+          cur.xrel_mask |= (1 << ti) | (t.in_alt << (kXAltShift + 2 * ti));
           for (int64_t p : t.sptr) cur.sptr[cur.nsstreams++] = p;
           for (const CStage& c : t.stages) cur.stages[nst++] = c;
         }
@@ -621,6 +643,7 @@ struct Builder {
       }
       for (auto& lu : last_use) o.groups[lu.first].terms[lu.second].xflags |= XF_RELEASE;
       B.ngroups = (int32_t)o.groups.size() - B.group_begin;
+      if (B.gate >> 4) o.groups.back().flags |= (B.gate >> 4) << BG_SIG_SHIFT;   // the unit's last group reports completion
       B.nx = next_alloc;
       o.max_rows = std::max(o.max_rows, nrows);
       o.bundles.push_back(B);
@@ -664,17 +687,7 @@ struct Builder {
         const Entry& e = es[k++];
         JETS_CHECK(in_sp.len[e.c] == out_sp.len[r], JETS_ERR_SHAPE, "elementwise block (%d,%d) maps %lld -> %lld elements",
                    (int)r, e.c, (long long)in_sp.len[e.c], (long long)out_sp.len[r]);
-        PTerm t;
-        t.pattern = classify(e.chain);
-        t.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
-        t.key = (src.off + io[e.c]) * (int64_t)esz;
-        for (const FStage& s : e.chain) {
-          CStage cs{};
-          cs.op = (uint8_t)s.op; cs.fn = (uint8_t)s.fn; cs.has_stream = s.ptr != nullptr; cs.c0 = s.c0;
-          t.stages.push_back(cs);
-          if (s.ptr) t.sptr.push_back((int64_t)reinterpret_cast<uintptr_t>(s.ptr));
-        }
-        row.terms.push_back(std::move(t));
+        row.terms.push_back(make_term(e, acc, (src.off + io[e.c]) * (int64_t)esz, 0));
       }
       if (row.len == 0) continue;
       if (row.terms.empty() && acc != ACC_SET) continue;  // nothing to add
@@ -683,15 +696,38 @@ struct Builder {
     Step st;
     st.kind = ST_FUSED;
     st.src = src; st.dst = dst; st.acc = acc;
+    if (!emit_bundle_rows(rows, st, hl, hr, acc != ACC_SET, variant_hint)) return false;
+    st.fused.covers_out = dst.off == 0;   // every non-empty output row is written by this launch (ACC_SET keeps term-less rows)
+    plan.steps.push_back(std::move(st));
+    return true;
+  }
+
+  static PTerm make_term(const Entry& e, int acc, int64_t key, int in_alt) {
+    PTerm t;
+    t.pattern = classify(e.chain);
+    t.sign = (acc == ACC_SUB) ? -e.sign : e.sign;
+    t.key = key;
+    t.in_alt = in_alt;
+    for (const FStage& s : e.chain) {
+      CStage cs{};
+      cs.op = (uint8_t)s.op; cs.fn = (uint8_t)s.fn; cs.has_stream = s.ptr != nullptr; cs.c0 = s.c0;
+      t.stages.push_back(cs);
+      if (s.ptr) t.sptr.push_back((int64_t)reinterpret_cast<uintptr_t>(s.ptr));
+    }
+    return t;
+  }
+
+  // Rows (in launch order: units are enumerated bundle-major, so rows listed first are claimed first) ->
+  // ONE bundle launch in `st`.  Returns false when the rings do not fit.
+  bool emit_bundle_rows(std::vector<PRow>& rows, Step& st, int hl, int hr, bool accflag, int variant_hint) {
+    const size_t esz = dsize(dtype);
     DevFused& f = st.fused;
     f.hl = hl; f.hr = hr;
     f.fast = f.use_tma = f.bundle = true;
     if (rows.empty()) {
       plan.engines |= 1;
-      plan.steps.push_back(std::move(st));
       return true;
     }
-    const bool accflag = acc != ACC_SET;
     // reuse distance with an unbounded ring -> how many buffers sharing needs
     BundleSim sim;
     simulate_bundles(rows, kMaxRing, 1 << 30, accflag, sim);
@@ -758,7 +794,12 @@ struct Builder {
     f.nunits = unit;
     f.nrows = (int32_t)rows.size();
     f.ntiles = unit;
-    f.covers_out = dst.off == 0;   // every non-empty output row is written by this launch (ACC_SET keeps term-less rows)
+    for (const BundleRec& b : sim.bundles) {        // units behind every cross-rank signal
+      const int64_t u = (b.len + te - 1) / te;
+      for (int s = 0; s < kGateFlags; ++s)
+        if ((b.gate >> (4 + s)) & 1) f.sig_total[s] += (int32_t)u;
+      if (b.gate) f.gated = true;
+    }
     // units per dynamic claim: what the producer can issue side by side for the shortest bundles
     int chunk = 1;
     for (const BundleRec& b : sim.bundles)
@@ -784,6 +825,7 @@ struct Builder {
     f.bundles = reinterpret_cast<BundleRec*>(blob + gb);
     f.table_bytes = gb + bb;
     f.sched = (!ctx().static_sched && unit > (int64_t)chunk * grid) ? reinterpret_cast<int32_t*>(blob + gb + bb) : nullptr;
+    f.sig_done = reinterpret_cast<int32_t*>(blob + gb + bb + 64);
     plan.engines |= 1 | 32;
     if (getenv("JETS_B200_PLAN_DEBUG")) {
       int64_t ng = 0, nxsum = 0, maxg = 0;
@@ -792,8 +834,156 @@ struct Builder {
               "variant=%d NX=%d NS=%d sstreams=%d G=%d chunk=%d dyn=%d\n", rows.size(), sim.bundles.size(), (long long)ng, (long long)maxg,
               (long long)nxsum, (long long)unit, (long long)te, variant, NX, NS, sim.sstreams, f.G, chunk, f.sched != nullptr);
     }
-    plan.steps.push_back(std::move(st));
     return true;
+  }
+
+
+  // ---- distributed block-banded apply (dist.cu) ------------------------------------------------
+  // A_loc is this rank's nloc x (nloc + 2h) block rows over the halo-extended domain
+  // [h blocks of the previous rank | nloc own blocks | h blocks of the next rank].  The launch works on the
+  // rank's OWN shards (`in`/`out` hold nloc blocks); halo data lives in the exchange arena:
+  //   forward   push rows copy the first / last h own blocks of `in` into the neighbours' halo buffers
+  //             (peer stores) and raise their "ready" flag; rows that read a halo buffer wait for this
+  //             rank's "ready" flag, are enumerated last, and report "done" back to the writer.
+  //   adjoint   the partial sums for the neighbours' columns (src/Jets.jl:1039-1055 restricted to this rank's
+  //             rows) are stored straight into the neighbours' staging buffers; the owner adds them as one
+  //             more term of its row sum -- the previous rank's partial FIRST, the next rank's LAST, which
+  //             is the single-GPU left-to-right order (:1049), so a block-tridiagonal result is bit-identical.
+  void emit_banded(jets_op A, int h, const BandedSel& sel) {
+    const bool adj = sel.mode == JETS_MODE_DFT;
+    const int nloc = A->R;
+    const size_t esz = dsize(dtype);
+    Entries es;
+    Space isp, osp;
+    JETS_CHECK(expand(A, sel.mode, es, isp, osp), JETS_ERR_UNSUPPORTED,
+               "distributed banded apply: the local block rows must be elementwise/stencil operators (one fused launch)");
+    int hl, hr;
+    halo_of(es, hl, hr);
+    JETS_CHECK(hl <= 1 && hr <= 1, JETS_ERR_UNSUPPORTED, "distributed banded apply: stencil halo too wide for fusion");
+    std::stable_sort(es.begin(), es.end(), [](const Entry& x, const Entry& y) { return x.r != y.r ? x.r < y.r : x.c < y.c; });
+    for (const Entry& e : es) {
+      JETS_CHECK(classify(e.chain) != PAT_GENERIC, JETS_ERR_UNSUPPORTED, "distributed banded apply: block (%d,%d) has no straight-line kernel path", e.r, e.c);
+      for (const FStage& s : e.chain)
+        JETS_CHECK(stream_tma_ok(s), JETS_ERR_UNSUPPORTED, "distributed banded apply: operator state must live in 16-byte aligned library-owned buffers");
+    }
+    const Space& dom = A->dom;   // nloc + 2h blocks
+    const Space& rng = A->rng;   // nloc blocks
+    for (auto l : dom.len) JETS_CHECK((l * esz) % 16 == 0, JETS_ERR_UNSUPPORTED, "distributed banded apply: block lengths must be multiples of 16 bytes");
+    for (auto l : rng.len) JETS_CHECK((l * esz) % 16 == 0, JETS_ERR_UNSUPPORTED, "distributed banded apply: block lengths must be multiples of 16 bytes");
+    // element offsets inside: the own-domain shard, the range shard, the lo / hi halo (or staging) buffers
+    std::vector<int64_t> own_off(nloc + 1, 0), rng_off(nloc + 1, 0), lo_off(h + 1, 0), hi_off(h + 1, 0), slo_off(h + 1, 0), shi_off(h + 1, 0);
+    for (int b = 0; b < nloc; ++b) { own_off[b + 1] = own_off[b] + dom.len[h + b]; rng_off[b + 1] = rng_off[b] + rng.len[b]; }
+    for (int k = 0; k < h; ++k) {
+      lo_off[k + 1] = lo_off[k] + dom.len[k];                 // forward halo / partials for the previous rank
+      hi_off[k + 1] = hi_off[k] + dom.len[nloc + h + k];
+      slo_off[k + 1] = slo_off[k] + dom.len[h + k];           // adjoint staging: partials received for my first / last h columns
+      shi_off[k + 1] = shi_off[k] + dom.len[nloc + k];
+    }
+    std::vector<PRow> early, plain, late;
+    auto copy_term = [&](int64_t key_bytes, int in_alt) {
+      Entry e;   // empty chain = PAT_COPY
+      return make_term(e, ACC_SET, key_bytes, in_alt);
+    };
+    if (!adj) {
+      if (sel.send_prev && sel.has_prev)
+        for (int b = 0; b < h; ++b) {       // my first h own blocks are the previous rank's hi halo
+          PRow row;
+          row.out_alt = 1; row.out_off = slo_off[b]; row.len = dom.len[h + b];
+          row.wait = 1 << GF_PREV_DONE; row.sig = 1 << GS_PREV_HI_READY;
+          row.terms.push_back(copy_term(own_off[b] * (int64_t)esz, 0));
+          if (row.len) early.push_back(std::move(row));
+        }
+      if (sel.send_next && sel.has_next)
+        for (int k = 0; k < h; ++k) {       // my last h own blocks are the next rank's lo halo
+          const int b = nloc - h + k;
+          PRow row;
+          row.out_alt = 2; row.out_off = shi_off[k]; row.len = dom.len[h + b];
+          row.wait = 1 << GF_NEXT_DONE; row.sig = 1 << GS_NEXT_LO_READY;
+          row.terms.push_back(copy_term(own_off[b] * (int64_t)esz, 0));
+          if (row.len) early.push_back(std::move(row));
+        }
+      size_t k = 0;
+      for (int r = 0; r < nloc; ++r) {
+        PRow row;
+        row.out_off = rng_off[r]; row.len = rng.len[r];
+        while (k < es.size() && es[k].r < r) ++k;
+        const bool want = r >= sel.row_begin && r < sel.row_end;
+        while (k < es.size() && es[k].r == r) {
+          const Entry& e = es[k++];
+          if (!want) continue;
+          JETS_CHECK(dom.len[e.c] == rng.len[r], JETS_ERR_SHAPE, "elementwise block (%d,%d) maps %lld -> %lld elements", r, e.c,
+                     (long long)dom.len[e.c], (long long)rng.len[r]);
+          if (e.c < h) {
+            JETS_CHECK(sel.has_prev, JETS_ERR_INVALID, "distributed banded apply: block (%d,%d) reads the previous rank's halo but this is the first rank", r, e.c);
+            row.terms.push_back(make_term(e, ACC_SET, lo_off[e.c] * (int64_t)esz, 1));
+            row.wait |= 1 << GF_LO_READY; row.sig |= 1 << GS_PREV_NEXT_DONE;
+          } else if (e.c >= nloc + h) {
+            JETS_CHECK(sel.has_next, JETS_ERR_INVALID, "distributed banded apply: block (%d,%d) reads the next rank's halo but this is the last rank", r, e.c);
+            row.terms.push_back(make_term(e, ACC_SET, hi_off[e.c - nloc - h] * (int64_t)esz, 2));
+            row.wait |= 1 << GF_HI_READY; row.sig |= 1 << GS_NEXT_PREV_DONE;
+          } else {
+            row.terms.push_back(make_term(e, ACC_SET, own_off[e.c - h] * (int64_t)esz, 0));
+          }
+        }
+        if (!want || row.len == 0) continue;
+        (row.wait ? late : plain).push_back(std::move(row));
+      }
+    } else {
+      // entries: r = extended column (output), c = local row (input block of d)
+      size_t k = 0;
+      for (int j = 0; j < nloc + 2 * h; ++j) {
+        PRow row;
+        row.len = dom.len[j];
+        bool want;
+        if (j < h) {                               // partial sums for the previous rank's last h columns
+          want = sel.send_prev && sel.has_prev;
+          row.out_alt = 1; row.out_off = lo_off[j];
+          row.wait = 1 << GF_PREV_DONE; row.sig = 1 << GS_PREV_HI_READY;
+        } else if (j >= nloc + h) {                // ... for the next rank's first h columns
+          want = sel.send_next && sel.has_next;
+          row.out_alt = 2; row.out_off = hi_off[j - nloc - h];
+          row.wait = 1 << GF_NEXT_DONE; row.sig = 1 << GS_NEXT_LO_READY;
+        } else {
+          const int b = j - h;
+          want = b >= sel.row_begin && b < sel.row_end;
+          row.out_off = own_off[b];
+          if (want && sel.has_prev && b < h) {     // the previous rank's partial enters first (:1049 order)
+            row.terms.push_back(copy_term(slo_off[b] * (int64_t)esz, 1));
+            row.wait |= 1 << GF_LO_READY; row.sig |= 1 << GS_PREV_NEXT_DONE;
+          }
+        }
+        while (k < es.size() && es[k].r < j) ++k;
+        while (k < es.size() && es[k].r == j) {
+          const Entry& e = es[k++];
+          if (!want) continue;
+          JETS_CHECK(rng.len[e.c] == dom.len[j], JETS_ERR_SHAPE, "elementwise block (%d,%d) maps %lld -> %lld elements", e.c, j,
+                     (long long)dom.len[j], (long long)rng.len[e.c]);
+          row.terms.push_back(make_term(e, ACC_SET, rng_off[e.c] * (int64_t)esz, 0));
+        }
+        if (want && j >= h && j < nloc + h && sel.has_next && j - h >= nloc - h) {   // the next rank's partial enters last
+          row.terms.push_back(copy_term(shi_off[j - h - (nloc - h)] * (int64_t)esz, 2));
+          row.wait |= 1 << GF_HI_READY; row.sig |= 1 << GS_NEXT_PREV_DONE;
+        }
+        if (!want || row.len == 0) continue;
+        if (j < h || j >= nloc + h) early.push_back(std::move(row));
+        else (row.wait ? late : plain).push_back(std::move(row));
+      }
+    }
+    std::vector<PRow> rows;
+    rows.reserve(early.size() + plain.size() + late.size());
+    for (auto* v : {&early, &plain, &late})
+      for (auto& r : *v) rows.push_back(std::move(r));
+    Step st;
+    st.kind = ST_FUSED;
+    st.src = Ref{0, 0}; st.dst = Ref{1, 0}; st.acc = ACC_SET;
+    int64_t longest = 0;
+    for (auto& r : rows) longest = std::max(longest, r.len);
+    const int variant = (ctx().fast_variant >= 0 && ctx().fast_variant <= 5) ? ctx().fast_variant : ((longest * (int64_t)esz >= 4 * 16384) ? 2 : 0);
+    JETS_CHECK(emit_bundle_rows(rows, st, hl, hr, false, variant), JETS_ERR_UNSUPPORTED,
+               "distributed banded apply: the operator's rows do not fit the bundle kernel's shared-memory rings");
+    st.fused.sig_owned = sel.owned;
+    st.fused.gated = sel.has_prev || sel.has_next;   // launched with the arena's flag words and halo bases
+    plan.steps.push_back(std::move(st));
   }
 
   // Dense entries sharing one orientation; groups = distinct output blocks.
@@ -1085,6 +1275,17 @@ std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok
     if (t->kind == K_BLOCK && t->C > 1 && m != JETS_MODE_DFT) acc = ACC_ADD;
   }
   b.lower(a, mode, Ref{1, 0}, Ref{0, 0}, acc);
+  plan->version = g_epoch;
+  return plan;
+}
+
+std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel& sel) {
+  auto plan = std::make_shared<Plan>();
+  g_esz = dsize(A_loc->dtype);
+  g_cplx = is_cplx(A_loc->dtype);
+  JETS_CHECK(!g_cplx, JETS_ERR_UNSUPPORTED, "distributed banded apply: complex eltypes are not implemented");
+  Builder b{*plan, A_loc->dtype, true, 0};
+  b.emit_banded(A_loc, halo, sel);
   plan->version = g_epoch;
   return plan;
 }

@@ -249,6 +249,91 @@ class LibComm:
         return r.value
 
 
+class DistOp:
+    """``jets_dist_op``: the rank-local rows of a block-row partitioned JopBlock behind ONE library call per
+    apply (include/jets_b200.h).  ``A_loc`` is the nloc x (nloc + 2*halo) JopBlock over the halo-extended
+    domain that ``build_local_operator`` makes (banded), or the nloc x ncol JopBlock over the whole domain
+    (``dense=True``).  The vectors are the rank's own shards; halo blocks, flags and staging live inside the
+    library.  Everything here is argument marshalling."""
+
+    def __init__(self, B, A_loc, halo=1, dense=False):
+        self.B, self.A_loc, self.halo, self.dense = B, A_loc, halo, dense
+        h = C.c_void_p()
+        if dense:
+            B.check(B.lib.jets_dist_op_create_dense(A_loc._h.h, C.byref(h)))
+        else:
+            B.check(B.lib.jets_dist_op_create(A_loc._h.h, halo, C.byref(h)))
+        self._h = h
+        dom, rng = B.domain(A_loc), B.range_(A_loc)
+        if dense:
+            world = max(1, B.lib.jets_dist_size())
+            self.own_space = B.JetSpace(dom.T, len(dom) // world)
+        else:
+            n = len(rng.spaces)
+            self.own_space = B.JetBSpace(dom.spaces[halo:halo + n])
+        self.range_space = rng
+
+    def close(self):
+        if self._h:
+            self.B.check(self.B.lib.jets_dist_op_destroy(self._h))
+            self._h = None
+
+    def __del__(self):
+        try:
+            if self._h and self.B.lib is not None:
+                self.B.lib.jets_dist_op_destroy(self._h)
+        except Exception:
+            pass
+
+    def forward(self, d, x, nonlinear=False):
+        """d = (A x)[own rows]; x = own domain shard."""
+        self.B.check(self.B.lib.jets_dist_apply(self._h, 0 if nonlinear else 1, d._h, x._h))
+        return d
+
+    def adjoint(self, m, d):
+        """m = (A' d)[own columns]; d = own range shard."""
+        self.B.check(self.B.lib.jets_dist_apply(self._h, 2, m._h, d._h))
+        return m
+
+    def normal_host(self, h_out_ptr, h_in_ptr, nchunks=0):
+        """host_out = A'(A host_in) on this rank's shards, chunk-pipelined (asynchronous; ``join`` to wait)."""
+        self.B.check(self.B.lib.jets_dist_apply_normal_host(self._h, C.c_void_p(h_out_ptr), C.c_void_p(h_in_ptr), nchunks))
+
+    def join(self):
+        self.B.check(self.B.lib.jets_dist_op_join(self._h))
+
+    def info(self, what):
+        return self.B.lib.jets_dist_op_info(self._h, what)
+
+    @property
+    def gate_timeouts(self):
+        return self.info(6)
+
+
+_BOOTSTRAP_KEEPALIVE = []
+
+
+def init_host_bootstrap(B, dist_mod, torch_mod, rank, world, group=None):
+    """jets_dist_init_host with torch.distributed as the out-of-band all-gather (a gloo group, or any group
+    that accepts CPU tensors).  Only set-up records and host scalars travel this way."""
+    AG = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64)
+
+    def _allgather(user, mine, all_, nbytes):
+        try:
+            t = torch_mod.frombuffer(bytearray(C.string_at(mine, nbytes)), dtype=torch_mod.uint8)
+            outs = [torch_mod.empty(nbytes, dtype=torch_mod.uint8) for _ in range(world)]
+            dist_mod.all_gather(outs, t, group=group)
+            C.memmove(all_, b"".join(bytes(o.numpy().tobytes()) for o in outs), world * nbytes)
+            return 0
+        except Exception:  # never let an exception unwind through the C frame
+            import traceback
+            traceback.print_exc()
+            return 1
+    cb = AG(_allgather)
+    _BOOTSTRAP_KEEPALIVE.append(cb)
+    B.check(B.lib.jets_dist_init_host(rank, world, cb, None))
+
+
 def init_nccl_from_torch(B, dist_mod, torch_mod, rank, world):
     """Create the library's NCCL communicator: rank 0 makes the ncclUniqueId, torch.distributed
     (already initialised by the launcher) broadcasts its 128 bytes."""

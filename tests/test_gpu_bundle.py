@@ -116,6 +116,26 @@ def test_many_inputs_and_many_rows(O, D, shape):
     both_ways(O, D, build, T, seed=R * 100 + C_)
 
 
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+@pytest.mark.parametrize("n", [4, 4100, 33_000])
+def test_weighted_stencil_blocks(O, D, T, n):
+    """w .* S(x) and S(w .* x) blocks (weighted derivatives and their adjoints) have straight-line kernel
+    paths (PAT_*_DIAG / PAT_DIAG_*): bit-identical to the oracle's stage-by-stage evaluation, block edges
+    included (the stencil needs the halo element of BOTH streams)."""
+    g = np.random.default_rng(31)
+    nb = 4
+    W = [[g.random(n).astype(T) - 0.5 for _ in range(nb)] for _ in range(nb)]
+
+    def build(K):
+        def blk(r, c):
+            S = K.JopStencil(T, n, ("fdiff", "lap")[(r + c) % 2])
+            Dg = K.JopDiagonal(W[r][c])
+            k = (2 * r + c) % 4
+            return Dg @ S if k == 0 else S @ Dg if k == 1 else K.adjoint(Dg @ S) if k == 2 else Dg
+        return K.blockop([[blk(r, c) for c in range(nb)] for r in range(nb)])
+    both_ways(O, D, build, T, seed=n)
+
+
 def test_ragged_rows_split_bundles(O, D):
     """Rows of different length cannot share a tile position: bundles close at every length change;
     zero blocks leave rows without terms (zero-filled) in the middle of the operator."""
