@@ -81,7 +81,9 @@ void* jets_stream_get(void);
 /* Fork/join onto one of two internal high-priority auxiliary streams, so that a communication call
  * overlaps the compute calls that follow: fork(a) makes the aux stream wait for everything issued
  * so far and directs subsequent calls to it; main() directs calls back to the main stream (the aux
- * work keeps running); join(a) makes the main stream wait for the aux stream.                   */
+ * work keeps running); join(a) makes the main stream wait for the aux stream.  One operator (and one
+ * reduction) must not be in flight on two streams at once: its plan's scheduler counters, temporaries and
+ * the context's reduction scratch are per plan / per context, not per stream.                    */
 int  jets_stream_fork(int aux);
 int  jets_stream_main(void);
 int  jets_stream_join(int aux);
@@ -288,27 +290,8 @@ int jets_dist_rank(void);
 int jets_dist_size(void);
 /* Sum a host scalar over ranks in rank order (bit-stable dot/norm): all-gathers the partials. */
 int jets_dist_sum_scalar(double* inout);
-/* Forward halo gather for a block-banded operator: recv the `nlo` last blocks of the previous
- * rank into lo and the `nhi` first blocks of the next rank into hi (either may be null).       */
-int jets_dist_halo_exchange(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
-/* Adjoint halo reduce: send partial contributions lo/hi to the neighbours and add what they
- * send into the first `nlo` / last `nhi` blocks of x, in rank order.                           */
-int jets_dist_halo_reduce(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
-/* Peer memory: registers the allocation behind x with the neighbouring ranks (CUDA IPC handles
- * all-gathered over NCCL; collective; every rank must hold the same layout).  Halo calls on a
- * registered vector move the blocks with the copy engines over NVLink -- they take no SM from the
- * kernels running meanwhile -- fenced by one tiny all-reduce before and after.                   */
-int jets_dist_register(jets_buf x);
-/* Forward halo gather in two halves: begin starts the transfer (asynchronously to the calls that
- * follow), end makes the stream wait for it.  Apply the interior rows in between.              */
-int jets_dist_halo_exchange_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
-int jets_dist_halo_exchange_end(void);
-/* The same in two halves, so that the transfer (begin: sends lo/hi, receives the mirror images into
- * library-owned staging) overlaps the local adjoint apply that writes x; end adds the received
- * partials into x's first nhi / last nlo blocks, previous rank first (deterministic).           */
-int jets_dist_halo_reduce_begin(jets_buf x, int32_t nlo, jets_buf lo, int32_t nhi, jets_buf hi);
-int jets_dist_halo_reduce_end(jets_buf x, int32_t nlo, int32_t nhi);
-/* Dense-structure exchange: all-gather domain shards / reduce-scatter partial domains.         */
+/* Dense-structure exchange on caller-owned vectors (what jets_dist_apply does inside for an operator made by
+ * jets_dist_op_create_dense): all-gather equal domain shards / reduce-scatter per-rank partial domains (NCCL).  */
 int jets_dist_allgather(jets_buf shard, jets_buf full);
 int jets_dist_reduce_scatter(jets_buf full, jets_buf shard);
 
@@ -348,6 +331,15 @@ int jets_dist_apply(jets_dist_op A, int mode, jets_buf out, jets_buf in);
  * everything issued so far (then jets_sync / events on the context stream see the results).              */
 int jets_dist_apply_normal_host(jets_dist_op A, void* host_out, const void* host_in, int32_t nchunks);
 int jets_dist_op_join(jets_dist_op A);
+/* The compute-stream issue order of that pipeline, from the block structure alone (pure host function, no GPU:
+ * the CPU tests replay it against NaN-poisoned buffers).  nz[r*(nloc+2*halo)+j] != 0 where block (r, j) of the
+ * rank-local operator is not a zero block.  items receives (what, k) pairs -- what: 0 forward of chunk k, 1
+ * adjoint of chunk k, 2 / 3 push the first / last halo blocks to the previous / next rank, 4 / 5 partial sums
+ * for the previous / next rank's columns; chunk_bounds the [begin, end) block rows of every chunk; up_need[k]
+ * the last upload chunk the forward of chunk k waits for.  Returns the number of items, -1 on error.        */
+int32_t jets_dist_pipeline_schedule(int32_t nloc, int32_t halo, int32_t nchunks, int32_t has_prev, int32_t has_next,
+                                    const uint8_t* nz, int32_t cap, int32_t* items, int32_t* chunk_bounds,
+                                    int32_t* up_need, int32_t* nchunks_out);
 /* what: 0 local block rows, 1 halo, 2 neighbours (bit0 previous, bit1 next), 3 chunks of the host pipeline,
  * 4 kernel launches of one jets_dist_apply, 5 kind (0 banded, 1 dense), 6 number of work units that gave up
  * waiting for a neighbour's flag (JETS_B200_GATE_TIMEOUT_MS, default 30 s; synchronises; results are invalid

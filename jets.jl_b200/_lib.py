@@ -138,13 +138,6 @@ SIGNATURES = {
     "jets_dist_rank": (_i, []),
     "jets_dist_size": (_i, []),
     "jets_dist_sum_scalar": (_i, [_pd]),
-    "jets_dist_halo_exchange": (_i, [_p, _i32, _p, _i32, _p]),
-    "jets_dist_halo_reduce": (_i, [_p, _i32, _p, _i32, _p]),
-    "jets_dist_register": (_i, [_p]),
-    "jets_dist_halo_exchange_begin": (_i, [_p, _i32, _p, _i32, _p]),
-    "jets_dist_halo_exchange_end": (_i, []),
-    "jets_dist_halo_reduce_begin": (_i, [_p, _i32, _p, _i32, _p]),
-    "jets_dist_halo_reduce_end": (_i, [_p, _i32, _i32]),
     "jets_dist_allgather": (_i, [_p, _p]),
     "jets_dist_reduce_scatter": (_i, [_p, _p]),
     "jets_dist_op_create": (_i, [_p, _i32, _pp]),
@@ -154,6 +147,7 @@ SIGNATURES = {
     "jets_dist_apply_normal_host": (_i, [_p, _p, _p, _i32]),
     "jets_dist_op_join": (_i, [_p]),
     "jets_dist_op_info": (_i32, [_p, _i32]),
+    "jets_dist_pipeline_schedule": (_i32, [_i32, _i32, _i32, _i32, _i32, _p, _i32, _pi32, _pi32, _pi32, _pi32]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

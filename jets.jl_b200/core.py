@@ -764,9 +764,16 @@ def state_(A, s):
         cur = A.meta.get(k)
         if isinstance(cur, DeviceArray):
             cur.assign(v)
+        elif k in _BAKED_STATE and k in A.meta:
+            # constants baked into the device operator when it was built (a Jets closure would see the new keyword
+            # argument; the kernels would silently keep the old value)
+            raise JetsError(5, f"state!: '{k}' is compiled into the device operator; build a new operator instead")
         else:
             A.meta[k] = v
     return A
+
+
+_BAKED_STATE = ("a", "p", "fn", "kind", "indices", "zero")
 
 
 def perfstat(A):

@@ -141,7 +141,7 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
   const int key = mode | ((accumulate ? 1 : 0) << 2) | ((io_ok ? 1 : 0) << 3) | (engine << 4);
   std::shared_ptr<Plan> plan;
   auto it = a->plans.find(key);
-  if (it != a->plans.end() && it->second->version == g_epoch) plan = it->second;
+  if (it != a->plans.end() && it->second->valid()) plan = it->second;
   else {
     plan = build_plan(a, mode, accumulate, io_ok, engine);
     a->plans[key] = plan;

@@ -396,7 +396,15 @@ struct Plan {
   std::vector<size_t> tmp_bytes;
   std::vector<void*> blobs;      // device table blobs (owned)
   int engines = 0;
+  // Validity: a plan holds raw pointers to the linearization points (mo) of the pointwise leaves it evaluated.
+  // It stays valid while every one of those leaves still points at the same buffer (`points`); trees with more
+  // than kMaxTrackedPoints such leaves fall back to the global point! epoch (`version`).  Plans that read no
+  // linearization point (every linear operator) are never invalidated by anybody's point!.
+  static constexpr size_t kMaxTrackedPoints = 64;
+  std::vector<std::pair<jets_op, const void*>> points;
+  bool uses_point = false;
   uint64_t version = 0;
+  bool valid() const;
   ~Plan();
 };
 

@@ -35,15 +35,6 @@ struct Dist {
   jets_allgather_fn host_ag = nullptr;   // host bootstrap (jets_dist_init_host): out-of-band all-gather of small records
   void* host_ag_user = nullptr;
   double* dev_gather = nullptr;  // [size] doubles
-  char* halo_tmp = nullptr;      // receive staging for halo_reduce
-  size_t halo_tmp_bytes = 0;
-  // peer memory (CUDA IPC): base pointers of the neighbours' copies of registered allocations
-  struct Peer { void* prev = nullptr; void* next = nullptr; size_t bytes = 0; };
-  std::map<const void*, Peer> peers;   // keyed by the local allocation base
-  cudaStream_t copy[2] = {nullptr, nullptr};          // copy-engine streams (pull from prev / next)
-  cudaEvent_t ev_begin = nullptr, ev_copy[2] = {nullptr, nullptr};
-  float* dev_flag = nullptr;     // 2 floats for the barrier all-reduce
-  bool pending_nccl = false;     // begin() used the NCCL fallback on an auxiliary stream
 };
 Dist& dist();
 void need_dist();

@@ -164,7 +164,6 @@ struct HostPipe {
   std::vector<cudaEvent_t> ev_up, ev_adj;
   cudaEvent_t ev_call = nullptr, ev_comp = nullptr, ev_down = nullptr;
   bool have_prev_step = false;
-  uint64_t version = 0;
   ~HostPipe() {
     for (cudaStream_t s : {s_up, s_comp, s_down})
       if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
@@ -206,75 +205,94 @@ void build_pipe_plans(jets_dist_op D, HostPipe& P) {
     s.mode = JETS_MODE_DFT;
     P.part[side] = build_banded_plan(D->A, h, s);
   }
-  P.version = g_epoch;
 }
 
-void make_pipe(jets_dist_op D, int nchunks) {
-  const int h = D->halo, n = D->nloc;
-  auto P = std::make_unique<HostPipe>();
+// Chunk bounds, dependencies and the issue order of the compute stream from the block structure alone
+// (nz(r, j): block (r, j) of the nloc x (nloc + 2h) rank-local operator is not a zero block).  Pure host code:
+// exported as jets_dist_pipeline_schedule so that the CPU tests can replay it.
+template <class NZ>
+void pipe_schedule(HostPipe& P, int n, int h, int nchunks, bool has_prev, bool has_next, NZ nz) {
   const int hh = std::max(1, h);
   nchunks = std::max(1, std::min(nchunks, n / hh));
   for (int k = 0; k < nchunks; ++k) {
     const int a = (int)((int64_t)n * k / nchunks), b = (int)((int64_t)n * (k + 1) / nchunks);
-    if (b > a) P->chunks.push_back({a, b});
+    if (b > a) P.chunks.push_back({a, b});
   }
-  const int K = P->K = (int)P->chunks.size();
+  const int K = P.K = (int)P.chunks.size();
   auto chunk_of = [&](int blk) {
     for (int k = 0; k < K; ++k)
-      if (blk >= P->chunks[k].first && blk < P->chunks[k].second) return k;
+      if (blk >= P.chunks[k].first && blk < P.chunks[k].second) return k;
     return K - 1;
   };
-  // dependencies from the block structure: forward chunk k reads own blocks -> uploads; adjoint chunk j reads
-  // the range blocks of the rows that hit its columns -> forward chunks
-  P->up_need.assign(K, 0);
-  P->fw_need.assign(K, {});
+  // forward chunk k reads own blocks -> uploads; adjoint chunk j reads the range blocks of the rows that hit its
+  // columns -> forward chunks.  "Late" = touches a neighbour's data (its kernel waits for a flag).
+  P.up_need.assign(K, 0);
+  P.fw_need.assign(K, {});
   std::vector<char> late_f(K, 0), late_a(K, 0);
   for (int k = 0; k < K; ++k) {
     int need = k;
-    for (int r = P->chunks[k].first; r < P->chunks[k].second; ++r)
+    for (int r = P.chunks[k].first; r < P.chunks[k].second; ++r)
       for (int j = 0; j < n + 2 * h; ++j) {
-        if (!block_nonzero(D->A, r, j)) continue;
-        if (j < h) { if (D->has_prev) late_f[k] = 1; }
-        else if (j >= n + h) { if (D->has_next) late_f[k] = 1; }
+        if (!nz(r, j)) continue;
+        if (j < h) { if (has_prev) late_f[k] = 1; }
+        else if (j >= n + h) { if (has_next) late_f[k] = 1; }
         else need = std::max(need, chunk_of(j - h));
       }
-    P->up_need[k] = need;
+    P.up_need[k] = need;
   }
   for (int jn = 0; jn < K; ++jn) {
     std::set<int> need;
     need.insert(jn);
-    for (int b = P->chunks[jn].first; b < P->chunks[jn].second; ++b)
+    for (int b = P.chunks[jn].first; b < P.chunks[jn].second; ++b)
       for (int r = 0; r < n; ++r)
-        if (block_nonzero(D->A, r, b + h)) need.insert(chunk_of(r));
-    P->fw_need[jn].assign(need.begin(), need.end());
+        if (nz(r, b + h)) need.insert(chunk_of(r));
+    P.fw_need[jn].assign(need.begin(), need.end());
     for (int f : need) late_a[jn] |= late_f[f];
-    if (D->has_prev && P->chunks[jn].first < h) late_a[jn] = 1;
-    if (D->has_next && P->chunks[jn].second > n - h) late_a[jn] = 1;
+    if (has_prev && P.chunks[jn].first < h) late_a[jn] = 1;
+    if (has_next && P.chunks[jn].second > n - h) late_a[jn] = 1;
   }
-  // issue order of the compute stream (pipeline.compute_schedule of round 1, dependencies generalised)
   std::vector<char> f_done(K, 0), a_done(K, 0);
   auto try_adj = [&]() {
     for (int jn = 0; jn < K; ++jn) {
       if (a_done[jn] || late_a[jn]) continue;
       bool ok = true;
-      for (int f : P->fw_need[jn]) ok = ok && f_done[f];
-      if (ok) { P->seq.push_back({1, jn}); a_done[jn] = 1; P->down_order.push_back(jn); }
+      for (int f : P.fw_need[jn]) ok = ok && f_done[f];
+      if (ok) { P.seq.push_back({1, jn}); a_done[jn] = 1; P.down_order.push_back(jn); }
     }
   };
-  if (D->has_prev) P->seq.push_back({2, 0});
+  // my first h blocks go to the previous rank as soon as they are uploaded; everything that does not touch a
+  // neighbour streams k / k-1 / k-2; the last h blocks can only be pushed once the upload is complete, and the
+  // chunks that wait for a neighbour follow, forward before the partial sums before the adjoint
+  if (has_prev) P.seq.push_back({2, 0});
   for (int k = 0; k < K; ++k) {
     if (late_f[k]) continue;
-    P->seq.push_back({0, k});
+    P.seq.push_back({0, k});
     f_done[k] = 1;
     try_adj();
   }
-  if (D->has_next) P->seq.push_back({3, 0});
+  if (has_next) P.seq.push_back({3, 0});
   for (int k = 0; k < K; ++k)
-    if (late_f[k]) { P->seq.push_back({0, k}); f_done[k] = 1; }
-  if (D->has_prev) P->seq.push_back({4, 0});
-  if (D->has_next) P->seq.push_back({5, 0});
+    if (late_f[k]) { P.seq.push_back({0, k}); f_done[k] = 1; }
+  if (has_prev) P.seq.push_back({4, 0});
+  if (has_next) P.seq.push_back({5, 0});
   for (int jn = 0; jn < K; ++jn)
-    if (!a_done[jn]) { P->seq.push_back({1, jn}); a_done[jn] = 1; P->down_order.push_back(jn); }
+    if (!a_done[jn]) { P.seq.push_back({1, jn}); a_done[jn] = 1; P.down_order.push_back(jn); }
+}
+
+bool pipe_plans_valid(const HostPipe& P) {
+  for (auto* v : {&P.fwd, &P.adj})
+    for (auto& p : *v)
+      if (!p->valid()) return false;
+  for (auto& p : {P.push[0], P.push[1], P.part[0], P.part[1]})
+    if (p && !p->valid()) return false;
+  return true;
+}
+
+void make_pipe(jets_dist_op D, int nchunks) {
+  const int h = D->halo, n = D->nloc;
+  auto P = std::make_unique<HostPipe>();
+  pipe_schedule(*P, n, h, nchunks, D->has_prev, D->has_next, [&](int r, int j) { return block_nonzero(D->A, r, j); });
+  const int K = P->K;
   build_pipe_plans(D, *P);
   // work vectors (own shards) and streams
   std::vector<int64_t> own(n), rng(n);
@@ -295,7 +313,7 @@ void make_pipe(jets_dist_op D, int nchunks) {
 
 void pipe_step(jets_dist_op D, char* host_out, const char* host_in) {
   HostPipe& P = *D->pipe;
-  if (P.version != g_epoch) build_pipe_plans(D, P);
+  if (!pipe_plans_valid(P)) build_pipe_plans(D, P);
   const size_t esz = dsize(D->dtype);
   const int K = P.K;
   // ordered after whatever the caller issued on the context stream
@@ -534,7 +552,7 @@ int jets_dist_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
     JETS_CHECK(buf_ok(in) && buf_ok(out), JETS_ERR_UNSUPPORTED, "distributed banded apply: in/out must be library-owned (guarded, 16-byte aligned) vectors");
     std::shared_ptr<Plan>& plan = D->mono[adj];
     const int pmode = adj ? JETS_MODE_DFT : (mode == JETS_MODE_F && !D->A->linear ? JETS_MODE_F : JETS_MODE_DF);
-    if (!plan || plan->version != g_epoch) {
+    if (!plan || !plan->valid()) {
       BandedSel s;
       s.mode = pmode;
       s.row_begin = 0; s.row_end = D->nloc;
@@ -572,6 +590,24 @@ int jets_dist_op_join(jets_dist_op D) {
       CUDA_TRY(cudaStreamWaitEvent(ctx().stream, D->pipe->ev_comp, 0));
     }
   });
+}
+
+int32_t jets_dist_pipeline_schedule(int32_t nloc, int32_t halo, int32_t nchunks, int32_t has_prev, int32_t has_next, const uint8_t* nz,
+                                    int32_t cap, int32_t* items, int32_t* chunk_bounds, int32_t* up_need, int32_t* nchunks_out) {
+  int32_t count = -1;
+  guard([&] {
+    JETS_CHECK(nloc >= 1 && halo >= 0 && halo <= kMaxHalo && nloc >= halo && nz && items && chunk_bounds && up_need && nchunks_out && cap >= 1,
+               JETS_ERR_INVALID, "bad arguments");
+    HostPipe P;
+    const int C = nloc + 2 * halo;
+    pipe_schedule(P, nloc, halo, nchunks, has_prev != 0, has_next != 0, [&](int r, int j) { return nz[(size_t)r * C + j] != 0; });
+    JETS_CHECK((int)P.seq.size() <= cap && P.K <= cap, JETS_ERR_INVALID, "schedule has %d items, capacity %d", (int)P.seq.size(), cap);
+    for (size_t i = 0; i < P.seq.size(); ++i) { items[2 * i] = P.seq[i].what; items[2 * i + 1] = P.seq[i].k; }
+    for (int k = 0; k < P.K; ++k) { chunk_bounds[2 * k] = P.chunks[k].first; chunk_bounds[2 * k + 1] = P.chunks[k].second; up_need[k] = P.up_need[k]; }
+    *nchunks_out = P.K;
+    count = (int32_t)P.seq.size();
+  });
+  return count;
 }
 
 int32_t jets_dist_op_info(jets_dist_op D, int32_t what) {

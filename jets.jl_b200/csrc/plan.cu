@@ -55,6 +55,7 @@ int chain_streams(const std::vector<FStage>& ch) {
 
 bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp);
 thread_local size_t g_esz = 8;  // element size of the plan being built
+thread_local std::vector<std::pair<jets_op, const void*>>* g_points = nullptr;  // linearization points the plan being built reads
 thread_local bool g_cplx = false;  // complex eltype: adjoint stages conjugate their operand stream
 
 bool has_stencil(const Entry& e) {
@@ -193,6 +194,7 @@ bool expand(jets_op a, int mode, Entries& out, Space& isp, Space& osp) {
       } else {
         JETS_CHECK(a->mo != nullptr, JETS_ERR_NO_POINT,
                    "Jacobian of a pointwise operator applied before point!/jacobian set mo");
+        if (g_points) g_points->push_back({a, a->mo->ptr()});
         e.chain.push_back(mk(S_PW_J, a->fn | ((g_cplx && mode == JETS_MODE_DFT) ? kConjFlag : 0), a->mo->ptr(), a->p, a->mo->guarded()));
       }
       out.push_back(e);
@@ -328,7 +330,8 @@ struct Builder {
     const size_t bytes = (size_t)elems * dsize(dtype);
     char* p = nullptr;
     CUDA_TRY(cudaMalloc(&p, bytes + 2 * kGuardBytes));
-    CUDA_TRY(cudaMemset(p, 0, bytes + 2 * kGuardBytes));
+    // on the context stream (non-blocking: the legacy stream's memset would not be ordered against it)
+    CUDA_TRY(cudaMemsetAsync(p, 0, bytes + 2 * kGuardBytes, ctx().stream));
     plan.tmps.push_back(p);
     plan.tmp_bytes.push_back(bytes);
     Ref r;
@@ -1260,11 +1263,39 @@ Plan::~Plan() {
   for (void* p : tmps) cudaFree(p);
   for (void* p : blobs) cudaFree(p);
 }
+bool Plan::valid() const {
+  if (!uses_point) return true;
+  if (points.size() > kMaxTrackedPoints) return version == g_epoch;
+  for (auto& pr : points)
+    if (!pr.first->mo || pr.first->mo->ptr() != pr.second) return false;
+  return true;
+}
+
+namespace {
+// Collects the linearization points a plan reads while it is being built (RAII around the builder calls).
+struct PointScope {
+  std::vector<std::pair<jets_op, const void*>> pts;
+  PointScope() { g_points = &pts; }
+  ~PointScope() { g_points = nullptr; }
+  void finish(Plan& p) {
+    p.uses_point = !pts.empty();
+    if (pts.size() <= Plan::kMaxTrackedPoints) {
+      std::sort(pts.begin(), pts.end());
+      pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
+      p.points = std::move(pts);
+    } else {
+      p.points.assign(Plan::kMaxTrackedPoints + 1, {nullptr, nullptr});   // marker: too many to track -> epoch
+    }
+    p.version = g_epoch;
+  }
+};
+}  // namespace
 
 std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok, int engine) {
   auto plan = std::make_shared<Plan>();
   g_esz = dsize(a->dtype);
   g_cplx = is_cplx(a->dtype);
+  PointScope scope;
   Builder b{*plan, a->dtype, io_ok, engine};
   int acc = ACC_SET;
   if (accumulate) {
@@ -1275,7 +1306,7 @@ std::shared_ptr<Plan> build_plan(jets_op a, int mode, int accumulate, bool io_ok
     if (t->kind == K_BLOCK && t->C > 1 && m != JETS_MODE_DFT) acc = ACC_ADD;
   }
   b.lower(a, mode, Ref{1, 0}, Ref{0, 0}, acc);
-  plan->version = g_epoch;
+  scope.finish(*plan);
   return plan;
 }
 
@@ -1284,9 +1315,10 @@ std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel
   g_esz = dsize(A_loc->dtype);
   g_cplx = is_cplx(A_loc->dtype);
   JETS_CHECK(!g_cplx, JETS_ERR_UNSUPPORTED, "distributed banded apply: complex eltypes are not implemented");
+  PointScope scope;
   Builder b{*plan, A_loc->dtype, true, 0};
   b.emit_banded(A_loc, halo, sel);
-  plan->version = g_epoch;
+  scope.finish(*plan);
   return plan;
 }
 

@@ -4,15 +4,15 @@ The reference has no distributed path (Jets.jl is single-process; DistributedJet
 package), so this is the build's own design: rank g owns a contiguous range of block rows, the
 matching range blocks of the result and the matching domain blocks.  For a block-banded operator
 (bandwidth b: op[r,c] == JopZeroBlock for |r-c| > b) the forward apply needs only b halo blocks
-from each neighbour (``jets_dist_halo_exchange``, NCCL send/recv over NVLink) instead of an
-all-gather of the whole domain, and the adjoint sends its partial contributions to the b blocks
-it does not own back to their owners, which add them in rank order (``jets_dist_halo_reduce``;
-deterministic).  Dense block structure uses ``jets_dist_allgather`` / ``jets_dist_reduce_scatter``.
+from each neighbour instead of an all-gather of the whole domain, and the adjoint sends its partial
+contributions to the b blocks it does not own back to their owners.  All of that -- the halo traffic over
+peer memory, the flags, the host-buffer pipeline -- happens INSIDE libjets_b200 behind one call per apply
+(``jets_dist_apply`` / ``jets_dist_apply_normal_host``, csrc/dist_op.cu); a dense block structure uses
+NCCL all-gather / reduce-scatter inside the same call.
 
-Everything here is host-side bookkeeping: pure functions of (nblk, world, rank) plus two
-communication strategies with the same interface -- ``LibComm`` (libjets_b200 + NCCL, device
-buffers) and any object with ``halo_exchange`` / ``halo_reduce`` / ``sum_scalar`` (the CPU tests
-drive the very same partition logic over torch.distributed gloo).
+What is left here is host-side bookkeeping: pure functions of (nblk, world, rank) that describe the
+rank-local operator (also driven over torch.distributed gloo by the CPU tests), the ``DistOp`` handle
+wrapper, and the communicator bootstrap.
 """
 from __future__ import annotations
 
@@ -84,169 +84,6 @@ def build_local_operator(K, part: RowPartition, make_block, zero_block):
     Z = zero_block()
     rows = [[Z if rc is None else make_block(*rc) for rc in row] for row in part.local_block_map()]
     return K.blockop(rows)
-
-
-def forward(K, part: RowPartition, comm, A_loc, x_ext, d_loc):
-    """d_loc = (A x)[own rows]: gather the halo blocks of x, then one local fused apply."""
-    h, n = part.halo, part.nloc
-    comm.halo_exchange(x_ext, h, n)
-    return K.mul_(d_loc, A_loc, x_ext)
-
-
-def adjoint(K, part: RowPartition, comm, A_loc, m_ext, d_loc):
-    """m_ext[own] = (A' d)[own columns]: one local fused adjoint apply produces partial sums for the
-    halo columns too; they are sent to their owners and added in rank order."""
-    h, n = part.halo, part.nloc
-    K.mul_(m_ext, K.adjoint(A_loc), d_loc)
-    comm.halo_reduce(m_ext, h, n)
-    return m_ext
-
-
-class OverlappedBanded:
-    """The rank-local part of a block-banded operator, split so that the halo traffic overlaps the
-    local compute (the exchange is ~0.2-0.8 ms against ~1 ms of local work at 8 GPUs):
-
-    forward   the halo gather runs on an auxiliary stream while the INTERIOR rows (which read own
-              blocks only) are applied; the `halo` first/last BOUNDARY rows follow once it landed.
-    adjoint   the partial sums for the neighbours' columns (they come from the boundary rows only)
-              are computed first and sent while the OWN columns are computed; the partials
-              received from the neighbours are added last, previous rank first (deterministic).
-
-    Every piece is an ordinary JopBlock over views of ``x_ext`` / ``d`` / ``m_ext``, so each output
-    block is computed by the same row sum as in the monolithic local operator.  ``K`` is the
-    backend (the device package, or a CPU stand-in in the gloo tests); ``comm`` provides
-    ``halo_exchange_begin/_end`` and ``halo_reduce_begin/_end`` (transfers asynchronous to the
-    compute calls issued in between).
-    """
-
-    def __init__(self, K, part: RowPartition, comm, make_block, zero_block, x_ext, d, m_ext, view):
-        self.K, self.part, self.comm = K, part, comm
-        h, n = part.halo, part.nloc
-        bmap = part.local_block_map()
-        Z = zero_block()
-        cache = {}
-
-        def blk(rc):
-            if rc is None:
-                return Z
-            if rc not in cache:
-                cache[rc] = make_block(*rc)
-            return cache[rc]
-
-        def sub(r0, r1, c0, c1):
-            return K.blockop([[blk(bmap[i][j]) for j in range(c0, c1)] for i in range(r0, r1)])
-        self.x_ext, self.d, self.m_ext = x_ext, d, m_ext
-        lo_i = h if part.has_prev else 0            # interior rows [lo_i, hi_i) read own blocks only
-        hi_i = n - h if part.has_next else n
-        self.f_int = None
-        if hi_i > lo_i:
-            self.f_int = (sub(lo_i, hi_i, lo_i, hi_i + 2 * h), view(d, lo_i, hi_i - lo_i), view(x_ext, lo_i, hi_i - lo_i + 2 * h))
-        self.f_bnd = []
-        if part.has_prev:
-            self.f_bnd.append((sub(0, h, 0, 3 * h), view(d, 0, h), view(x_ext, 0, 3 * h)))
-        if part.has_next:
-            self.f_bnd.append((sub(n - h, n, n - h, n + 2 * h), view(d, n - h, h), view(x_ext, n - h, 3 * h)))
-        # adjoint: partial sums for the neighbours' columns live in the halo blocks of m_ext
-        self.t_halo = []
-        if part.has_prev:       # extended columns [0,h) <- rows [0,h)
-            self.t_halo.append((K.adjoint(sub(0, h, 0, h)), view(m_ext, 0, h), view(d, 0, h)))
-        if part.has_next:       # extended columns [n+h, n+2h) <- rows [n-h, n)
-            self.t_halo.append((K.adjoint(sub(n - h, n, n + h, n + 2 * h)), view(m_ext, n + h, h), view(d, n - h, h)))
-        self.t_own = (K.adjoint(sub(0, n, h, n + h)), view(m_ext, h, n), d)
-
-    def forward(self):
-        """d = (A x)[own rows]; x_ext's own blocks hold x."""
-        K, c, p = self.K, self.comm, self.part
-        c.halo_exchange_begin(self.x_ext, p.halo, p.nloc)
-        if self.f_int is not None:
-            A, dv, xv = self.f_int
-            K.mul_(dv, A, xv)
-        c.halo_exchange_end()
-        for A, dv, xv in self.f_bnd:
-            K.mul_(dv, A, xv)
-        return self.d
-
-    def adjoint(self):
-        """m_ext[own] = (A' d)[own columns]."""
-        K, c, p = self.K, self.comm, self.part
-        for At, mv, dv in self.t_halo:
-            K.mul_(mv, At, dv)
-        c.halo_reduce_begin(self.m_ext, p.halo, p.nloc)
-        At, mv, dv = self.t_own
-        K.mul_(mv, At, dv)
-        c.halo_reduce_end(self.m_ext, p.halo, p.nloc)
-        return self.m_ext
-
-
-class LibComm:
-    """NCCL inside libjets_b200.so (device buffers).  ``x_ext`` is a DeviceArray with
-    nloc + 2*halo blocks."""
-
-    def __init__(self, B, part: RowPartition):
-        self.B, self.part = B, part
-        self._views = {}
-
-    def _view(self, x, first, n):
-        key = (id(x), first, n)
-        v = self._views.get(key)
-        if v is None:
-            h = C.c_void_p()
-            self.B.check(self.B.lib.jets_buf_view(x._h, first, n, C.byref(h)))
-            sp = self.B.JetBSpace(x.space.spaces[first:first + n])
-            v = self._views[key] = self.B.DeviceArray(h, sp, owner=x)
-        return v
-
-    def halo_exchange(self, x_ext, h, n):
-        if self.part.world == 1:
-            return
-        own, lo, hi = self._view(x_ext, h, n), self._view(x_ext, 0, h), self._view(x_ext, h + n, h)
-        self.B.check(self.B.lib.jets_dist_halo_exchange(own._h, h, lo._h, h, hi._h))
-
-    def halo_reduce(self, m_ext, h, n):
-        if self.part.world == 1:
-            return
-        own, lo, hi = self._view(m_ext, h, n), self._view(m_ext, 0, h), self._view(m_ext, h + n, h)
-        self.B.check(self.B.lib.jets_dist_halo_reduce(own._h, h, lo._h, h, hi._h))
-
-    def halo_reduce_begin(self, m_ext, h, n):
-        if self.part.world == 1:
-            return
-        own, lo, hi = self._view(m_ext, h, n), self._view(m_ext, 0, h), self._view(m_ext, h + n, h)
-        self.B.check(self.B.lib.jets_dist_halo_reduce_begin(own._h, h, lo._h, h, hi._h))
-
-    def halo_reduce_end(self, m_ext, h, n):
-        if self.part.world == 1:
-            return
-        self.B.check(self.B.lib.jets_dist_halo_reduce_end(self._view(m_ext, h, n)._h, h, h))
-
-    def halo_exchange_begin(self, x_ext, h, n):
-        if self.part.world == 1:
-            return
-        own, lo, hi = self._view(x_ext, h, n), self._view(x_ext, 0, h), self._view(x_ext, h + n, h)
-        self.B.check(self.B.lib.jets_dist_halo_exchange_begin(own._h, h, lo._h, h, hi._h))
-
-    def halo_exchange_end(self):
-        if self.part.world > 1:
-            self.B.check(self.B.lib.jets_dist_halo_exchange_end())
-
-    def register(self, x_ext):
-        """Collective: map the neighbours' copies of this vector (CUDA IPC) so that its halo traffic
-        goes through the copy engines over NVLink instead of NCCL kernels."""
-        if self.part.world > 1:
-            self.B.check(self.B.lib.jets_dist_register(x_ext._h))
-
-    def view(self, x, first, n):
-        return self._view(x, first, n)
-
-    def own(self, x_ext):
-        return self._view(x_ext, self.part.halo, self.part.nloc)
-
-    def sum_scalar(self, v):
-        if self.part.world == 1:
-            return float(v)
-        r = C.c_double(float(v))
-        self.B.check(self.B.lib.jets_dist_sum_scalar(C.byref(r)))
-        return r.value
 
 
 class DistOp:

@@ -1,8 +1,9 @@
 # JetsB200.jl -- the reference-side binding for libjets_b200.so.
 #
-# STATUS: UNEXECUTED.  Julia is not installed in the build image, so this file has never been
-# parsed or run; it is the stub a Jets.jl maintainer would add (see INTEGRATION.md) and is kept
-# deliberately thin so that it can be checked by inspection against include/jets_b200.h.
+# STATUS: EXPERIMENTAL / UNEXECUTED.  Julia is not installed in the build image, so this file has never
+# been parsed or run; it is the stub a Jets.jl maintainer would add (see INTEGRATION.md) and must be brought
+# up under Julia CI before use.  It is kept thin so that it can be checked by inspection against
+# include/jets_b200.h (tests/test_julia_shim_static.py checks every ccall's name, arity and argument classes).
 # Every `ccall` below names one entry point of that header; nothing else crosses the boundary.
 #
 # What it provides, in Jets' own vocabulary (src/Jets.jl line numbers of v1.4.1):
@@ -13,6 +14,9 @@
 #   * `LinearAlgebra.mul!` methods for JopLn/JopNl/JopAdjoint whose tree is all-B200: the WHOLE
 #     tree (block / sum / composite / adjoint) is handed to ONE `jets_apply`.  :390-392
 #   * device methods for dot / norm / fill! / extrema / broadcast-axpy.   :834-911
+#   * DistJop: the rank-local rows of a block-row partitioned JopBlock (one process per GPU) -- `mul!` is ONE
+#     `jets_dist_apply`, the halo exchange happens inside the kernel; `normal_host!` is the host-buffer pipeline.
+#   * device scalars, fused apply-axpby and CUDA-graph capture for CG/LSQR loops without host round trips.
 module JetsB200
 
 using Jets, LinearAlgebra
@@ -167,8 +171,9 @@ function Base.deepcopy_internal(x::B200Array{T}, d::IdDict) where {T}
     check(ccall((:jets_buf_retain, LIB), Cint, (Ptr{Cvoid},), x.h))
     d[x] = B200Array{T}(x.h, copy(x.blocklengths))
 end
-# The closures exist so that a B200 leaf is a legal Jet; they are only reached when a B200 leaf is
-# mixed with CPU operators (then each leaf is one jets_apply on its own).
+# The closures exist so that a B200 leaf is a legal Jet; they are reached when a tree mixes B200 leaves with
+# other operators that accept B200Arrays (mul! below falls back to Jets' own dispatch for such trees, and each
+# B200 leaf is then one jets_apply on its own).
 function leaf_apply!(out::B200Array, h::OpHandle, mode::Integer, in::B200Array)
     check(ccall((:jets_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint), h.h, mode, out.h, in.h, 0))
     out
@@ -199,11 +204,14 @@ function JopPointwiseB200(::Type{T}, n::Integer, fn::Integer = 0, p::Real = 0) w
     h = Ref{Ptr{Cvoid}}(C_NULL)
     check(ccall((:jets_op_pointwise, LIB), Cint, (Cint, Int64, Cint, Cdouble, Ptr{Ptr{Cvoid}}), dtype_code(T), n, fn, p, h))
     oh = OpHandle(h[])
+    # jets_apply refuses mode DFT on a nonlinear handle (src/Jets.jl:392): df!/df′! go through the linear view of
+    # the SAME jet (jets_op_as_linear: it sees the point that upstate! sets on `oh`)
+    lin = unary(:jets_op_as_linear, oh)
     sp = JetSpace(T, n)
-    JopNl(dom = sp, rng = sp, s = (b200 = oh,),
+    JopNl(dom = sp, rng = sp, s = (b200 = oh, b200lin = lin),
           f! = (d, m; b200, kw...) -> leaf_apply!(d, b200, 0, m),
-          df! = (d, m; mₒ, b200, kw...) -> leaf_apply!(d, b200, 1, m),
-          df′! = (m, d; mₒ, b200, kw...) -> leaf_apply!(m, b200, 2, d),
+          df! = (d, m; mₒ, b200lin, kw...) -> leaf_apply!(d, b200lin, 1, m),
+          df′! = (m, d; mₒ, b200lin, kw...) -> leaf_apply!(m, b200lin, 2, d),
           upstate! = (mₒ, s) -> check(ccall((:jets_op_set_point, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), s.b200.h, mₒ.h)))
 end
 function JopStencilB200(::Type{T}, n::Integer, kind::Integer = 0) where {T}
@@ -279,9 +287,140 @@ end
 const MODE_F, MODE_DF, MODE_DFT = Cint(0), Cint(1), Cint(2)
 apply!(d::B200Array, A::Jets.Jop, m::B200Array, mode::Cint) =
     (check(ccall((:jets_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cint), handle(A).h, mode, d.h, m.h, 0)); d)
-LinearAlgebra.mul!(d::B200Array, A::Jets.JopNl, m::B200Array) = apply!(d, A, m, MODE_F)
-LinearAlgebra.mul!(d::B200Array, A::Jets.JopLn, m::B200Array) = apply!(d, A, m, MODE_DF)
-LinearAlgebra.mul!(m::B200Array, A::Jets.JopAdjoint, d::B200Array) = apply!(m, A.op, d, MODE_DFT)
+# all-B200 trees go to the library whole; anything else takes Jets' own closure dispatch (:390-392)
+LinearAlgebra.mul!(d::B200Array, A::Jets.JopNl, m::B200Array) =
+    isb200(jet(A)) ? apply!(d, A, m, MODE_F) : invoke(mul!, Tuple{AbstractArray,Jets.JopNl,AbstractArray}, d, A, m)
+LinearAlgebra.mul!(d::B200Array, A::Jets.JopLn, m::B200Array) =
+    isb200(jet(A)) ? apply!(d, A, m, MODE_DF) : invoke(mul!, Tuple{AbstractArray,Jets.JopLn,AbstractArray}, d, A, m)
+LinearAlgebra.mul!(m::B200Array, A::Jets.JopAdjoint, d::B200Array) =
+    isb200(jet(A)) ? apply!(m, A.op, d, MODE_DFT) : invoke(mul!, Tuple{AbstractArray,Jets.JopAdjoint,AbstractArray}, m, A, d)
 Base.:*(A::Jets.Jop, m::B200Array) = mul!(b200zeros(range(A)), A, m)       # :399
+
+# point! of a composition evaluates the chain with `mul!(zeros(range(ops[i])), ops[i], _m)` (:578-589); zeros(R)
+# is a host Array, so the device version allocates on the device instead.  (Sums and block operators recurse
+# through point!/getblock only, :710-715 and :1059-1066, and need nothing.)
+function Jets.point!(j::Jets.Jet{D,R,typeof(Jets.JetComposite_f!)}, mₒ::B200Array) where {D<:Jets.JetAbstractSpace,R<:Jets.JetAbstractSpace}
+    j.mₒ = mₒ
+    ops = state(j).ops
+    _m = copy(mₒ)
+    for i = length(ops):-1:1
+        Jets.point!(jet(ops[i]), _m)
+        if i > 1
+            _m = mul!(b200zeros(range(ops[i])), ops[i], _m)
+        end
+    end
+    j
+end
+
+# ------------------------------------------------------------------ device scalars, fused updates, graphs ----
+# A CG/LSQR iteration without a host round trip (docs/src/index.md:235-246): reductions leave their result on
+# the device, updates read their coefficients from there, and the whole iteration is captured in a CUDA graph.
+mutable struct B200Scalar
+    h::Ptr{Cvoid}
+    function B200Scalar(v::Real = 0.0)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        check(ccall((:jets_scalar_create, LIB), Cint, (Ptr{Ptr{Cvoid}},), h))
+        s = new(h[])
+        finalizer(s -> ccall((:jets_scalar_destroy, LIB), Cint, (Ptr{Cvoid},), s.h), s)
+        check(ccall((:jets_scalar_set, LIB), Cint, (Ptr{Cvoid}, Cdouble), s.h, v))
+        s
+    end
+end
+function Base.getindex(s::B200Scalar)
+    v = Ref{Cdouble}(0)
+    check(ccall((:jets_scalar_get, LIB), Cint, (Ptr{Cvoid}, Ptr{Cdouble}), s.h, v)); v[]
+end
+dot!(out::B200Scalar, x::B200Array, y::B200Array) =
+    (check(ccall((:jets_dot_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}), x.h, y.h, out.h)); out)
+norm!(out::B200Scalar, x::B200Array, p::Real = 2) =
+    (check(ccall((:jets_norm_dev, LIB), Cint, (Ptr{Cvoid}, Cdouble, Ptr{Cvoid}), x.h, p, out.h)); out)
+# out[i] = a[i] (op[i]) b[i] in ONE launch; op in '+','-','*','/', 'n' (negate), 's' (sqrt), 'h' (hypot)
+function scalar_prog!(outs::Vector{B200Scalar}, ops::String, as::Vector{B200Scalar}, bs::Vector{<:Union{B200Scalar,Nothing}})
+    nul(x) = x === nothing ? C_NULL : x.h
+    check(ccall((:jets_scalar_prog, LIB), Cint, (Int32, Ptr{Ptr{Cvoid}}, Cstring, Ptr{Ptr{Cvoid}}, Ptr{Ptr{Cvoid}}),
+                length(outs), [o.h for o in outs], ops, [a.h for a in as], [nul(b) for b in bs]))
+end
+# out .= (sa or ca) .* x .+ (sb or cb) .* y with device-resident coefficients; flags: 1 negate, 2 reciprocal
+function axpby!(out::B200Array, sa::Union{B200Scalar,Nothing}, ca::Real, aflags::Integer, x::B200Array,
+                sb::Union{B200Scalar,Nothing}, cb::Real, bflags::Integer, y::B200Array)
+    nul(s) = s === nothing ? C_NULL : s.h
+    check(ccall((:jets_axpby_dev, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}),
+                out.h, nul(sa), ca, aflags, x.h, nul(sb), cb, bflags, y.h))
+    out
+end
+# out .= cA .* (A in) .+ cO .* out in ONE pass (the Golub-Kahan updates u = A v - alpha u, v = A'u - beta v)
+function mul_axpby!(out::B200Array, A::Jets.Jop, in::B200Array, sa::Union{B200Scalar,Nothing}, ca::Real, aflags::Integer,
+                    so::Union{B200Scalar,Nothing}, co::Real, oflags::Integer)
+    nul(s) = s === nothing ? C_NULL : s.h
+    mode = A isa Jets.JopAdjoint ? MODE_DFT : MODE_DF
+    B = A isa Jets.JopAdjoint ? A.op : A
+    check(ccall((:jets_apply_axpby, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}, Cdouble, Cint),
+                handle(B).h, mode, out.h, in.h, nul(sa), ca, aflags, nul(so), co, oflags))
+    out
+end
+# graph = capture() do ... library calls ... end; launch(graph) replays them
+mutable struct B200Graph
+    h::Ptr{Cvoid}
+end
+function capture(f)
+    check(ccall((:jets_graph_begin, LIB), Cint, ()))
+    g = Ref{Ptr{Cvoid}}(C_NULL)
+    try
+        f()
+    finally
+        check(ccall((:jets_graph_end, LIB), Cint, (Ptr{Ptr{Cvoid}},), g))
+    end
+    x = B200Graph(g[])
+    finalizer(x -> ccall((:jets_graph_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), x)
+    x
+end
+launch(g::B200Graph) = check(ccall((:jets_graph_launch, LIB), Cint, (Ptr{Cvoid},), g.h))
+sync() = check(ccall((:jets_sync, LIB), Cint, ()))
+
+# ------------------------------------------------------------------ distributed operators --------------------
+# One process per GPU.  The communicator is bootstrapped either through NCCL (unique id broadcast by the host
+# program, e.g. MPI.Bcast) or through a host all-gather callback (MPI.Allgather behind @cfunction): the banded
+# path needs only the latter -- its payload moves through peer memory inside the apply kernel.
+dist_unique_id() = (id = zeros(UInt8, 128); check(ccall((:jets_dist_unique_id, LIB), Cint, (Ptr{UInt8},), id)); id)
+dist_init(rank::Integer, nranks::Integer, id::Vector{UInt8}) =
+    check(ccall((:jets_dist_init, LIB), Cint, (Cint, Cint, Ptr{UInt8}), rank, nranks, id))
+# allgather = @cfunction(my_allgather, Cint, (Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Int64))
+dist_init_host(rank::Integer, nranks::Integer, allgather::Ptr{Cvoid}, user::Ptr{Cvoid} = C_NULL) =
+    check(ccall((:jets_dist_init_host, LIB), Cint, (Cint, Cint, Ptr{Cvoid}, Ptr{Cvoid}), rank, nranks, allgather, user))
+dist_shutdown() = check(ccall((:jets_dist_shutdown, LIB), Cint, ()))
+function dist_sum(v::Real)      # rank-ordered (bit-stable) sum of a host scalar: distributed dot / norm
+    r = Ref{Cdouble}(v)
+    check(ccall((:jets_dist_sum_scalar, LIB), Cint, (Ptr{Cdouble},), r)); r[]
+end
+
+# The rank-local rows of a block-row partitioned JopBlock.  `Aloc` is an ordinary all-B200 JopBlock: nloc x
+# (nloc + 2*halo) over [halo blocks of rank-1 | own blocks | halo blocks of rank+1] (banded), or nloc x ncol
+# over the whole domain (dense = true).  Vectors are the rank's own shards.
+mutable struct DistJop
+    h::Ptr{Cvoid}
+    Aloc::Jets.Jop
+    function DistJop(Aloc::Jets.Jop; halo::Integer = 1, dense::Bool = false)
+        h = Ref{Ptr{Cvoid}}(C_NULL)
+        if dense
+            check(ccall((:jets_dist_op_create_dense, LIB), Cint, (Ptr{Cvoid}, Ptr{Ptr{Cvoid}}), handle(Aloc).h, h))
+        else
+            check(ccall((:jets_dist_op_create, LIB), Cint, (Ptr{Cvoid}, Int32, Ptr{Ptr{Cvoid}}), handle(Aloc).h, halo, h))
+        end
+        x = new(h[], Aloc)
+        finalizer(x -> ccall((:jets_dist_op_destroy, LIB), Cint, (Ptr{Cvoid},), x.h), x)
+        x
+    end
+end
+# mul!(d, A, m) / mul!(m, A', d) on the shards: ONE call, one kernel launch per rank (banded)
+LinearAlgebra.mul!(d::B200Array, A::DistJop, m::B200Array) =
+    (check(ccall((:jets_dist_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), A.h, MODE_DF, d.h, m.h)); d)
+mul_adjoint!(m::B200Array, A::DistJop, d::B200Array) =
+    (check(ccall((:jets_dist_apply, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}), A.h, MODE_DFT, m.h, d.h)); m)
+# host_out = A'(A host_in) for this rank's shards, chunk-pipelined inside the library (pinned host arrays)
+function normal_host!(host_out::Vector{T}, A::DistJop, host_in::Vector{T}; nchunks::Integer = 0) where {T}
+    check(ccall((:jets_dist_apply_normal_host, LIB), Cint, (Ptr{Cvoid}, Ptr{T}, Ptr{T}, Int32), A.h, host_out, host_in, nchunks))
+    host_out
+end
+join!(A::DistJop) = check(ccall((:jets_dist_op_join, LIB), Cint, (Ptr{Cvoid},), A.h))
 
 end # module

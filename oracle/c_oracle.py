@@ -82,3 +82,11 @@ def chain_apply(w, mo, x, adj=False, mode=0, out=None):
 
 def num_threads():
     return load().jets_ref_num_threads()
+
+
+def use_all_cores():
+    """Sets the OpenMP team to every core this process may run on (ignores OMP_NUM_THREADS) and returns it."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib = load()
+    lib.jets_ref_set_threads(int(n))
+    return lib.jets_ref_num_threads()

@@ -44,6 +44,16 @@ int jets_ref_num_threads(void) {
 #endif
 }
 
+/* The CPU arm of bench.py asks for every host core explicitly: launchers such as torchrun export
+ * OMP_NUM_THREADS=1, which would silently turn the "all host threads" baseline into a one-thread one. */
+void jets_ref_set_threads(int n) {
+#ifdef _OPENMP
+  if (n >= 1) omp_set_num_threads(n);
+#else
+  (void)n;
+#endif
+}
+
 #define DEFINE(T, SUF)                                                                              \
   /* leaf applied to a whole block: out = op(in) (adj: op'(in)) */                                  \
   static void leaf_apply_##SUF(const jets_ref_leaf* op, int adj, T* out, const T* in, int64_t n,   \

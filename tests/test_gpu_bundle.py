@@ -239,10 +239,10 @@ def test_large_rows_many_units(D):
 
 @pytest.mark.parametrize("nchunks", [1, 3, 12])
 def test_chunked_host_pipeline_matches_monolithic_apply(D, nchunks):
-    """pipeline.ChunkedBandedApply (host m -> A -> A' -> host m', chunked over block rows on three
-    streams) must reproduce the monolithic device applies bit for bit, step after step."""
+    """jets_dist_apply_normal_host (host m -> A -> A' -> host m', chunked over block rows on three streams
+    inside the library; here one rank, no neighbours) must reproduce the monolithic device applies bit for
+    bit, step after step -- through jets_dist_apply AND through plain jets_apply on the same block rows."""
     import torch
-    import ctypes as C
     B = D.B
     T = np.float32
     nblk, n = 12, 40_000
@@ -255,33 +255,36 @@ def test_chunked_host_pipeline_matches_monolithic_apply(D, nchunks):
         if r == c:
             return B.JopDiagonal(B.getblock(W, r + 1))
         return B.JopStencil(T, n, "fdiff") if c == r + 1 else B.JopStencil(T, n, "lap")
-    A = B.dist.build_local_operator(B, part, make_block, lambda: Z)
-    comm = B.dist.LibComm(B, part)
-    x_ext, m_ext, d = B.zeros(B.domain(A)), B.zeros(B.domain(A)), B.zeros(B.range_(A))
-    # a private non-default stream (kept alive for the rest of the session: the library adopts it,
-    # and CUDA-graph capture in later tests is impossible on the legacy default stream)
-    stream = _KEEP.setdefault("stream", torch.cuda.Stream())
-    pipe = B.pipeline.ChunkedBandedApply(B, torch, part, make_block, lambda: Z, x_ext, d, m_ext, nchunks=nchunks)
+    A = B.dist.build_local_operator(B, part, make_block, lambda: Z)     # nblk x (nblk + 2), zero halo columns
+    op = B.dist.DistOp(B, A, halo=1)
+    own = B.JetBSpace([sp] * nblk)
     g = np.random.default_rng(22)
     h_in = torch.empty(nblk * n, dtype=torch.float32, pin_memory=True)
     h_out = torch.empty(nblk * n, dtype=torch.float32, pin_memory=True)
-    mine = C.c_void_p(stream.cuda_stream)
-    B.check(B.lib.jets_stream_set(mine))   # the library adopts torch's stream for the monolithic reference
     try:
         for it in range(3):
             m = g.random(nblk * n).astype(T)
             h_in.copy_(torch.from_numpy(m))
             h_out.zero_()
-            pipe.step(h_in, h_out, stream).synchronize()
+            op.normal_host(h_out.data_ptr(), h_in.data_ptr(), nchunks)
+            op.join()
+            B.sync()
             got = h_out.numpy().copy()
-            # monolithic reference on fresh buffers
-            x2, m2, d2 = B.zeros(B.domain(A)), B.zeros(B.domain(A)), B.zeros(B.range_(A))
-            comm.own(x2).from_host(m)
-            B.mul_(d2, A, x2)
-            B.mul_(m2, B.adjoint(A), d2)
-            assert_bits(got, comm.own(m2).to_host())
+            assert op.info(3) == min(nchunks, nblk)
+            # one jets_dist_apply per direction on device-resident shards
+            x, d2, m2 = B.to_device(m, own), B.zeros(own), B.zeros(own)
+            op.forward(d2, x)
+            op.adjoint(m2, d2)
+            assert_bits(got, m2.to_host())
+            # and the plain operator path over the halo-extended vectors (halo blocks zero, unread)
+            x_ext, m_ext, d3 = B.zeros(B.domain(A)), B.zeros(B.domain(A)), B.zeros(B.range_(A))
+            B.reshape(x_ext, B.JetSpace(T, (nblk + 2) * n)).from_host(np.concatenate([np.zeros(n, T), m, np.zeros(n, T)]))
+            B.mul_(d3, A, x_ext)
+            B.mul_(m_ext, B.adjoint(A), d3)
+            assert_bits(got, m_ext.to_host()[n:-n])
     finally:
         B.sync()
+        op.close()
 
 
 @pytest.mark.parametrize("env", [

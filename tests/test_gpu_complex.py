@@ -320,6 +320,10 @@ def test_state_plumbing(D):  # state/state!/perfstat/close: src/Jets.jl:264-290,
     w2 = g.random(n)
     B.state_(A, {"diagonal": w2})              # state!: the kernels read the new values
     assert np.array_equal(Cmp * m, 2.5 * (w2 * m))
+    with pytest.raises(B.JetsError):           # constants compiled into the device operator cannot be swapped silently
+        B.state_(S, {"a": 3.0})
+    B.state_(S, {"note": "user metadata"})     # anything else is host-side state, as in the reference
+    assert B.state(S, "note") == "user metadata" and B.state(S, "a") == 2.5
     ps = B.perfstat(Cmp)
     assert ps["engines"] == ["tma"] and ps["launches"] == 1
     assert B.close(A) is False and B.close(B.compose(S, B.JopDiagonal(w))) is None

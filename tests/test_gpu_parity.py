@@ -638,6 +638,18 @@ def test_unaligned_blocks_and_wrapped_memory(O, D):
     B.sync()
     assert torch.equal(y._owner, t * 2)
     assert "ldg" in B.plan_info(A)["engines"]
+    # operator STATE in caller-owned (unguarded) memory under a stencil chain, applied to library-owned vectors:
+    # the TMA engines would fetch 16 bytes before and up to 31 bytes past the caller's allocation, so
+    # the planner must route the whole launch to the guarded-load engine -- and the result must not change
+    n = 4096
+    wt = torch.rand(n, dtype=torch.float32, device="cuda")
+    S = B.JopStencil(T, n, "lap")
+    Aw = S @ B.JopDiagonal(B.wrap_torch(wt))              # S(w .* x): the stencil reads w[i-1], w[i+1]
+    Ag = S @ B.JopDiagonal(wt.cpu().numpy())              # the same operator with library-owned state
+    xin = B.rand(B.JetSpace(T, n), seed=5)
+    assert_bits((Aw * xin).to_host(), (Ag * xin).to_host())
+    assert_bits((Aw.T * xin).to_host(), (Ag.T * xin).to_host())
+    assert B.plan_info(Aw)["engines"] == ["ldg"] and B.plan_info(Ag)["engines"] == ["tma"]
 
 
 def test_shape_and_dtype_errors(D):

@@ -21,7 +21,7 @@ def c_declarations():
         kinds = []
         for p in params.split(","):
             p = p.strip()
-            if "*" in p or "[" in p or re.match(r"(const\s+)?jets_(buf|op|scalar)\b", p):
+            if "*" in p or "[" in p or re.match(r"(const\s+)?jets_(buf|op|scalar|dist_op|allgather_fn)\b", p):
                 kinds.append("ptr")
             elif re.match(r"(const\s+)?(double|float)\b", p):
                 kinds.append("fp")
@@ -81,6 +81,17 @@ def test_every_ccall_matches_a_declared_entry_point():
             assert julia_kind(t) == w, f"julia/JetsB200.jl:{line}: {name} argument {k + 1}: Julia type {t} vs C parameter class {w}"
 
 
+def test_nonlinear_leaf_uses_the_linear_view_for_its_jacobian():
+    """jets_apply rejects mode DFT on a nonlinear handle, so the pointwise leaf's df!/df'! closures must
+    go through a jets_op_as_linear view; and a composition's point! must not allocate host zeros."""
+    src = open(os.path.join(ROOT, "julia", "JetsB200.jl")).read()
+    body = src[src.index("function JopPointwiseB200"):src.index("function JopStencilB200")]
+    assert "unary(:jets_op_as_linear, oh)" in body
+    assert "leaf_apply!(m, b200lin, 2, d)" in body and "leaf_apply!(d, b200lin, 1, m)" in body
+    assert "leaf_apply!(m, b200, 2, d)" not in body
+    assert "function Jets.point!(j::Jets.Jet{D,R,typeof(Jets.JetComposite_f!)}, mₒ::B200Array)" in src
+
+
 def test_shim_binds_the_hot_path():
     # (jacobian is Jets' own: copy(jet, false) -> deepcopy of the state -> jets_op_clone, then point! ->
     # the leaf's upstate! -> jets_op_set_point)
@@ -88,5 +99,10 @@ def test_shim_binds_the_hot_path():
     for must in ("jets_init", "jets_buf_create", "jets_buf_upload", "jets_buf_download", "jets_buf_view", "jets_op_diag",
                  "jets_op_pointwise", "jets_op_stencil", "jets_op_dense", "jets_op_compose", "jets_op_sum", "jets_op_block",
                  "jets_op_adjoint", "jets_op_clone", "jets_op_set_point", "jets_apply", "jets_dot", "jets_norm",
-                 "jets_lincomb", "jets_op_destroy", "jets_buf_destroy", "jets_last_error"):
+                 "jets_lincomb", "jets_op_destroy", "jets_buf_destroy", "jets_last_error",
+                 # one call per distributed apply, the host-buffer pipeline, and the solver-loop plumbing
+                 "jets_dist_init", "jets_dist_init_host", "jets_dist_op_create", "jets_dist_op_create_dense", "jets_dist_apply",
+                 "jets_dist_apply_normal_host", "jets_dist_op_join", "jets_dist_op_destroy", "jets_dist_sum_scalar",
+                 "jets_graph_begin", "jets_graph_end", "jets_graph_launch", "jets_apply_axpby", "jets_scalar_create",
+                 "jets_scalar_prog", "jets_dot_dev", "jets_norm_dev", "jets_axpby_dev", "jets_op_as_linear"):
         assert must in bound, f"the Julia shim does not bind {must}"
