@@ -412,6 +412,16 @@ def run_ours(args):
     gate_timeouts = op.gate_timeouts
     engine = {"launches_per_apply": op.info(4), "neighbours": op.info(2), "gate_timeouts": gate_timeouts}
 
+    if args.no_e2e:     # tuning runs only: a line without e2e is not a bench result
+        if rank == 0:
+            print(json.dumps({"tuning_only": True, "n_gpus": world, "value": round(value, 2), "launch_ms": [round(k_fwd, 4), round(k_adj, 4)],
+                              "frac": round((bytes_apply / world) / ((k_fwd + k_adj) / 2 * 1e-3) / 1e9 / peaks()[0], 4),
+                              "dpt": dpt, "checksum": checksum, "engine": engine}), flush=True)
+        S["op"].close()
+        if world > 1:
+            B.check(lib.jets_dist_shutdown())
+            dist.destroy_process_group()
+        return
     # ---- end to end through the C ABI with HOST buffers (pinned): jets_dist_apply_normal_host moves this rank's
     # shard H2D, applies A then A', and moves the result D2H, chunk-pipelined inside the library
     nloc = rl * blk
@@ -864,6 +874,7 @@ def main():
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the block length (debugging only)")
     ap.add_argument("--no-extra", action="store_true", help="skip the secondary configs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--no-e2e", action="store_true", help="tuning runs: device-resident timing only (prints a reduced line)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

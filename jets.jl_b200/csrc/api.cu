@@ -291,6 +291,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_NO_PDL")) c.no_pdl = atoi(v);
     if (const char* v = getenv("JETS_B200_STATIC_SCHED")) c.static_sched = atoi(v);
     if (const char* v = getenv("JETS_B200_GRID")) c.grid_limit = atoi(v);
+    if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);
     c.ready = true;
   });
 }

@@ -72,6 +72,7 @@ struct Context {
   int bundle_ns = 0;
   int bundle_bmax = 0;
   int no_pdl = 0;
+  int dist_early_ctas = 16;  // JETS_B200_DIST_EARLY_CTAS: CTAs that take the peer-store units of a distributed apply (0: all)
   int grid_limit = 0;    // JETS_B200_GRID=n: launch the fused kernels with at most n CTAs (leaves SMs to concurrent kernels)
   int static_sched = 0;  // JETS_B200_STATIC_SCHED=1: deal units round-robin instead of claiming them dynamically        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
   double* host_scratch = nullptr;  // pinned, 64 doubles
@@ -253,8 +254,8 @@ struct GroupRec {    // 272 bytes
 // at the same tile position, and every input tile lives in a shared-memory ring ("x ring") from
 // its first to its last use, so a block-tridiagonal row costs 2 tile loads instead of 4.
 enum : int { XF_LOAD = 1, XF_RELEASE = 2 };
-// BGroupRec::flags: bits 4-5 select the output base (0 = the apply's `out`, k = GateLaunch::out_alt[k-1]);
-// bits 8-11 (only on the LAST group of a unit) name the cross-rank signals the finished unit counts towards.
+// BGroupRec::flags: bits 4-5 select the output base (0 = the apply's `out`, k = GateLaunch::out_alt[k-1]).
+// (BG_SIG_SHIFT: where the kernel's slot metadata carries a bundle's signal mask.)
 enum : int { BG_ROW_FIRST = 1, BG_ROW_LAST = 2, BG_ACC = 4, BG_OUT_ALT_SHIFT = 4, BG_SIG_SHIFT = 8 };
 // BGroupRec::xrel_mask: bit t = input of term t is an offset from a base pointer; bits 8+2t..9+2t select
 // that base (0 = the apply's `in`, k = GateLaunch::in_alt[k-1]).
@@ -282,13 +283,14 @@ struct BGroupRec {   // 320 bytes
 static_assert(offsetof(BGroupRec, nsstreams) % 16 == 0 && offsetof(BGroupRec, terms) % 16 == 0 &&
               offsetof(BGroupRec, stages) % 16 == 0, "BGroupRec alignment");
 static_assert(sizeof(BGroupRec) == 320, "BGroupRec layout");
-struct BundleRec {   // 32 bytes: consecutive output rows of equal length walked by one CTA per tile position
+struct BundleRec {   // 40 bytes: consecutive output rows of equal length walked by one CTA per tile position
   int64_t unit_begin;          // first (bundle, position) unit of this bundle in the launch-wide enumeration
   int64_t len;                 // row length (elements)
   int32_t group_begin, ngroups;
   int32_t nx;                  // x-ring allocations per unit
   int32_t gate;                // bits 0-3: flag words the producer waits for before the unit's first load;
                                // bits 4-7: signals a finished unit of this bundle counts towards
+  int32_t claim_begin, chunk;  // dynamic scheduling: first claim of this bundle, units per claim
 };
 
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
@@ -338,6 +340,8 @@ struct DevFused {   // device copy + launch geometry
   void* blob = nullptr;
   // cross-rank gating (distributed banded apply, dist.cu): units per signal, the signals this launch must
   // raise even when no unit feeds them, and the completion counters (in the plan blob)
+  int64_t nclaims = 0;        // dynamic claims (bundle-major)
+  int64_t early_claims = 0;   // leading claims whose units store to peer memory (taken by a few CTAs only)
   int32_t sig_total[kGateFlags] = {0, 0, 0, 0};
   int32_t sig_owned = 0;
   int32_t* sig_done = nullptr;

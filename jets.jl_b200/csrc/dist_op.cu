@@ -73,6 +73,7 @@ struct jets_dist_op_s {
   ArenaLayout lay{}, prev_lay{}, next_lay{};
   char* prev_base = nullptr;         // the neighbours' arenas mapped into this process
   char* next_base = nullptr;
+  bool loopback = false;             // single-process test mode: prev_base == next_base == arena
   uint32_t epoch[2] = {0, 0};        // forward / adjoint applies issued so far
   std::shared_ptr<Plan> mono[2];
   std::unique_ptr<HostPipe> pipe;
@@ -396,8 +397,8 @@ void destroy_op(jets_dist_op D) {
   if (D->pipe) D->pipe.reset();
   cudaStreamSynchronize(ctx().stream);
   D->mono[0].reset(); D->mono[1].reset();
-  if (D->prev_base) cudaIpcCloseMemHandle(D->prev_base);
-  if (D->next_base) cudaIpcCloseMemHandle(D->next_base);
+  if (D->prev_base && !D->loopback) cudaIpcCloseMemHandle(D->prev_base);
+  if (D->next_base && !D->loopback) cudaIpcCloseMemHandle(D->next_base);
   if (D->arena) cudaFree(D->arena);
   if (D->full) jets_buf_destroy(D->full);
   if (D->A) jets_op_destroy(D->A);
@@ -411,6 +412,7 @@ void dist_ops_shutdown() {
   // NCCL is going away: release the peer mappings while the neighbours are still alive
   for (jets_dist_op D : live_ops()) {
     if (D->pipe) D->pipe.reset();
+    if (D->loopback) continue;
     if (D->prev_base) { cudaIpcCloseMemHandle(D->prev_base); D->prev_base = nullptr; }
     if (D->next_base) { cudaIpcCloseMemHandle(D->next_base); D->next_base = nullptr; }
     D->has_prev = D->has_next = false;
@@ -438,6 +440,11 @@ int jets_dist_op_create(jets_op A_loc, int32_t halo, jets_dist_op* out) {
     D->halo = halo; D->nloc = A_loc->R; D->dtype = A_loc->dtype;
     D->has_prev = d.ready && d.rank > 0 && halo > 0;
     D->has_next = d.ready && d.rank + 1 < d.size && halo > 0;
+    // JETS_B200_DIST_LOOPBACK=1 (single process): the rank is its own previous and next neighbour -- a block-
+    // CIRCULANT operator -- so that the whole gated path (push units, flag waits, signals) runs, and can be
+    // profiled, on one GPU without a second process
+    const bool loopback = !(d.ready && d.size > 1) && halo > 0 && getenv("JETS_B200_DIST_LOOPBACK") && atoi(getenv("JETS_B200_DIST_LOOPBACK"));
+    if (loopback) D->has_prev = D->has_next = true;
     const int n = D->nloc, h = halo;
     const size_t esz = dsize(D->dtype);
     for (int b = 0; b < n; ++b) { D->n_own += A_loc->dom.len[h + b]; D->n_rng += A_loc->rng.len[b]; }
@@ -497,6 +504,11 @@ int jets_dist_op_create(jets_op A_loc, int32_t halo, jets_dist_op* out) {
           JETS_CHECK(D->next_lay.len_first[k] == L.len_hi[k] && D->next_lay.len_lo[k] == L.len_last[k], JETS_ERR_SHAPE,
                      "halo block %d: this rank and rank %d disagree about the block lengths at their common boundary", k, d.rank + 1);
       }
+    }
+    if (loopback) {
+      D->loopback = true;
+      D->prev_base = D->next_base = D->arena;
+      D->prev_lay = D->next_lay = L;
     }
     A_loc->refs++;
     D->A = A_loc;

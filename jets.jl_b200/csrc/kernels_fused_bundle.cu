@@ -35,7 +35,9 @@ constexpr int kSmemLimit = 227 * 1024;
 constexpr int kHdr = 3 * 128 + kMaxRing * 80;          // sfull | sempty | xempty | slot metadata
 constexpr int kHdrAligned = (kHdr + 127) & ~127;
 
-enum : int { F_FIRST = 1, F_LAST = 2, F_END = 4, F_ACC = 8, F_BLK0 = 32, F_BLKEND = 64 };
+// F_FLUSH: a marker slot without data -- this CTA has finished `nvalid` units that feed the cross-rank signals in
+// bits 8-11 (also carried by the F_END sentinel)
+enum : int { F_FIRST = 1, F_LAST = 2, F_END = 4, F_ACC = 8, F_BLK0 = 32, F_BLKEND = 64, F_FLUSH = 128 };
 
 struct BMeta {                    // 80 bytes, 16B aligned
   char* out_tile;                 // absolute address of out[tile_start]
@@ -52,8 +54,13 @@ struct BundleParams {
   int32_t nbundles, NX, NS, sstreams, G, tile_elems;
   int64_t nunits;
   int64_t table_bytes;        // bytes of the plan tables starting at `groups` (prefetch bound)
-  int32_t* sched;             // {next chunk, finished CTAs} or null (static round-robin)
-  int32_t chunk;              // units per claim
+  int32_t* sched;             // {next claim, finished CTAs, next early claim} or null (static round-robin)
+  int64_t nclaims;            // dynamic claims in the launch (bundle-major, BundleRec::claim_begin / chunk)
+  // the first `early_claims` claims (peer-memory stores of the distributed apply: NVLink-bound, not HBM-bound) are
+  // taken from their own queue by the first `early_ctas` CTAs only, so that the other SMs stream the HBM-bound
+  // units meanwhile instead of all queueing behind the link
+  int32_t early_ctas;
+  int64_t early_claims;
   const char* in;
   char* out;
   int32_t hl, hr;
@@ -157,6 +164,17 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     uint32_t xbase = 0;            // x-ring allocations made by this CTA so far
     int b = 0;
     int waited = 0;                // gate flags this CTA has already seen raised (epochs only grow)
+    int cur_sig = 0, sig_units = 0;   // signals the current bundle feeds / units of it this CTA has issued
+    auto flush_marker = [&](int kind) {
+      if (lane == 0) {
+        mbar_wait(sempty0 + 8 * slot, par ^ 1);
+        meta[slot].flags = kind | (cur_sig << BG_SIG_SHIFT);
+        meta[slot].nvalid = sig_units;
+        mbar_arrive(sfull0 + 8 * slot);
+      }
+      if (++slot == NS) { slot = 0; par ^= 1; }
+      __syncwarp();
+    };
     int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
 
     // One lane issues one term group of unit `q` into state slot `my`.
@@ -202,7 +220,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       M.rec = rec;
       const int fl = (tile_start == 0 ? F_BLK0 : 0) | (rem <= te ? F_BLKEND : 0) |
                      ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
-                     ((gflags & BG_ACC) ? F_ACC : 0) | (gflags & (0xF << BG_SIG_SHIFT));
+                     ((gflags & BG_ACC) ? F_ACC : 0);
       *reinterpret_cast<int4*>(&M.nvalid) = make_int4(nvalid, fl, nterms, xrelease);
       *reinterpret_cast<uint4*>(&M.terms[0]) = *reinterpret_cast<uint4*>(&tt[0]);
       *reinterpret_cast<uint4*>(&M.terms[2]) = *reinterpret_cast<uint4*>(&tt[2]);
@@ -237,25 +255,57 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     const int64_t stride = dyn ? 1 : (int64_t)gridDim.x;
     // claim_issue() starts the atomic (lane 0 keeps the ticket in a register); claim_take() broadcasts
     // it when the next chunk is actually needed, so the atomic's latency hides behind a whole chunk.
+    // Dynamic claims are enumerated per bundle (BundleRec::claim_begin / chunk: the planner sizes a claim for
+    // roughly equal work, many light units or one heavy one); a claim never spans two bundles.
     int ticket = 0;
-    auto claim_issue = [&]() { if (lane == 0) ticket = atomicAdd(P.sched, 1); };
-    auto claim_take = [&]() -> int64_t { return (int64_t)__shfl_sync(0xffffffffu, ticket, 0) * P.chunk; };
+    const int64_t n_early = (dyn && P.early_ctas > 0) ? P.early_claims : 0;
+    int phase = (n_early > 0 && (int)blockIdx.x < P.early_ctas) ? 0 : 1;       // 0: draining the early queue
+    auto claim_issue = [&]() { if (lane == 0) ticket = atomicAdd(P.sched + (phase == 0 ? 2 : 0), 1); };
+    auto claim_take = [&]() -> int64_t {
+      const int64_t t = (int64_t)__shfl_sync(0xffffffffu, ticket, 0);
+      return phase == 0 ? t : n_early + t;
+    };
+    auto locate_claim = [&](int64_t c) {   // bundle of claim c (claims are bundle-major like units)
+      if (c < B.claim_begin || c >= B.claim_begin + ((unit_end - B.unit_begin) + B.chunk - 1) / B.chunk) {
+        int lo = 0, hi = P.nbundles - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if ((int64_t)__ldg(&P.bundles[mid].claim_begin) <= c) lo = mid; else hi = mid - 1;
+        }
+        b = lo;
+        B = P.bundles[b];
+        unit_end = B.unit_begin + (B.len + te - 1) / te;
+      }
+    };
     int64_t q = blockIdx.x, q_end = P.nunits;
+    int64_t c = 0;
+    auto open_claim = [&]() {              // unit range of claim c
+      locate_claim(c);
+      q = B.unit_begin + (c - B.claim_begin) * B.chunk;
+      q_end = q + B.chunk < unit_end ? q + B.chunk : unit_end;
+    };
+    bool have = true;
     if (dyn) {
       claim_issue();
-      q = claim_take();
-      q_end = q + P.chunk < P.nunits ? q + P.chunk : P.nunits;
-      claim_issue();
+      c = claim_take();
+      if (phase == 0 && c >= n_early) { phase = 1; claim_issue(); c = claim_take(); }
+      have = c < P.nclaims;
+      if (have) { open_claim(); claim_issue(); }
     }
-    while (true) {
+    while (have) {
       if (q >= q_end) {
         if (!dyn) break;
-        q = claim_take();
-        if (q >= P.nunits) break;
-        q_end = q + P.chunk < P.nunits ? q + P.chunk : P.nunits;
+        c = claim_take();
+        if (phase == 0 && c >= n_early) {      // early queue drained: join the main queue
+          phase = 1;
+          claim_issue();
+          c = claim_take();
+        }
+        if (c >= P.nclaims) break;
+        open_claim();
         claim_issue();
       }
-      if (q >= unit_end || q < B.unit_begin) {  // another bundle (units are enumerated bundle-major)
+      if (q >= unit_end || q < B.unit_begin) {  // another bundle (static mode: units are enumerated bundle-major)
         int lo = 0, hi = P.nbundles - 1;
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
@@ -264,6 +314,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         b = lo;
         B = P.bundles[b];
         unit_end = B.unit_begin + (B.len + te - 1) / te;
+      }
+      if ((B.gate >> 4) != cur_sig) {
+        // leaving a bundle whose units feed cross-rank signals: tell the consumers how many this CTA completed
+        // (BEFORE any flag wait below -- a neighbour may be waiting for exactly this signal)
+        if (cur_sig) flush_marker(F_FLUSH);
+        cur_sig = B.gate >> 4;
+        sig_units = 0;
       }
       if ((B.gate & 15) & ~waited) {
         // the unit reads (or overwrites) memory a neighbouring rank fills (or is still reading): wait for
@@ -329,20 +386,18 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
       xbase += (uint32_t)(U * B.nx);
       q += (int64_t)U * stride;
+      sig_units += U;
     }
     if (dyn && lane == 0) {   // the last CTA to run out of work re-arms the counters for the next launch
       __threadfence();
       if (atomicAdd(P.sched + 1, 1) == (int)gridDim.x - 1) {
         P.sched[0] = 0;
         P.sched[1] = 0;
+        P.sched[2] = 0;
         __threadfence();
       }
     }
-    if (lane == 0) {  // end-of-work sentinel
-      mbar_wait(sempty0 + 8 * slot, par ^ 1);
-      meta[slot].flags = F_END;
-      mbar_arrive(sfull0 + 8 * slot);
-    }
+    flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
   } else {
     // =============================== consumer warps ==============================
     T acc[VPT][V];
@@ -364,7 +419,35 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       mbar_wait(sfull0 + 8 * slot, par);
       const BMeta& M = meta[slot];
       const int flags = M.flags;
-      if (flags & F_END) break;
+      if (flags & (F_END | F_FLUSH)) {
+        const int smask = (flags >> BG_SIG_SHIFT) & 15;
+        const int cnt = M.nvalid;
+        if (smask && cnt > 0) {
+          // every consumer warp has issued its stores of those units (slots are consumed in order); one thread
+          // orders them system-wide and counts; the CTA that completes a signal raises the neighbour's flag word
+          // (data and flag may both live in peer memory: fence.sys orders them for the observer's acquire)
+          asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
+          if (tid == 0) {
+            __threadfence_system();
+            int m = smask;
+            while (m) {
+              const int k = __ffs(m) - 1;
+              m &= m - 1;
+              if (atomicAdd(P.sig_done + k, cnt) + cnt == P.sig_total[k]) {
+                P.sig_done[k] = 0;               // re-armed for the next launch of this plan
+                __threadfence_system();
+                if (P.gate.sig_addr[k] != nullptr) st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
+              }
+            }
+          }
+        }
+        if (flags & F_END) break;
+        __syncwarp();
+        if ((tid & 31) == 0) mbar_arrive(sempty0 + 8 * slot);
+        sl_p += slot_bytes;
+        if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
+        continue;
+      }
       const int nvalid = M.nvalid;
       const int nterms = M.nterms;
       const int xrelease = M.xrelease;
@@ -464,25 +547,6 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       }
-      if (flags & (0xF << BG_SIG_SHIFT)) {
-        // last row of a unit whose bundle feeds cross-rank signals: once every consumer warp has stored its
-        // part, count the unit; the CTA that completes a signal's last unit raises the neighbour's flag word
-        // (data and flag may both live in peer memory: fence.sys orders them for the observer's acquire).
-        asm volatile("bar.sync 1, %0;" ::"n"(kConsumers) : "memory");
-        if (tid == 0) {
-          __threadfence_system();
-          int m = (flags >> BG_SIG_SHIFT) & 15;
-          while (m) {
-            const int k = __ffs(m) - 1;
-            m &= m - 1;
-            if (atomicAdd(P.sig_done + k, 1) == P.sig_total[k] - 1) {
-              P.sig_done[k] = 0;               // re-armed for the next launch of this plan
-              __threadfence_system();
-              if (P.gate.sig_addr[k] != nullptr) st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
-            }
-          }
-        }
-      }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
@@ -502,7 +566,7 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
   }
   int64_t grid = ctx().sm_count;
   if (ctx().grid_limit > 0 && ctx().grid_limit < grid) grid = ctx().grid_limit;
-  const int64_t nclaims = P.sched ? (P.nunits + P.chunk - 1) / P.chunk : P.nunits;
+  const int64_t nclaims = P.sched ? P.nclaims : P.nunits;
   if (grid > nclaims) grid = nclaims > 0 ? nclaims : 1;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
@@ -554,7 +618,10 @@ void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out
   P.nbundles = f.nbundles; P.NX = f.NX; P.NS = f.NS; P.sstreams = f.sstreams; P.G = f.G;
   P.tile_elems = f.tile_elems; P.nunits = f.nunits;
   P.table_bytes = (int64_t)f.table_bytes;
-  P.sched = f.sched; P.chunk = f.chunk > 0 ? f.chunk : 1;
+  P.sched = f.sched;
+  P.nclaims = f.nclaims;
+  P.early_claims = f.early_claims;
+  P.early_ctas = f.early_claims > 0 ? ctx().dist_early_ctas : 0;
   P.in = in; P.out = out; P.hl = f.hl; P.hr = f.hr;
   if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
   else launch_dtype<double>(f, P, s);

@@ -646,7 +646,6 @@ struct Builder {
       }
       for (auto& lu : last_use) o.groups[lu.first].terms[lu.second].xflags |= XF_RELEASE;
       B.ngroups = (int32_t)o.groups.size() - B.group_begin;
-      if (B.gate >> 4) o.groups.back().flags |= (B.gate >> 4) << BG_SIG_SHIFT;   // the unit's last group reports completion
       B.nx = next_alloc;
       o.max_rows = std::max(o.max_rows, nrows);
       o.bundles.push_back(B);
@@ -803,17 +802,36 @@ struct Builder {
         if ((b.gate >> (4 + s)) & 1) f.sig_total[s] += (int32_t)u;
       if (b.gate) f.gated = true;
     }
-    // units per dynamic claim: what the producer can issue side by side for the shortest bundles
-    int chunk = 1;
-    for (const BundleRec& b : sim.bundles)
-      if (2 * b.ngroups <= f.G) {
-        int u = f.G / b.ngroups;
-        if (b.nx > 0) u = std::min(u, NX / b.nx);
-        chunk = std::max(chunk, u);
+    // Dynamic claims: sized per bundle for roughly equal work (a unit's work ~ its number of term groups): the
+    // heaviest bundle is claimed one unit at a time, light ones (a push row, a term-less row) many at a time so
+    // that the claim atomics stay off their critical path -- but never so coarse that a CTA gets fewer than ~8
+    // claims (a coarse claim on a heavy bundle is a long tail: measured 14% on the gated config-5 launch).
+    int max_groups = 1;
+    for (const BundleRec& b : sim.bundles) max_groups = std::max(max_groups, b.ngroups);
+    int64_t nclaims = 0;
+    for (int pass = 0; pass < 2; ++pass) {
+      nclaims = 0;
+      for (BundleRec& b : sim.bundles) {
+        const int64_t u = (b.len + te - 1) / te;
+        int64_t ch = std::max<int64_t>(1, std::min<int64_t>(32, max_groups / std::max(1, b.ngroups)));
+        if (pass == 1) ch = 1;
+        b.chunk = (int32_t)ch;
+        b.claim_begin = (int32_t)nclaims;
+        nclaims += (u + ch - 1) / ch;
       }
-    // ... but keep at least ~8 claims per CTA so that the last wave stays short
-    chunk = (int)std::max<int64_t>(1, std::min<int64_t>(chunk, unit / (8 * (int64_t)grid)));
-    f.chunk = chunk;
+      if (nclaims >= 8 * (int64_t)grid) break;    // otherwise fall back to one unit per claim
+    }
+    f.nclaims = nclaims;
+    const int chunk = 1;
+    f.chunk = 1;
+    {   // leading bundles whose rows store to peer memory
+      bool lead = true;
+      for (const BundleRec& b : sim.bundles) {
+        const bool peer = ((sim.groups[b.group_begin].flags >> BG_OUT_ALT_SHIFT) & 3) != 0;
+        lead = lead && peer;
+        if (lead) f.early_claims += ((b.len + te - 1) / te + b.chunk - 1) / b.chunk;
+      }
+    }
     const size_t gb = (sim.groups.size() * sizeof(BGroupRec) + 255) & ~(size_t)255;
     const size_t bb = (sim.bundles.size() * sizeof(BundleRec) + 255) & ~(size_t)255;
     std::vector<char> host(gb + bb + 256, 0);     // tables, then the (zeroed) scheduler counters
@@ -827,7 +845,7 @@ struct Builder {
     f.bgroups = reinterpret_cast<BGroupRec*>(blob);
     f.bundles = reinterpret_cast<BundleRec*>(blob + gb);
     f.table_bytes = gb + bb;
-    f.sched = (!ctx().static_sched && unit > (int64_t)chunk * grid) ? reinterpret_cast<int32_t*>(blob + gb + bb) : nullptr;
+    f.sched = (!ctx().static_sched && nclaims > (int64_t)grid) ? reinterpret_cast<int32_t*>(blob + gb + bb) : nullptr;
     f.sig_done = reinterpret_cast<int32_t*>(blob + gb + bb + 64);
     plan.engines |= 1 | 32;
     if (getenv("JETS_B200_PLAN_DEBUG")) {

@@ -66,3 +66,62 @@ def test_dense_dist_op_allgather_reduce_scatter():
     case = {"dtype": "float32", "nblk": 8, "halo": 1, "block_len": 8192, "iters": 1, "chunks": 2, "nccl": 1, "dense": 1, "seed": 5}
     res = run_ranks(2, case)
     assert all(r["fails"] == [] for r in res), res
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,n", [("float32", 40_000), ("float64", 1_000_004)])
+def test_loopback_block_circulant_single_process(dtype, n, monkeypatch):
+    """JETS_B200_DIST_LOOPBACK=1: the rank is its own previous and next neighbour, i.e. the operator is block-
+    CIRCULANT.  The whole gated path (push units, flag waits, flush markers, signals, double-buffered arena) runs
+    in ONE process on one GPU and must match the explicit circulant JopBlock: bit for bit on every block row /
+    column without a wrapped term; the first and last ones sum their wrapped term in halo order (first / last)
+    instead of column order, so they are held to the north_star tolerance."""
+    import numpy as np
+    import jets_b200 as B
+    B.init(0)
+    T = np.dtype(dtype)
+    nb = 6
+    g = np.random.default_rng(3)
+    W = {(r, c): B.to_device(g.random(n).astype(T)) for r in range(nb) for c in (r, (r + 1) % nb, (r - 1) % nb)}
+    sp = B.JetSpace(T, n)
+
+    def blk(r, c):
+        if c == r:
+            return B.JopDiagonal(W[(r, c)])
+        if c == (r + 1) % nb:
+            return B.JopStencil(T, n, "fdiff") @ B.JopDiagonal(W[(r, c)])
+        if c == (r - 1) % nb:
+            return 0.5 * B.JopStencil(T, n, "lap")
+        return B.JopZeroBlock(sp, sp)
+    A = B.blockop([[blk(r, c) for c in range(nb)] for r in range(nb)])
+    # rank-local rows over [block nb-1 | blocks 0..nb-1 | block 0]
+    cols = [nb - 1] + list(range(nb)) + [0]
+    rows = []
+    for r in range(nb):
+        row = []
+        for j, c in enumerate(cols):
+            wrap_lo = j == 0 and r == 0
+            wrap_hi = j == nb + 1 and r == nb - 1
+            inside = 1 <= j <= nb and (c == r or (abs(c - r) == 1))
+            row.append(blk(r, c) if (wrap_lo or wrap_hi or inside) else B.JopZeroBlock(sp, sp))
+        rows.append(row)
+    A_loc = B.blockop(rows)
+    monkeypatch.setenv("JETS_B200_DIST_LOOPBACK", "1")
+    op = B.dist.DistOp(B, A_loc, halo=1)
+    assert op.info(2) == 3
+    own = B.JetBSpace([sp] * nb)
+    tol = 1e-12 if T == np.float64 else 1e-5
+    for it in range(4):     # more than two epochs: both halves of the double-buffered arena, flags re-armed
+        x = B.rand(own, seed=100 + it)
+        y = B.rand(own, seed=200 + it)
+        d = op.forward(B.zeros(own), x).to_host()
+        m = op.adjoint(B.zeros(own), y).to_host()
+        d_ref = (A * x).to_host()
+        m_ref = (A.T * y).to_host()
+        inner = slice(n, (nb - 1) * n)      # rows / columns without a wrapped term: same order, same bits
+        assert np.linalg.norm(d.astype(np.float64) - d_ref) <= tol * np.linalg.norm(d_ref)
+        assert np.linalg.norm(m.astype(np.float64) - m_ref) <= tol * np.linalg.norm(m_ref)
+        assert np.array_equal(d[inner], d_ref[inner])
+        assert np.array_equal(m[inner], m_ref[inner])
+    assert op.gate_timeouts == 0 and op.info(4) == 1
+    op.close()
