@@ -263,6 +263,7 @@ def build_c5(B, rank, world, blk):
     op = D.DistOp(B, A, halo=1)
     x = B.zeros(own)
     B.check(B.lib.jets_buf_rand(x._h, SEED_M, C.c_uint64(r0 * blk), 0))
+    op.register(x)      # collective: forward applies on x read the neighbours' halo blocks in place (NVLink, no copy)
     return dict(A=A, op=op, x=x, d=B.zeros(own), m=B.zeros(own), W=W, rl=rl, part=part, own=own)
 
 

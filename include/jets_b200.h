@@ -323,6 +323,14 @@ int jets_dist_op_destroy(jets_dist_op A);
  * are added in rank order (previous rank first), which for halo == 1 is bit-identical to the single-GPU
  * apply.  Asynchronous on the context stream; every rank must issue the same sequence of applies.        */
 int jets_dist_apply(jets_dist_op A, int mode, jets_buf out, jets_buf in);
+/* Registers a domain shard with the operator (collective: every rank registers its corresponding vector, in
+ * the same order; library-owned vectors only).  The neighbours map the vector (CUDA IPC), and a FORWARD apply
+ * whose `in` is a registered vector reads the halo blocks straight from the neighbours' memory (TMA loads over
+ * NVLink inside the same single launch): no halo copy, the block rows that need a neighbour stay inside the
+ * main row sweep, and the launch ends with a handshake (the neighbours are done reading) so that whatever
+ * follows on the stream may overwrite `in`.  Unregistered vectors take the push path described above; the
+ * results are bit-identical either way.                                                                   */
+int jets_dist_op_register(jets_dist_op A, jets_buf x);
 /* Host-buffer pipeline: host_out = A' * (A * host_in) for this rank's shards (nloc own blocks each, pinned
  * host memory), cut into `nchunks` block-row chunks (<= 0: default) pipelined on three internal streams:
  * upload k | forward k-1, adjoint k-2 | download k-2.  Bit-identical to upload, jets_dist_apply x2,

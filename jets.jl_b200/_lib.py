@@ -144,6 +144,7 @@ SIGNATURES = {
     "jets_dist_op_create_dense": (_i, [_p, _pp]),
     "jets_dist_op_destroy": (_i, [_p]),
     "jets_dist_apply": (_i, [_p, _i, _p, _p]),
+    "jets_dist_op_register": (_i, [_p, _p]),
     "jets_dist_apply_normal_host": (_i, [_p, _p, _p, _i32]),
     "jets_dist_op_join": (_i, [_p]),
     "jets_dist_op_info": (_i32, [_p, _i32]),

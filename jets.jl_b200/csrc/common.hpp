@@ -425,6 +425,7 @@ struct BandedSel {
   bool send_prev = false, send_next = false;    // include the push rows (forward) / partial-sum rows (adjoint)
   bool has_prev = false, has_next = false;
   int owned = 0;                                // signals this launch must raise even if no unit feeds them
+  bool pull = false;                            // forward only: halo terms read the neighbours' vectors in place
 };
 std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel& sel);
 std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
@@ -463,6 +464,10 @@ struct GateLaunch {
   // in the buffer -- a missing neighbour must never hang the GPU; the host turns err != 0 into an error
   uint32_t* err = nullptr;
   uint64_t timeout_ns = 0;
+  // flag words that must have reached exit_val before the LAST CTA of the launch may exit (pull mode: the
+  // neighbours have finished reading this rank's input vector, so whatever follows on the stream may overwrite it)
+  int32_t exit_wait = 0;
+  uint32_t exit_val[kGateFlags] = {0, 0, 0, 0};
 };
 void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s,
                          const ApplyCoef* coef = nullptr, const GateLaunch* gate = nullptr);

@@ -26,6 +26,7 @@
 // (jets_dist_apply_normal_host): upload k | forward k-1, adjoint k-2 | download k-2 on three streams.
 #include <algorithm>
 #include <cstdlib>
+#include <map>
 #include <memory>
 #include <set>
 #include "dist.hpp"
@@ -76,7 +77,11 @@ struct jets_dist_op_s {
   bool loopback = false;             // single-process test mode: prev_base == next_base == arena
   uint32_t epoch[2] = {0, 0};        // forward / adjoint applies issued so far
   std::shared_ptr<Plan> mono[2];
+  std::shared_ptr<Plan> mono_pull;   // forward on a registered input vector: halo terms read the neighbours' memory
   std::unique_ptr<HostPipe> pipe;
+  // registered domain vectors (jets_dist_op_register): where the neighbours' copies are mapped
+  struct Reg { char* prev = nullptr; char* next = nullptr; void* prev_map = nullptr; void* next_map = nullptr; jets_buf keep = nullptr; };
+  std::map<const void*, Reg> regs;   // keyed by the local vector's first byte
   int64_t n_own = 0, n_rng = 0;      // elements of the own domain / range shards
   // dense structure
   jets_buf full = nullptr;           // the whole domain (all-gathered forward, partial sums adjoint)
@@ -100,7 +105,7 @@ uint64_t gate_timeout_ns() {   // JETS_B200_GATE_TIMEOUT_MS: how long a work uni
   return v;
 }
 
-GateLaunch gate_for(jets_dist_op D, int adj, uint32_t e) {
+GateLaunch gate_for(jets_dist_op D, int adj, uint32_t e, const jets_dist_op_s::Reg* pull = nullptr) {
   GateLaunch g;
   if (!D->has_prev && !D->has_next) return g;
   const int par = e & 1;
@@ -126,6 +131,14 @@ GateLaunch gate_for(jets_dist_op D, int adj, uint32_t e) {
     g.sig_addr[GS_NEXT_LO_READY] = nf + GF_LO_READY * kGateFlagStride;
     g.sig_addr[GS_NEXT_PREV_DONE] = nf + GF_PREV_DONE * kGateFlagStride;
     g.out_alt[1] = D->next_base + D->next_lay.buf[adj][0][par];      // the next rank's lo buffer
+  }
+  if (pull) {
+    // the halo terms read the neighbours' vectors in place; the launch may not end before the neighbours have
+    // finished reading this rank's vector
+    g.in_alt[0] = pull->prev;
+    g.in_alt[1] = pull->next;
+    g.exit_wait = (D->has_prev ? 1 << GF_PREV_DONE : 0) | (D->has_next ? 1 << GF_NEXT_DONE : 0);
+    g.exit_val[GF_PREV_DONE] = g.exit_val[GF_NEXT_DONE] = e;
   }
   return g;
 }
@@ -393,10 +406,23 @@ void dense_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
   }
 }
 
+void close_regs(jets_dist_op D) {
+  for (auto& kv : D->regs) {
+    if (!D->loopback) {
+      if (kv.second.prev_map) cudaIpcCloseMemHandle(kv.second.prev_map);
+      if (kv.second.next_map) cudaIpcCloseMemHandle(kv.second.next_map);
+    }
+    if (kv.second.keep) jets_buf_destroy(kv.second.keep);   // the registration held the vector alive (its address is the key)
+  }
+  D->regs.clear();
+}
+
 void destroy_op(jets_dist_op D) {
   if (D->pipe) D->pipe.reset();
   cudaStreamSynchronize(ctx().stream);
   D->mono[0].reset(); D->mono[1].reset();
+  D->mono_pull.reset();
+  close_regs(D);
   if (D->prev_base && !D->loopback) cudaIpcCloseMemHandle(D->prev_base);
   if (D->next_base && !D->loopback) cudaIpcCloseMemHandle(D->next_base);
   if (D->arena) cudaFree(D->arena);
@@ -413,6 +439,8 @@ void dist_ops_shutdown() {
   for (jets_dist_op D : live_ops()) {
     if (D->pipe) D->pipe.reset();
     if (D->loopback) continue;
+    D->mono_pull.reset();
+    close_regs(D);
     if (D->prev_base) { cudaIpcCloseMemHandle(D->prev_base); D->prev_base = nullptr; }
     if (D->next_base) { cudaIpcCloseMemHandle(D->next_base); D->next_base = nullptr; }
     D->has_prev = D->has_next = false;
@@ -562,7 +590,12 @@ int jets_dist_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
     JETS_CHECK(in->length() == nin, JETS_ERR_SHAPE, "input shard has %lld elements, the rank-local operator expects %lld", (long long)in->length(), (long long)nin);
     JETS_CHECK(out->length() == nout, JETS_ERR_SHAPE, "output shard has %lld elements, the rank-local operator produces %lld", (long long)out->length(), (long long)nout);
     JETS_CHECK(buf_ok(in) && buf_ok(out), JETS_ERR_UNSUPPORTED, "distributed banded apply: in/out must be library-owned (guarded, 16-byte aligned) vectors");
-    std::shared_ptr<Plan>& plan = D->mono[adj];
+    const jets_dist_op_s::Reg* reg = nullptr;
+    if (!adj && (D->has_prev || D->has_next)) {
+      auto it = D->regs.find(in->ptr());
+      if (it != D->regs.end()) reg = &it->second;
+    }
+    std::shared_ptr<Plan>& plan = reg ? D->mono_pull : D->mono[adj];
     const int pmode = adj ? JETS_MODE_DFT : (mode == JETS_MODE_F && !D->A->linear ? JETS_MODE_F : JETS_MODE_DF);
     if (!plan || !plan->valid()) {
       BandedSel s;
@@ -571,10 +604,55 @@ int jets_dist_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
       s.send_prev = s.send_next = true;
       s.has_prev = D->has_prev; s.has_next = D->has_next;
       s.owned = owned_signals(D);
+      s.pull = reg != nullptr;
       plan = build_banded_plan(D->A, D->halo, s);
     }
     const uint32_t e = ++D->epoch[adj];
-    launch_plan(D, *plan, in->ptr(), out->ptr(), gate_for(D, adj, e), ctx().stream);
+    launch_plan(D, *plan, in->ptr(), out->ptr(), gate_for(D, adj, e, reg), ctx().stream);
+  });
+}
+
+int jets_dist_op_register(jets_dist_op D, jets_buf x) {
+  return guard([&] {
+    require_ready();
+    JETS_CHECK(D && live_ops().count(D), JETS_ERR_INVALID, "null or destroyed distributed operator handle");
+    JETS_CHECK(x && x->refs > 0, JETS_ERR_INVALID, "null or destroyed buffer handle");
+    JETS_CHECK(D->kind == 0, JETS_ERR_UNSUPPORTED, "jets_dist_op_register applies to block-banded operators");
+    JETS_CHECK(x->dtype == D->dtype && x->length() == D->n_own, JETS_ERR_SHAPE, "the vector is not a domain shard of this operator");
+    JETS_CHECK(x->st && x->st->alloc && buf_ok(x), JETS_ERR_UNSUPPORTED, "only library-owned vectors can be registered");
+    if (D->regs.count(x->ptr())) return;
+    Dist& d = dist();
+    const size_t esz = dsize(D->dtype);
+    const int h = D->halo;
+    int64_t lo_elems = 0, first_elems = 0;
+    for (int k = 0; k < h; ++k) { lo_elems += D->lay.len_lo[k]; first_elems += D->lay.len_first[k]; }
+    jets_dist_op_s::Reg r;
+    if (D->loopback) {
+      // own previous / next neighbour: the last h blocks sit at the end of the shard, the first h at its start
+      r.prev = x->ptr() + (size_t)(D->n_own - lo_elems) * esz;
+      r.next = x->ptr();
+      x->refs++;
+      r.keep = x;
+      D->regs[x->ptr()] = r;
+      return;
+    }
+    if (!(d.ready && d.size > 1)) return;     // one rank: nothing to map
+    struct Rec { cudaIpcMemHandle_t handle; int64_t data_off, elems; } mine{}, zero{};
+    (void)zero;
+    CUDA_TRY(cudaIpcGetMemHandle(&mine.handle, x->st->alloc));
+    mine.data_off = x->ptr() - reinterpret_cast<char*>(x->st->alloc);
+    mine.elems = x->length();
+    std::vector<Rec> all(d.size);
+    dist_allgather_host(&mine, all.data(), sizeof(Rec));
+    auto open = [&](int rk, void** map) {
+      CUDA_TRY(cudaIpcOpenMemHandle(map, all[rk].handle, cudaIpcMemLazyEnablePeerAccess));
+      return reinterpret_cast<char*>(*map) + all[rk].data_off;
+    };
+    if (D->has_prev) r.prev = open(d.rank - 1, &r.prev_map) + (size_t)(all[d.rank - 1].elems - lo_elems) * esz;   // its last h blocks
+    if (D->has_next) r.next = open(d.rank + 1, &r.next_map);                                                     // its first h blocks
+    x->refs++;
+    r.keep = x;
+    D->regs[x->ptr()] = r;
   });
 }
 

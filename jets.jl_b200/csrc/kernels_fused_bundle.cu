@@ -398,6 +398,30 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
     }
     flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
+    if (P.gate.exit_wait && lane == 0) {
+      // the last CTA to run out of work keeps the grid alive until the neighbours have finished reading this
+      // rank's input (their flag words): everything that follows on the stream may then overwrite it
+      __threadfence();
+      if (atomicAdd(P.sig_done + kGateFlags, 1) == (int)gridDim.x - 1) {
+        P.sig_done[kGateFlags] = 0;
+        int m = P.gate.exit_wait;
+        while (m) {
+          const int k = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t* fp = P.gate.flags + k * kGateFlagStride;
+          uint64_t t0 = 0;
+          while ((int32_t)(ld_acquire_sys(fp) - P.gate.exit_val[k]) < 0) {
+            __nanosleep(200);
+            if (P.gate.timeout_ns) {
+              uint64_t now;
+              asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+              if (t0 == 0) t0 = now;
+              else if (now - t0 > P.gate.timeout_ns) { atomicAdd(P.gate.err, 1u); break; }
+            }
+          }
+        }
+      }
+    }
   } else {
     // =============================== consumer warps ==============================
     T acc[VPT][V];

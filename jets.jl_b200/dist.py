@@ -132,6 +132,12 @@ class DistOp:
         self.B.check(self.B.lib.jets_dist_apply(self._h, 2, m._h, d._h))
         return m
 
+    def register(self, x):
+        """Collective: lets the neighbours map this domain shard, so that forward applies on it read their halo
+        blocks in place over NVLink (no halo copy).  Returns x."""
+        self.B.check(self.B.lib.jets_dist_op_register(self._h, x._h))
+        return x
+
     def normal_host(self, h_out_ptr, h_in_ptr, nchunks=0):
         """host_out = A'(A host_in) on this rank's shards, chunk-pipelined (asynchronous; ``join`` to wait)."""
         self.B.check(self.B.lib.jets_dist_apply_normal_host(self._h, C.c_void_p(h_out_ptr), C.c_void_p(h_in_ptr), nchunks))

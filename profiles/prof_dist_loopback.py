@@ -58,11 +58,13 @@ def timed(fn):
 
 x, d, m = B.rand(own, seed=2), B.zeros(own), B.zeros(own)
 gb = 3 * nblk * blk * 4 / 1e9
-for mode in ("plain", "loopback"):
-    os.environ["JETS_B200_DIST_LOOPBACK"] = "1" if mode == "loopback" else "0"
-    op = B.dist.DistOp(B, local_rows(mode == "loopback"), halo=1)
+for mode in ("plain", "loopback", "loopback+registered"):
+    os.environ["JETS_B200_DIST_LOOPBACK"] = "0" if mode == "plain" else "1"
+    op = B.dist.DistOp(B, local_rows(mode != "plain"), halo=1)
+    if mode.endswith("registered"):
+        op.register(x)
     tf = timed(lambda: op.forward(d, x))
     tt = timed(lambda: op.adjoint(m, d))
-    print(f"{mode:9s} nblk={nblk} blk={blk}: forward {tf:.4f} ms ({gb / tf * 1e3:.0f} GB/s)  adjoint {tt:.4f} ms ({gb / tt * 1e3:.0f} GB/s)"
+    print(f"{mode:19s} nblk={nblk} blk={blk}: forward {tf:.4f} ms ({gb / tf * 1e3:.0f} GB/s)  adjoint {tt:.4f} ms ({gb / tt * 1e3:.0f} GB/s)"
           f"  neighbours={op.info(2)} timeouts={op.gate_timeouts}", flush=True)
     op.close()

@@ -111,8 +111,10 @@ def test_loopback_block_circulant_single_process(dtype, n, monkeypatch):
     assert op.info(2) == 3
     own = B.JetBSpace([sp] * nb)
     tol = 1e-12 if T == np.float64 else 1e-5
-    for it in range(4):     # more than two epochs: both halves of the double-buffered arena, flags re-armed
+    for it in range(6):     # more than two epochs: both halves of the double-buffered arena, flags re-armed
         x = B.rand(own, seed=100 + it)
+        if it >= 3:         # registered input: the pull path (halo terms read the "neighbour's" vector in place)
+            op.register(x)
         y = B.rand(own, seed=200 + it)
         d = op.forward(B.zeros(own), x).to_host()
         m = op.adjoint(B.zeros(own), y).to_host()

@@ -98,7 +98,15 @@ def main():
         d_ref = (A * xd).to_host()
         m_ref = (A.T * B.to_device(y, B.range_(A))).to_host()
         x_own = B.to_device(x[sl], own_dom)
+        if it % 2 == 1:          # every other iteration on a REGISTERED vector: the pull path (halo read in place)
+            op.register(x_own)
         d_own = op.forward(B.zeros(own_dom), x_own).to_host()
+        if it % 2 == 1 and it >= 3:    # ... and again on the same registered vector after overwriting it
+            x2 = g.random(off[-1]).astype(T) - 0.5
+            x_own.from_host(x2[sl])
+            d2 = op.forward(B.zeros(own_dom), x_own).to_host()
+            if not np.array_equal(d2, (A * B.to_device(x2, B.domain(A))).to_host()[sl]):
+                fails.append(f"iter {it}: forward on a re-used registered vector differs")
         y_own = B.to_device(y[sl], own_dom)
         m_own = op.adjoint(B.zeros(own_dom), y_own).to_host()
         if not np.array_equal(d_own, d_ref[sl]):
