@@ -90,6 +90,9 @@ int  jets_stream_join(int aux);
 int  jets_sync(void);
 /* Introspection used by tests and bench: total kernels launched by this library so far.       */
 int64_t jets_launch_count(void);
+/* Diagnostics (JETS_B200_TRACE=1 at jets_init): per-CTA timelines of the last 64 fused block-apply launches, 160 CTA
+ * records of 8 %globaltimer stamps each (see csrc/kernels_fused_bundle.cu); returns the launches traced so far.   */
+int64_t jets_debug_trace(uint64_t* host, int64_t capacity);
 int  jets_device_sm_count(void);
 
 /* ------------------------------------------------- device storage: JetSpace / JetBSpace ---- */

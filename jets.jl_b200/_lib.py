@@ -56,6 +56,7 @@ SIGNATURES = {
     "jets_stream_get": (_p, []),
     "jets_sync": (_i, []),
     "jets_launch_count": (_i64, []),
+    "jets_debug_trace": (_i64, [_p, _i64]),
     "jets_device_sm_count": (_i, []),
     "jets_buf_create": (_i, [_i, _i32, _pi64, _pp]),
     "jets_buf_wrap": (_i, [_i, _p, _i32, _pi64, _pp]),

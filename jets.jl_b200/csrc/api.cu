@@ -292,6 +292,15 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_STATIC_SCHED")) c.static_sched = atoi(v);
     if (const char* v = getenv("JETS_B200_GRID")) c.grid_limit = atoi(v);
     if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_PRE_STATE")) c.no_pre_state = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_FIRST_STATIC")) c.no_first_static = atoi(v);
+    if (const char* v = getenv("JETS_B200_TRACE")) {
+      if (atoi(v)) {
+        const size_t n = (size_t)Context::kTraceLaunches * Context::kTraceCtas * 8 * sizeof(unsigned long long);
+        CUDA_TRY(cudaMalloc(&c.trace_buf, n));
+        CUDA_TRY(cudaMemset(c.trace_buf, 0, n));
+      }
+    }
     c.ready = true;
   });
 }
@@ -359,6 +368,17 @@ int jets_sync(void) {
   return guard([&] { require_ready(); CUDA_TRY(cudaStreamSynchronize(ctx().stream)); });
 }
 int64_t jets_launch_count(void) { return ctx().launches; }
+int64_t jets_debug_trace(uint64_t* host, int64_t capacity) {
+  // JETS_B200_TRACE=1: copies the ring of per-CTA launch timelines (kTraceLaunches x kTraceCtas x 8 globaltimer
+  // stamps) to `host`; returns the number of bundle launches traced so far, -1 when tracing is off.
+  Context& c = ctx();
+  if (!c.trace_buf) return -1;
+  const int64_t n = (int64_t)Context::kTraceLaunches * Context::kTraceCtas * 8;
+  if (!host || capacity < n) return -1;
+  if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+  if (cudaMemcpy(host, c.trace_buf, (size_t)n * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+  return c.trace_count;
+}
 int jets_device_sm_count(void) { return ctx().sm_count; }
 int jets_set_fused_engine(int which) {
   return guard([&] {

@@ -72,6 +72,13 @@ struct Context {
   int bundle_ns = 0;
   int bundle_bmax = 0;
   int no_pdl = 0;
+  // JETS_B200_TRACE=1: every bundle launch writes a per-CTA timeline (globaltimer) into a ring of launch records
+  static constexpr int kTraceLaunches = 64, kTraceCtas = 160;
+  unsigned long long* trace_buf = nullptr;
+  int64_t trace_count = 0;
+  int no_first_static = 0;   // JETS_B200_NO_FIRST_STATIC=1: the first claim of a CTA goes through the atomic counter too (A/B)
+  int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)
+  uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last bundle launch (the only kernel that triggers its dependents early) writes
   int dist_early_ctas = 16;  // JETS_B200_DIST_EARLY_CTAS: CTAs that take the peer-store units of a distributed apply (0: all)
   int grid_limit = 0;    // JETS_B200_GRID=n: launch the fused kernels with at most n CTAs (leaves SMs to concurrent kernels)
   int static_sched = 0;  // JETS_B200_STATIC_SCHED=1: deal units round-robin instead of claiming them dynamically        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
@@ -340,6 +347,10 @@ struct DevFused {   // device copy + launch geometry
   void* blob = nullptr;
   // cross-rank gating (distributed banded apply, dist.cu): units per signal, the signals this launch must
   // raise even when no unit feeds them, and the completion counters (in the plan blob)
+  // byte range the launch writes relative to the apply's `out`, and the absolute range of its operator-state
+  // streams: a launch may fetch state before griddepcontrol.wait unless the previous launch wrote into that range
+  int64_t out_lo = 0, out_hi = 0;
+  uintptr_t state_lo = 0, state_hi = 0;
   int64_t nclaims = 0;        // dynamic claims (bundle-major)
   int64_t early_claims = 0;   // leading claims whose units store to peer memory (taken by a few CTAs only)
   int32_t sig_total[kGateFlags] = {0, 0, 0, 0};

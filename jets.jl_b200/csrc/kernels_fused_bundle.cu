@@ -61,6 +61,9 @@ struct BundleParams {
   // units meanwhile instead of all queueing behind the link
   int32_t early_ctas;
   int64_t early_claims;
+  unsigned long long* trace;  // JETS_B200_TRACE: 8 globaltimer stamps per CTA of the launch (null: off)
+  int32_t no_first_static;    // A/B: every claim through the atomic counter
+  int32_t pre_state;          // operator state may be fetched before griddepcontrol.wait (no kernel of the stream writes it)
   const char* in;
   char* out;
   int32_t hl, hr;
@@ -104,6 +107,15 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Timeline of one CTA (profiles/trace_launch.py): 0 entry, 1 barriers initialised, 2 producer past
+// griddepcontrol.wait, 3 first tile landed (consumer), 4 first row tile stored, 5 producer issued its last group,
+// 6 consumer saw the end sentinel (all stores issued), 7 state bytes put in flight before the wait.
+#define JETS_TRACE(slot, val) do { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } while (0)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                    "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   const uint32_t sring0 = xring0 + (uint32_t)NX * kBufBytes;
   const uint32_t slot_bytes = (uint32_t)P.sstreams * kBufBytes;
   const int tid = threadIdx.x;
+  if (tid == 0) JETS_TRACE(0, gtime());
   if (tid < kMaxRing) {            // 16 threads initialise the three barrier arrays side by side
     mbar_init(sfull0 + 8 * tid, 1);
     mbar_init(sempty0 + 8 * tid, CW);
@@ -141,8 +154,9 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     if (o < P.table_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.groups) + o));
   }
   BundleRec B = P.bundles[0];
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-  __syncthreads();
+  __syncthreads();                 // barriers initialised; nothing a previous kernel may write has been touched yet
+  if (tid == 0) JETS_TRACE(1, gtime());
+  if (tid < kConsumers) asm volatile("griddepcontrol.wait;" ::: "memory");
   if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
     // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
 #pragma unroll
@@ -178,7 +192,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
 
     // One lane issues one term group of unit `q` into state slot `my`.
-    auto issue = [&](const BGroupRec* rec, int64_t q, uint32_t xb, int my, uint32_t mypar) {
+    // stage 0: the whole group.  stage 1 (before griddepcontrol.wait): only the operator-STATE streams, which no
+    // kernel of this stream writes (the host checked) -- their bytes are announced with a plain expect_tx, the
+    // barrier's one arrival stays pending.  stage 2: the rest of a group whose state is already in flight.
+    auto issue = [&](const BGroupRec* rec, int64_t q, uint32_t xb, int my, uint32_t mypar, int stage) {
       const int4 hd = __ldg(reinterpret_cast<const int4*>(&rec->nsstreams));  // nsstreams nterms xrel_mask flags
       const uint4 t01 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[0]));
       const uint4 t23 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[2]));
@@ -195,8 +212,19 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       // ring position of the unit's first allocation (one division per group, none per term)
       const uint32_t xb_use = xb / (uint32_t)NX;
       const uint32_t xb_mod = xb - xb_use * (uint32_t)NX;
-      mbar_wait(sempty0 + 8 * my, mypar ^ 1);
-      uint32_t total = bytes * (uint32_t)nss;
+      if (stage != 2) mbar_wait(sempty0 + 8 * my, mypar ^ 1);
+      if (stage == 1) {
+        if (nss > 0) {
+          asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(sfull0 + 8 * my), "r"(bytes * (uint32_t)nss) : "memory");
+          const uint32_t sb = sring0 + my * slot_bytes + (kPad - lpad);
+          for (int k = 0; k < nss; ++k) {
+            const char* src = reinterpret_cast<const char*>(__ldg(&rec->sptr[k]));
+            bulk_g2s(sb + k * kBufBytes, src + goff, bytes, sfull0 + 8 * my);
+          }
+        }
+        return;
+      }
+      uint32_t total = stage == 2 ? 0u : bytes * (uint32_t)nss;
       int xrelease = 0;
 #pragma unroll
       for (int t = 0; t < kGroupTerms; ++t) {
@@ -239,6 +267,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           bulk_g2s(xring0 + tt[t].xrel * kBufBytes + (kPad - lpad), src + goff, bytes, sfull0 + 8 * my);
         }
       }
+      if (stage == 2) return;
       const uint32_t sb = sring0 + my * slot_bytes + (kPad - lpad);
       for (int k = 0; k < nss; ++k) {
         const char* src = reinterpret_cast<const char*>(__ldg(&rec->sptr[k]));
@@ -259,11 +288,12 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     // roughly equal work, many light units or one heavy one); a claim never spans two bundles.
     int ticket = 0;
     const int64_t n_early = (dyn && P.early_ctas > 0) ? P.early_claims : 0;
+    const int64_t ticket_base_v = (dyn && n_early == 0 && !P.no_first_static) ? (int64_t)gridDim.x : 0;
     int phase = (n_early > 0 && (int)blockIdx.x < P.early_ctas) ? 0 : 1;       // 0: draining the early queue
     auto claim_issue = [&]() { if (lane == 0) ticket = atomicAdd(P.sched + (phase == 0 ? 2 : 0), 1); };
     auto claim_take = [&]() -> int64_t {
       const int64_t t = (int64_t)__shfl_sync(0xffffffffu, ticket, 0);
-      return phase == 0 ? t : n_early + t;
+      return phase == 0 ? t : n_early + t + ticket_base_v;
     };
     auto locate_claim = [&](int64_t c) {   // bundle of claim c (claims are bundle-major like units)
       if (c < B.claim_begin || c >= B.claim_begin + ((unit_end - B.unit_begin) + B.chunk - 1) / B.chunk) {
@@ -284,8 +314,37 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       q = B.unit_begin + (c - B.claim_begin) * B.chunk;
       q_end = q + B.chunk < unit_end ? q + B.chunk : unit_end;
     };
+    auto locate_unit = [&]() {             // static mode: bundle of unit q (units are enumerated bundle-major)
+      if (q >= unit_end || q < B.unit_begin) {
+        int lo = 0, hi = P.nbundles - 1;
+        while (lo < hi) {
+          const int mid = (lo + hi + 1) >> 1;
+          if (__ldg(&P.bundles[mid].unit_begin) <= q) lo = mid; else hi = mid - 1;
+        }
+        b = lo;
+        B = P.bundles[b];
+        unit_end = B.unit_begin + (B.len + te - 1) / te;
+      }
+    };
+    // Without an early queue the FIRST claim of a CTA is static (claim blockIdx.x: the grid never exceeds the
+    // number of claims), tickets count from gridDim.x: no atomic sits between the launch and the first load.
+    const bool first_static = dyn && n_early == 0 && !P.no_first_static;
     bool have = true;
-    if (dyn) {
+    int pre_groups = 0;                    // groups of the first unit whose state loads are already in flight
+    if (first_static) { c = blockIdx.x; open_claim(); }
+    else if (!dyn) locate_unit();
+    if (P.pre_state && (first_static || !dyn) && q < q_end && B.gate == 0 && 2 * B.ngroups > G) {
+      // the previous kernel of the stream is still draining: put the operator state of this CTA's first unit in
+      // flight now (plan tables and operator state are immutable for it); everything else waits below
+      pre_groups = B.ngroups < G ? B.ngroups : G;
+      if (lane < pre_groups) issue(P.groups + B.group_begin + lane, q, 0u, lane < NS ? lane : lane - NS, 0u, 1);
+      __syncwarp();
+      if (lane == 0) JETS_TRACE(7, (unsigned long long)pre_groups);
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    if (lane == 0) JETS_TRACE(2, gtime());
+    if (first_static) claim_issue();
+    else if (dyn) {
       claim_issue();
       c = claim_take();
       if (phase == 0 && c >= n_early) { phase = 1; claim_issue(); c = claim_take(); }
@@ -305,16 +364,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         open_claim();
         claim_issue();
       }
-      if (q >= unit_end || q < B.unit_begin) {  // another bundle (static mode: units are enumerated bundle-major)
-        int lo = 0, hi = P.nbundles - 1;
-        while (lo < hi) {
-          const int mid = (lo + hi + 1) >> 1;
-          if (__ldg(&P.bundles[mid].unit_begin) <= q) lo = mid; else hi = mid - 1;
-        }
-        b = lo;
-        B = P.bundles[b];
-        unit_end = B.unit_begin + (B.len + te - 1) / te;
-      }
+      locate_unit();
       if ((B.gate >> 4) != cur_sig) {
         // leaving a bundle whose units feed cross-rank signals: tell the consumers how many this CTA completed
         // (BEFORE any flag wait below -- a neighbour may be waiting for exactly this signal)
@@ -365,7 +415,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           int my = slot + lane;
           uint32_t mypar = par;
           if (my >= NS) { my -= NS; mypar ^= 1; }
-          issue(P.groups + B.group_begin + g, q + (int64_t)u * stride, xbase + (uint32_t)(u * B.nx), my, mypar);
+          issue(P.groups + B.group_begin + g, q + (int64_t)u * stride, xbase + (uint32_t)(u * B.nx), my, mypar, 0);
         }
         slot += n;
         if (slot >= NS) { slot -= NS; par ^= 1; }
@@ -377,11 +427,12 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
             int my = slot + lane;
             uint32_t mypar = par;
             if (my >= NS) { my -= NS; mypar ^= 1; }
-            issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar);
+            issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar, (g0 == 0 && lane < pre_groups) ? 2 : 0);
           }
           slot += n;
           if (slot >= NS) { slot -= NS; par ^= 1; }
           __syncwarp();
+          pre_groups = 0;                 // only the very first batch of the CTA was issued ahead
         }
       }
       xbase += (uint32_t)(U * B.nx);
@@ -397,6 +448,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         __threadfence();
       }
     }
+    if (lane == 0) JETS_TRACE(5, gtime());
     flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
     if (P.gate.exit_wait && lane == 0) {
       // the last CTA to run out of work keeps the grid alive until the neighbours have finished reading this
@@ -439,8 +491,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
     const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
+    bool tr_first = P.trace != nullptr && tid == 0, tr_store = tr_first;
     while (true) {
       mbar_wait(sfull0 + 8 * slot, par);
+      if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; }
       const BMeta& M = meta[slot];
       const int flags = M.flags;
       if (flags & (F_END | F_FLUSH)) {
@@ -465,7 +519,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
             }
           }
         }
-        if (flags & F_END) break;
+        if (flags & F_END) {
+          if (tid == 0) JETS_TRACE(6, gtime());
+          break;
+        }
         __syncwarp();
         if ((tid & 31) == 0) mbar_arrive(sempty0 + 8 * slot);
         sl_p += slot_bytes;
@@ -571,6 +628,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       }
+      if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
@@ -647,6 +705,23 @@ void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out
   P.early_claims = f.early_claims;
   P.early_ctas = f.early_claims > 0 ? ctx().dist_early_ctas : 0;
   P.in = in; P.out = out; P.hl = f.hl; P.hr = f.hr;
+  {
+    // Operator state may be put in flight before griddepcontrol.wait unless the previous bundle launch -- the only
+    // kernel that lets its dependents start early -- writes into it (e.g. a diagonal operator built on the vector
+    // the previous apply produced).  Gated launches write through peer pointers: unknown, so never early after one.
+    Context& c = ctx();
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(out) + (uintptr_t)f.out_lo, hi = reinterpret_cast<uintptr_t>(out) + (uintptr_t)f.out_hi;
+    P.no_first_static = c.no_first_static;
+    P.trace = nullptr;
+    if (c.trace_buf) {          // ring of per-launch records: [launch index % kTraceLaunches][CTA][8]
+      P.trace = c.trace_buf + (size_t)(c.trace_count % Context::kTraceLaunches) * Context::kTraceCtas * 8;
+      ++c.trace_count;
+    }
+    P.pre_state = (!c.no_pdl && !c.no_pre_state && !gate && f.state_hi != 0 &&
+                   !(f.state_lo < c.pdl_out_hi && c.pdl_out_lo < f.state_hi)) ? 1 : 0;
+    if (gate) { c.pdl_out_lo = 0; c.pdl_out_hi = ~(uintptr_t)0; }
+    else { c.pdl_out_lo = lo; c.pdl_out_hi = hi; }
+  }
   if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
   else launch_dtype<double>(f, P, s);
 }

@@ -735,6 +735,22 @@ struct Builder {
       plan.engines |= 1;
       return true;
     }
+    {   // what the launch writes (relative to `out`) and where its operator state lives
+      bool first_o = true;
+      for (const PRow& r : rows) {
+        if (r.out_alt == 0) {
+          const int64_t lo = r.out_off * (int64_t)esz, hi = (r.out_off + r.len) * (int64_t)esz;
+          if (first_o) { f.out_lo = lo; f.out_hi = hi; first_o = false; }
+          else { f.out_lo = std::min(f.out_lo, lo); f.out_hi = std::max(f.out_hi, hi); }
+        }
+        for (const PTerm& t : r.terms)
+          for (int64_t p : t.sptr) {
+            const uintptr_t lo = (uintptr_t)p, hi = lo + (uintptr_t)r.len * esz;
+            if (!f.state_hi) { f.state_lo = lo; f.state_hi = hi; }
+            else { f.state_lo = std::min(f.state_lo, lo); f.state_hi = std::max(f.state_hi, hi); }
+          }
+      }
+    }
     // reuse distance with an unbounded ring -> how many buffers sharing needs
     BundleSim sim;
     simulate_bundles(rows, kMaxRing, 1 << 30, accflag, sim);
@@ -814,17 +830,26 @@ struct Builder {
     int max_groups = 1;
     for (const BundleRec& b : sim.bundles) max_groups = std::max(max_groups, b.ngroups);
     int64_t nclaims = 0;
-    for (int pass = 0; pass < 2; ++pass) {
+    for (int shrink = 0; ; ++shrink) {
       nclaims = 0;
+      bool any = false;
       for (BundleRec& b : sim.bundles) {
         const int64_t u = (b.len + te - 1) / te;
-        int64_t ch = std::max<int64_t>(1, std::min<int64_t>(32, max_groups / std::max(1, b.ngroups)));
-        if (pass == 1) ch = 1;
+        // equal work per claim ...
+        int64_t ch = std::max<int64_t>(1, max_groups / std::max(1, b.ngroups));
+        // ... and at least what the producer issues side by side for a short bundle (several units per batch)
+        if (2 * b.ngroups <= f.G) {
+          int64_t side = f.G / b.ngroups;
+          if (b.nx > 0) side = std::min<int64_t>(side, NX / b.nx);
+          ch = std::max(ch, side);
+        }
+        ch = std::max<int64_t>(1, std::min<int64_t>(32, ch) >> shrink);
+        any = any || ch > 1;
         b.chunk = (int32_t)ch;
         b.claim_begin = (int32_t)nclaims;
         nclaims += (u + ch - 1) / ch;
       }
-      if (nclaims >= 8 * (int64_t)grid) break;    // otherwise fall back to one unit per claim
+      if (nclaims >= 8 * (int64_t)grid || !any) break;    // keep at least ~8 claims per CTA: halve the claims and retry
     }
     f.nclaims = nclaims;
     const int chunk = 1;
