@@ -388,6 +388,8 @@ struct Step {
   int32_t* d_row_ptr = nullptr;  // output-row grouping for GEMV
   int32_t n_out_rows = 0;
   int64_t gemv_tiles = 0;
+  int32_t gemv_ksplit = 1;         // N orientation with few row tiles: CTAs per tile (kernels_dense.cu)
+  double* gemv_partials = nullptr; // [ksplit][tiles][rows per tile] f64 (owned by the plan)
   int acc = ACC_SET;
   int64_t fill_len = 0;
   // ST_GATHER: dst[i] (acc)= src[idx[i]] (g_scatter=0) or dst[idx[i]] (acc)= src[i] (g_scatter=1), i < g_n

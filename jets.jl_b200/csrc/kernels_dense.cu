@@ -27,6 +27,12 @@ struct GemvParams {
   int32_t acc;              // ACC_SET / ACC_ADD / ACC_SUB
   const char* in;
   char* out;
+  // N orientation with few row tiles (a block-ROW shard of a wide operator: 4 x 32 blocks give 64 CTAs for 148 SMs):
+  // `ksplit` CTAs share a row tile, each summing a contiguous part of the group's blocks into f64 partials
+  // [part][tile][TM]; gemv_n_finish_kernel adds the parts in order (deterministic) and stores.
+  int32_t ksplit;
+  double* partials;
+  int32_t ntiles;
 };
 
 __device__ __forceinline__ int find_group(const int32_t* tile_ptr, int ngroups, int tile) {
@@ -54,10 +60,17 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const GemvParams P) {
   constexpr int TM = 32 * V;
   constexpr int CU = 8;  // columns in flight per lane
   __shared__ double red[kWarps][TM];
-  const int g = find_group(P.tile_ptr, P.ngroups, blockIdx.x);
-  const int tile = blockIdx.x - P.tile_ptr[g];
+  const int gtile = P.ksplit > 1 ? (int)(blockIdx.x / P.ksplit) : (int)blockIdx.x;
+  const int part_k = P.ksplit > 1 ? (int)(blockIdx.x % P.ksplit) : 0;
+  const int g = find_group(P.tile_ptr, P.ngroups, gtile);
+  const int tile = gtile - P.tile_ptr[g];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int e_begin = P.row_ptr[g], e_end = P.row_ptr[g + 1];
+  int e_begin = P.row_ptr[g], e_end = P.row_ptr[g + 1];
+  if (P.ksplit > 1) {        // this CTA's contiguous share of the group's blocks
+    const int ne = e_end - e_begin;
+    const int a = e_begin + (int)((int64_t)ne * part_k / P.ksplit), b2 = e_begin + (int)((int64_t)ne * (part_k + 1) / P.ksplit);
+    e_begin = a; e_end = b2;
+  }
   const int64_t i0 = (int64_t)tile * TM + lane * V;  // first row owned by this lane
   double acc[V];
 #pragma unroll
@@ -131,9 +144,27 @@ __global__ void __launch_bounds__(kThreads) gemv_n_kernel(const GemvParams P) {
     double s = 0.0;
 #pragma unroll
     for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+    if (P.ksplit > 1) {
+      P.partials[((size_t)part_k * P.ntiles + gtile) * TM + threadIdx.x] = s;
+      return;
+    }
     const int64_t i = (int64_t)tile * TM + threadIdx.x;
     if (i < out_len) finish_store(reinterpret_cast<T*>(P.out) + out_off + i, s, P.acc);
   }
+}
+
+// Second pass of the split N orientation: parts added in order, one thread per output row.
+template <typename T>
+__global__ void __launch_bounds__(32 * VecOf<T>::V) gemv_n_finish_kernel(const GemvParams P) {
+  constexpr int TM = 32 * VecOf<T>::V;
+  const int gtile = blockIdx.x;
+  const int g = find_group(P.tile_ptr, P.ngroups, gtile);
+  const int tile = gtile - P.tile_ptr[g];
+  const DBlock b = P.blocks[P.row_ptr[g]];
+  double s = 0.0;
+  for (int k = 0; k < P.ksplit; ++k) s += P.partials[((size_t)k * P.ntiles + gtile) * TM + threadIdx.x];
+  const int64_t i = (int64_t)tile * TM + threadIdx.x;
+  if (i < b.rows) finish_store(reinterpret_cast<T*>(P.out) + b.out_off + i, s, P.acc);
 }
 
 // ---------------------------------------------------------------- T: out = A' * in --------
@@ -234,7 +265,10 @@ void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStrea
   P.in = in;
   P.out = out;
   const bool trans = st.dblocks[0].trans != 0;
-  const unsigned grid = (unsigned)st.gemv_tiles;
+  P.ksplit = (!trans && st.gemv_ksplit > 1 && st.gemv_partials) ? st.gemv_ksplit : 1;
+  P.partials = st.gemv_partials;
+  P.ntiles = (int32_t)st.gemv_tiles;
+  const unsigned grid = (unsigned)(st.gemv_tiles * P.ksplit);
   if (dtype == JETS_F32) {
     if (trans) gemv_t_kernel<float><<<grid, kThreads, 0, s>>>(P);
     else gemv_n_kernel<float><<<grid, kThreads, 0, s>>>(P);
@@ -244,6 +278,12 @@ void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStrea
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();
+  if (P.ksplit > 1) {
+    if (dtype == JETS_F32) gemv_n_finish_kernel<float><<<(unsigned)st.gemv_tiles, 128, 0, s>>>(P);
+    else gemv_n_finish_kernel<double><<<(unsigned)st.gemv_tiles, 64, 0, s>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+  }
 }
 
 }  // namespace jets

@@ -1085,6 +1085,21 @@ struct Builder {
     plan.blobs.push_back(blob);
     st.d_dblocks = reinterpret_cast<DBlock*>(blob);
     st.d_row_ptr = reinterpret_cast<int32_t*>(blob + nb_al);
+    if (!trans && st.gemv_tiles > 0 && st.gemv_tiles < 2 * (int64_t)ctx().sm_count) {
+      // a block-row shard of a wide operator has few row tiles: split every tile's blocks over several CTAs
+      int min_entries = 1 << 30;
+      for (size_t g = 0; g + 1 < row_ptr.size(); ++g) min_entries = std::min(min_entries, row_ptr[g + 1] - row_ptr[g]);
+      const int64_t want = (4 * (int64_t)ctx().sm_count + st.gemv_tiles - 1) / st.gemv_tiles;
+      const int ks = (int)std::max<int64_t>(1, std::min<int64_t>(want, min_entries));
+      if (ks > 1) {
+        const int tm = 32 * (dtype == JETS_F32 ? 4 : 2);
+        double* part = nullptr;
+        CUDA_TRY(cudaMalloc(&part, (size_t)ks * st.gemv_tiles * tm * sizeof(double)));
+        plan.blobs.push_back(part);
+        st.gemv_ksplit = ks;
+        st.gemv_partials = part;
+      }
+    }
     plan.engines |= 4;
     plan.steps.push_back(std::move(st));
   }
