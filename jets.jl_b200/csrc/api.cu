@@ -121,7 +121,8 @@ static bool needs_point(jets_op a) {
   return false;
 }
 
-static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate, const ApplyCoef* coef = nullptr) {
+static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate, const ApplyCoef* coef = nullptr,
+                       double* norm_out = nullptr) {
   require_ready();
   check_op(a); check_buf(out); check_buf(in);
   JETS_CHECK(mode >= 0 && mode <= 2, JETS_ERR_INVALID, "bad mode %d", mode);
@@ -149,7 +150,12 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
   if (coef) {
     check_real(a->dtype, "jets_apply_axpby");
     // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...
-    if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef)) return;
+    if (norm_out && ctx().no_fused_norm) {      // A/B: the norm as a pass of its own
+      if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef, nullptr)) {
+        vec_reduce(a->dtype, 1, out->ptr(), nullptr, out->length(), 2.0, norm_out, ctx().stream);
+        return;
+      }
+    } else if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef, norm_out)) return;
     // ... else through a temporary owned by the operator (dense / staged plans)
     const size_t bytes = (size_t)out->length() * dsize(a->dtype);
     if (!a->axpby_tmp || a->axpby_tmp_bytes < bytes) {
@@ -162,6 +168,7 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
     run_plan(*plan, a->dtype, in->ptr(), tmp);
     vec_axpby_dev(a->dtype, out->ptr(), out->length(), coef->a_ptr, coef->a_const, coef->a_flags, tmp, coef->o_ptr,
                   coef->o_const, coef->o_flags, out->ptr(), ctx().stream);
+    if (norm_out) vec_reduce(a->dtype, 1, out->ptr(), nullptr, out->length(), 2.0, norm_out, ctx().stream);   // a pass of its own
     return;
   }
   run_plan(*plan, a->dtype, in->ptr(), out->ptr());
@@ -293,6 +300,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_GRID")) c.grid_limit = atoi(v);
     if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_PRE_STATE")) c.no_pre_state = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_FUSED_NORM")) c.no_fused_norm = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_FIRST_STATIC")) c.no_first_static = atoi(v);
     if (const char* v = getenv("JETS_B200_TRACE")) {
       if (atoi(v)) {
@@ -1074,6 +1082,16 @@ int jets_apply_axpby(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar
     c.a_ptr = sa ? sa->dev : nullptr; c.a_const = ca; c.a_flags = a_flags;
     c.o_ptr = so ? so->dev : nullptr; c.o_const = co; c.o_flags = o_flags;
     apply_impl(a, mode, out, in, 0, &c);
+  });
+}
+int jets_apply_axpby_norm(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar sa, double ca, int a_flags,
+                          jets_scalar so, double co, int o_flags, jets_scalar norm2_out) {
+  return guard([&] {
+    JETS_CHECK(norm2_out, JETS_ERR_INVALID, "null scalar");
+    ApplyCoef c;
+    c.a_ptr = sa ? sa->dev : nullptr; c.a_const = ca; c.a_flags = a_flags;
+    c.o_ptr = so ? so->dev : nullptr; c.o_const = co; c.o_flags = o_flags;
+    apply_impl(a, mode, out, in, 0, &c, norm2_out->dev);
   });
 }
 int jets_scalar_prog(int32_t n, const jets_scalar* out, const char* op, const jets_scalar* a, const jets_scalar* b) {

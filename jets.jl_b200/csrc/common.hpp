@@ -77,6 +77,7 @@ struct Context {
   unsigned long long* trace_buf = nullptr;
   int64_t trace_count = 0;
   int no_first_static = 0;   // JETS_B200_NO_FIRST_STATIC=1: the first claim of a CTA goes through the atomic counter too (A/B)
+  int no_fused_norm = 0;     // JETS_B200_NO_FUSED_NORM=1: jets_apply_axpby_norm runs the norm as a separate pass (A/B)
   int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)
   uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last bundle launch (the only kernel that triggers its dependents early) writes
   int dist_early_ctas = 16;  // JETS_B200_DIST_EARLY_CTAS: CTAs that take the peer-store units of a distributed apply (0: all)
@@ -285,12 +286,12 @@ struct BGroupRec {   // 320 bytes
   BTerm terms[kGroupTerms];    // 16B aligned
   CStage stages[kGroupStages]; // 16B aligned
   int64_t out_off;             // element offset of the output row relative to the apply's `out`
-  int64_t pad;
+  int32_t row_in_bundle, pad;  // which row of its bundle the group belongs to (norm partial index)
 };
 static_assert(offsetof(BGroupRec, nsstreams) % 16 == 0 && offsetof(BGroupRec, terms) % 16 == 0 &&
               offsetof(BGroupRec, stages) % 16 == 0, "BGroupRec alignment");
 static_assert(sizeof(BGroupRec) == 320, "BGroupRec layout");
-struct BundleRec {   // 40 bytes: consecutive output rows of equal length walked by one CTA per tile position
+struct BundleRec {   // 56 bytes: consecutive output rows of equal length walked by one CTA per tile position
   int64_t unit_begin;          // first (bundle, position) unit of this bundle in the launch-wide enumeration
   int64_t len;                 // row length (elements)
   int32_t group_begin, ngroups;
@@ -298,6 +299,8 @@ struct BundleRec {   // 40 bytes: consecutive output rows of equal length walked
   int32_t gate;                // bits 0-3: flag words the producer waits for before the unit's first load;
                                // bits 4-7: signals a finished unit of this bundle counts towards
   int32_t claim_begin, chunk;  // dynamic scheduling: first claim of this bundle, units per claim
+  int64_t pbase;               // first (unit, row) tile of this bundle in the launch-wide enumeration (norm partials)
+  int32_t nrows, pad;
 };
 
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active
@@ -353,6 +356,9 @@ struct DevFused {   // device copy + launch geometry
   uintptr_t state_lo = 0, state_hi = 0;
   int64_t nclaims = 0;        // dynamic claims (bundle-major)
   int64_t early_claims = 0;   // leading claims whose units store to peer memory (taken by a few CTAs only)
+  int64_t nrowtiles = 0;      // (unit, row) tiles of the launch: the store epilogue can leave one sum-of-squares partial
+                              // per tile and consumer warp for a fixed-order norm (jets_apply_axpby_norm)
+  int consumer_warps = 16;
   int32_t sig_total[kGateFlags] = {0, 0, 0, 0};
   int32_t sig_owned = 0;
   int32_t* sig_done = nullptr;
@@ -412,6 +418,7 @@ struct Plan {
   std::vector<void*> tmps;       // device temporaries (owned)
   std::vector<size_t> tmp_bytes;
   std::vector<void*> blobs;      // device table blobs (owned)
+  double* nrm_partials = nullptr;  // norm partials of jets_apply_axpby_norm (in blobs once allocated)
   int engines = 0;
   // Validity: a plan holds raw pointers to the linearization points (mo) of the pointwise leaves it evaluated.
   // It stays valid while every one of those leaves still points at the same buffer (`points`); trees with more
@@ -444,7 +451,7 @@ std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel
 std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
 void run_plan(Plan& p, int dtype, char* in, char* out);
 struct ApplyCoef;
-bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef);  // false: plan is not one bundle launch
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef, double* norm_out = nullptr);  // false: plan is not one bundle launch
 
 // kernels_fused.cu
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
@@ -461,6 +468,7 @@ int bundle_smem_budget();
 struct ApplyCoef {
   const double* a_ptr = nullptr; double a_const = 1.0; int a_flags = 0;
   const double* o_ptr = nullptr; double o_const = 0.0; int o_flags = 0;
+  double* nrm_partials = nullptr;   // [row tiles][consumer warps] sums of squares of what the launch stores, or null
 };
 // Per-launch cross-rank wiring of a gated bundle launch: flag words in THIS rank's exchange arena that
 // neighbours raise (a unit whose bundle names flag k starts only once flags[k*stride] >= wait_val[k]),
@@ -512,6 +520,9 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
                    const void* x, const double* sb, double cb, int bf, const void* y,
                    cudaStream_t s);
 void scalar_finish_norm(double* v, double p, cudaStream_t s);
+// out = sqrt(sum of partials[0..n)) summed in a fixed order (one block): the finish of the norm folded into an apply
+void norm_finish_partials(const double* partials, int64_t n, double* scratch, double* out, cudaStream_t s);
+size_t norm_finish_scratch_bytes();
 // restriction / its adjoint: out[i] (acc)= in[idx[i]]  or  out[idx[i]] (acc)= in[i]   (indices unique)
 void vec_gather(int dtype, void* out, const void* in, const void* idx, int idx64, int64_t n, int scatter, int acc, cudaStream_t s);
 

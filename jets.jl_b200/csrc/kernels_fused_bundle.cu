@@ -246,6 +246,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       char* obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
       M.out_tile = obase + (out_off + tile_start) * (int64_t)sizeof(T);
       M.rec = rec;
+      M.pad2[0] = B.pbase + (q - B.unit_begin) * B.nrows + __ldg(&rec->row_in_bundle);   // (unit, row) tile index
       const int fl = (tile_start == 0 ? F_BLK0 : 0) | (rem <= te ? F_BLKEND : 0) |
                      ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
                      ((gflags & BG_ACC) ? F_ACC : 0);
@@ -605,6 +606,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
       }
       if (flags & F_LAST) {
+        double ss = 0.0;               // sum of squares of what this thread stores (norm folded into the apply)
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
           const int e0 = (i * kConsumers + tid) * V;
@@ -621,11 +623,26 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
               for (int j = 0; j < V; ++j) vs[j] = acc[i][j];
             }
             *reinterpret_cast<Vec*>(out_tile + e0) = v;
+            if (P.coef.nrm_partials) {
+#pragma unroll
+              for (int j = 0; j < V; ++j) ss = __dadd_rn(ss, __dmul_rn((double)vs[j], (double)vs[j]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
-              if (e0 + j < nvalid) out_tile[e0 + j] = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
+              if (e0 + j < nvalid) {
+                const T r = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
+                out_tile[e0 + j] = r;
+                if (P.coef.nrm_partials) ss = __dadd_rn(ss, __dmul_rn((double)r, (double)r));
+              }
           }
+        }
+        if (P.coef.nrm_partials) {
+          // fixed shuffle tree per warp, one partial per (unit, row) tile and warp: the result does not depend on
+          // which CTA happened to claim the unit
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) ss = __dadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+          if ((tid & 31) == 0) P.coef.nrm_partials[(size_t)M.pad2[0] * CW + (tid >> 5)] = ss;
         }
       }
       if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; }

@@ -600,6 +600,7 @@ struct Builder {
         bool first = true;
         auto flush = [&](bool row_last) {
           cur.out_off = row.out_off;
+          cur.row_in_bundle = nrows;
           cur.flags = (first ? BG_ROW_FIRST : 0) | (row_last ? BG_ROW_LAST : 0) | (accflag ? BG_ACC : 0) |
                       (row.out_alt << BG_OUT_ALT_SHIFT);
           o.sstreams = std::max(o.sstreams, (int)cur.nsstreams);
@@ -650,6 +651,7 @@ struct Builder {
       }
       for (auto& lu : last_use) o.groups[lu.first].terms[lu.second].xflags |= XF_RELEASE;
       B.ngroups = (int32_t)o.groups.size() - B.group_begin;
+      B.nrows = nrows;
       B.nx = next_alloc;
       o.max_rows = std::max(o.max_rows, nrows);
       o.bundles.push_back(B);
@@ -804,11 +806,16 @@ struct Builder {
         BTerm& bt = gr.terms[t];
         bt.xflags = (uint8_t)((bt.xflags & 3) | (((bt.xrel / NX) & 1) << 2) | ((bt.xrel % NX) << 4));
       }
-    int64_t unit = 0;
+    int64_t unit = 0, rowtiles = 0;
     for (BundleRec& b : sim.bundles) {
       b.unit_begin = unit;
-      unit += (b.len + te - 1) / te;
+      b.pbase = rowtiles;
+      const int64_t u = (b.len + te - 1) / te;
+      unit += u;
+      rowtiles += u * b.nrows;
     }
+    f.nrowtiles = rowtiles;
+    { static const int cw[6] = {16, 8, 16, 8, 30, 24}; f.consumer_warps = cw[variant >= 0 && variant < 6 ? variant : 0]; }
     f.variant = variant;
     f.NX = NX; f.NS = NS; f.sstreams = sim.sstreams;
     f.G = safe_lanes(sim, NX, NS);
@@ -1401,13 +1408,29 @@ std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel
 
 // out = cA*(A in) + cO*out fused into the store epilogue when the whole apply is ONE bundle launch
 // that writes every output row (otherwise the caller stages through a temporary).
-bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef) {
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef, double* norm_out) {
   if (p.steps.size() != 1) return false;
   Step& st = p.steps[0];
   if (st.kind != ST_FUSED || !st.fused.bundle || st.acc != ACC_SET || st.src.which != 0 || st.dst.which != 1 ||
       !st.fused.covers_out)
     return false;
-  launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
+  if (!norm_out) {
+    launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
+    return true;
+  }
+  // the norm of what the launch stores: per-(unit, row, warp) sums of squares from the store epilogue, finished in a
+  // fixed order by one block -- no second pass over the vector
+  const int64_t n = st.fused.nrowtiles * st.fused.consumer_warps;
+  if (n <= 0 || st.fused.nunits == 0) return false;
+  if (!p.nrm_partials) {
+    CUDA_TRY(cudaMalloc(&p.nrm_partials, (size_t)n * sizeof(double) + norm_finish_scratch_bytes()));
+    CUDA_TRY(cudaMemsetAsync(p.nrm_partials + n, 0, norm_finish_scratch_bytes(), ctx().stream));
+    p.blobs.push_back(p.nrm_partials);
+  }
+  ApplyCoef c = coef;
+  c.nrm_partials = p.nrm_partials;
+  launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &c);
+  norm_finish_partials(p.nrm_partials, n, p.nrm_partials + n, norm_out, ctx().stream);
   return true;
 }
 

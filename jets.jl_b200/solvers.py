@@ -163,6 +163,12 @@ def _apply_axpby(out, A, x, sa, ca, af, so, co, of):
                                so.h if so is not None else None, co, of))
 
 
+def _apply_axpby_norm(out, A, x, sa, ca, af, so, co, of, nrm):
+    """The same, and nrm = norm(out) from the store epilogue's partials: no norm pass (jets_apply_axpby_norm)."""
+    check(lib.jets_apply_axpby_norm(A._h.h, A._mode, out._h, x._h, sa.h if sa is not None else None, ca, af,
+                                    so.h if so is not None else None, co, of, nrm.h))
+
+
 def _sprog(steps):
     """[(out, op, a, b|None), ...] scalar operations in ONE launch (jets_scalar_prog)."""
     n = len(steps)
@@ -181,9 +187,10 @@ class LsqrGraphFused(LsqrGraph):
         u~ <- (1/alpha) A v~  - (alpha/beta) u~        one fused apply (reads v~, state, u~; writes u~)
         v~ <- (1/beta') A'u~  - (beta'/alpha) v~       one fused apply
 
-    replace apply + axpy + scale (9 -> 4 vector passes per half iteration), the scalar recurrences
-    run as two scalar programs, and the normalisations are folded into the coefficients of the
-    x / w updates.  Same iterates as ``LsqrGraph`` up to rounding."""
+    replace apply + axpy + scale (9 -> 4 vector passes per half iteration), ``beta = ||u~||`` and ``alpha = ||v~||``
+    come out of the same launches (``jets_apply_axpby_norm``: no norm pass), the scalar recurrences run as two
+    scalar programs, and the normalisations are folded into the coefficients of the x / w updates.  Same
+    iterates as ``LsqrGraph`` up to rounding."""
 
     def __init__(self, A, b):
         self.x = x = J.zeros(J.domain(A))
@@ -201,11 +208,11 @@ class LsqrGraphFused(LsqrGraph):
         self._keep = (A, At, u, v, w, rho, rhobar, phibar, phi, theta, c, s, t, t1, t2, tab, tba)
 
         def body():
-            _apply_axpby(u, A, v, alpha, 0.0, L.COEF_INV, tab, 0.0, L.COEF_NEG)    # u~ = A v~/alpha - (alpha/beta) u~
-            check(lib.jets_norm_dev(u._h, 2.0, beta.h))
+            # u~ = A v~/alpha - (alpha/beta) u~ ; beta = ||u~|| comes out of the same launch (store-epilogue partials +
+            # a one-block finish): the coefficients are read when the launch starts, the norm is written after it
+            _apply_axpby_norm(u, A, v, alpha, 0.0, L.COEF_INV, tab, 0.0, L.COEF_NEG, beta)
             _sprog([(tba, "/", beta, alpha)])
-            _apply_axpby(v, At, u, beta, 0.0, L.COEF_INV, tba, 0.0, L.COEF_NEG)   # v~ = A'u~/beta - (beta/alpha) v~
-            check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
+            _apply_axpby_norm(v, At, u, beta, 0.0, L.COEF_INV, tba, 0.0, L.COEF_NEG, alpha)   # v~ = A'u~/beta - (beta/alpha) v~ ; alpha = ||v~||
             _sprog([(rho, "h", rhobar, beta), (c, "/", rhobar, rho), (s, "/", beta, rho), (theta, "*", s, alpha),
                     (t, "*", c, alpha), (rhobar, "n", t, None), (phi, "*", c, phibar), (phibar, "*", s, phibar),
                     (t1, "/", phi, rho), (t2, "/", theta, rho), (tab, "/", alpha, beta)])

@@ -792,6 +792,18 @@ def test_apply_axpby_matches_separate_ops(D, kind):
         tmp = op * xin
         B.solvers._axpby(ref, sa, 0.0, L.COEF_INV, tmp, so, 0.0, L.COEF_NEG, ref)
         assert_bits(got.to_host(), ref.to_host())
+        # jets_apply_axpby_norm: the same vector, and its norm from the store epilogue's partials (no norm pass for
+        # the fused plan; a separate pass for the staged one) -- 1e-12 against numpy, and run-to-run identical
+        nrm = B.solvers._S(0.0)
+        vals = []
+        for _ in range(3):
+            got2 = o0.copy()
+            B.solvers._apply_axpby_norm(got2, op, xin, sa, 0.0, L.COEF_INV, so, 0.0, L.COEF_NEG, nrm)
+            vals.append(nrm.get())
+            assert_bits(got2.to_host(), ref.to_host())
+        want = np.linalg.norm(ref.to_host().astype(np.float64))
+        assert abs(vals[0] - want) <= 1e-12 * want
+        assert vals[0] == vals[1] == vals[2]
 
 
 def test_vectorized_operator(O, D):
