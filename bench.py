@@ -263,7 +263,8 @@ def build_c5(B, rank, world, blk):
     op = D.DistOp(B, A, halo=1)
     x = B.zeros(own)
     B.check(B.lib.jets_buf_rand(x._h, SEED_M, C.c_uint64(r0 * blk), 0))
-    op.register(x)      # collective: forward applies on x read the neighbours' halo blocks in place (NVLink, no copy)
+    if os.environ.get("JETS_BENCH_NO_REGISTER", "0") != "1":   # (tuning: the push path instead)
+        op.register(x)  # collective: forward applies on x read the neighbours' halo blocks in place (NVLink, no copy)
     return dict(A=A, op=op, x=x, d=B.zeros(own), m=B.zeros(own), W=W, rl=rl, part=part, own=own)
 
 
@@ -413,6 +414,11 @@ def run_ours(args):
     gate_timeouts = op.gate_timeouts
     engine = {"launches_per_apply": op.info(4), "neighbours": op.info(2), "gate_timeouts": gate_timeouts}
 
+    if os.environ.get("JETS_B200_TRACE") == "1":   # tuning: per-CTA timelines of the last 64 launches of every rank
+        tb = np.zeros(64 * 160 * 8, dtype=np.uint64)
+        nt = lib.jets_debug_trace(tb.ctypes.data_as(C.c_void_p), tb.size)
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        np.save(os.path.join(ROOT, "gpurun_out", f"trace_n{world}_rank{rank}.npy"), np.concatenate([[np.uint64(nt)], tb]))
     if args.no_e2e:     # tuning runs only: a line without e2e is not a bench result
         if rank == 0:
             print(json.dumps({"tuning_only": True, "n_gpus": world, "value": round(value, 2), "launch_ms": [round(k_fwd, 4), round(k_adj, 4)],
@@ -749,10 +755,12 @@ def extra_workloads(B, torch, stream, peak):
     out["config4_lsqr_200it_fused_updates"] = {
         "total_ms": round(msf, 3), "us_per_iteration": round(1e3 * msf / iters, 2), "value": round(by_iter * iters / msf / 1e6, 1),
         "unit": "GB/s (per-primitive algorithmic bytes / time)", "frac_of_per_primitive_roofline": round(by_iter * iters / msf / 1e6 / peak, 4),
-        "bytes_actually_required_per_iteration": 16 * nb * n4 * 8,
+        "bytes_actually_required_per_iteration": 15 * nb * n4 * 8,
+        "bytes_note": "2 fused applies (4 N w each) + 2 norms (1 each, folded into the applies' store epilogue) + the x / w updates in "
+                      "one pass (5 instead of 6): 15 N w of DRAM traffic; frac_of_fused_roofline keeps round 1's 16 N w numerator",
         "frac_of_fused_roofline": round(16 * nb * n4 * 8 * iters / msf / 1e6 / peak, 4),
-        "what": "u, v unnormalised; u = A v/alpha - (alpha/beta) u and v = A'u/beta - (beta/alpha) v each ONE fused apply; "
-                "two scalar programs; > 1.0 of the per-primitive roofline comes from fusion",
+        "what": "u, v unnormalised; u = A v/alpha - (alpha/beta) u and v = A'u/beta - (beta/alpha) v each ONE fused apply whose store "
+                "epilogue also yields the norm; x and w updated in one pass; two scalar programs; > 1.0 of the per-primitive roofline comes from fusion",
         "final_alpha_beta": [af, bf], "norm_x": nxf, "rel_diff_norm_x_vs_unfused": abs(nxf - nx4) / nx4}
     del Gf, xf
     del G, A4, Bd, Sd, W4, rhs4, x4

@@ -177,6 +177,12 @@ int jets_axpby_dev(jets_buf out, jets_scalar sa, double ca, int a_flags, jets_bu
                    jets_scalar sb, double cb, int b_flags, jets_buf y);
 #define JETS_COEF_NEG 1
 #define JETS_COEF_INV 2
+/* Two such updates of equal length in ONE pass -- out1 = a1.*x1 .+ b1.*y1 and out2 = a2.*x2 .+ b2.*y2 -- every
+ * input element read before either output element is written, so outputs may alias inputs: CG's x += a p,
+ * r -= a q and LSQR's x += (phi/rho) w, w = v - (theta/rho) w share one read of the common vector and one launch.
+ * Bit-identical to two jets_axpby_dev calls issued in that order on non-overlapping updates.                    */
+int jets_axpby_pair_dev(jets_buf out1, jets_scalar s1a, double c1a, int f1a, jets_buf x1, jets_scalar s1b, double c1b, int f1b, jets_buf y1,
+                        jets_buf out2, jets_scalar s2a, double c2a, int f2a, jets_buf x2, jets_scalar s2b, double c2b, int f2b, jets_buf y2);
 /* CUDA-graph capture of a sequence of library calls on the context stream.                    */
 int jets_graph_begin(void);
 int jets_graph_end(void** graph_exec_out);

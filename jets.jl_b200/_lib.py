@@ -100,6 +100,7 @@ SIGNATURES = {
     "jets_scalar_prog": (_i, [_i32, _p, C.c_char_p, _p, _p]),
     "jets_apply_axpby": (_i, [_p, _i, _p, _p, _p, _d, _i, _p, _d, _i]),
     "jets_axpby_dev": (_i, [_p, _p, _d, _i, _p, _p, _d, _i, _p]),
+    "jets_axpby_pair_dev": (_i, [_p, _p, _d, _i, _p, _p, _d, _i, _p, _p, _p, _d, _i, _p, _p, _d, _i, _p]),
     "jets_apply_axpby_norm": (_i, [_p, _i, _p, _p, _p, _d, _i, _p, _d, _i, _p]),
     "jets_graph_begin": (_i, []),
     "jets_graph_end": (_i, [_pp]),

@@ -702,6 +702,23 @@ int jets_axpby_dev(jets_buf out, jets_scalar sa, double ca, int af, jets_buf x, 
                   sb ? sb->dev : nullptr, cb, bf, y ? y->ptr() : nullptr, ctx().stream);
   });
 }
+int jets_axpby_pair_dev(jets_buf out1, jets_scalar s1a, double c1a, int f1a, jets_buf x1, jets_scalar s1b, double c1b, int f1b, jets_buf y1,
+                        jets_buf out2, jets_scalar s2a, double c2a, int f2a, jets_buf x2, jets_scalar s2b, double c2b, int f2b, jets_buf y2) {
+  return guard([&] {
+    require_ready();
+    JETS_CHECK(x1 && y1 && x2 && y2, JETS_ERR_INVALID, "null buffer handle");
+    check_pair(out1, x1); check_pair(out1, y1); check_pair(out2, x2); check_pair(out2, y2); check_pair(out1, out2);
+    check_real(out1->dtype, "jets_axpby_pair_dev");
+    void* const out[2] = {out1->ptr(), out2->ptr()};
+    const void* const x[2] = {x1->ptr(), x2->ptr()};
+    const void* const y[2] = {y1->ptr(), y2->ptr()};
+    const double* const sa[2] = {s1a ? s1a->dev : nullptr, s2a ? s2a->dev : nullptr};
+    const double* const sb[2] = {s1b ? s1b->dev : nullptr, s2b ? s2b->dev : nullptr};
+    const double ca[2] = {c1a, c2a}, cb[2] = {c1b, c2b};
+    const int af[2] = {f1a, f2a}, bf[2] = {f1b, f2b};
+    vec_axpby_pair_dev(out1->dtype, out1->length(), out, sa, ca, af, x, sb, cb, bf, y, ctx().stream);
+  });
+}
 int jets_graph_begin(void) {
   return guard([&] {
     require_ready();

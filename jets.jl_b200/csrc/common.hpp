@@ -519,6 +519,9 @@ void scalar_prog(const ScalarProg& p, cudaStream_t s);
 void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca, int af,
                    const void* x, const double* sb, double cb, int bf, const void* y,
                    cudaStream_t s);
+void vec_axpby_pair_dev(int dtype, int64_t n, void* const out[2], const double* const sa[2], const double ca[2], const int af[2],
+                        const void* const x[2], const double* const sb[2], const double cb[2], const int bf[2], const void* const y[2],
+                        cudaStream_t s);
 void scalar_finish_norm(double* v, double p, cudaStream_t s);
 // out = sqrt(sum of partials[0..n)) summed in a fixed order (one block): the finish of the norm folded into an apply
 void norm_finish_partials(const double* partials, int64_t n, double* scratch, double* out, cudaStream_t s);

@@ -214,6 +214,61 @@ __global__ void __launch_bounds__(kThreads) axpby_dev_kernel(T* __restrict__ out
   }
 }
 
+// Two such updates in ONE pass (CG: x += a p, r -= a q; LSQR: x += t1 w, w = v/alpha - t2 w): every input element is
+// read before either output element is written, so an output may alias any input.  Same arithmetic per update as
+// axpby_dev_kernel (one rounding per operation), so the results are bit-identical to two separate calls.
+struct AxpbyPair {
+  void* out[2]; const void* x[2]; const void* y[2];
+  const double* sa[2]; const double* sb[2];
+  double ca[2], cb[2];
+  int af[2], bf[2];
+};
+__device__ __forceinline__ double coef_of(const double* s, double c, int f) {
+  double v = s ? *s : c;
+  if (f & JETS_COEF_INV) v = 1.0 / v;
+  if (f & JETS_COEF_NEG) v = -v;
+  return v;
+}
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(kThreads) axpby_pair_kernel(const AxpbyPair P, int64_t n) {
+  using Vec = typename VecOf<T>::type;
+  constexpr int V = VEC ? VecOf<T>::V : 1;
+  const T a0 = (T)coef_of(P.sa[0], P.ca[0], P.af[0]), b0 = (T)coef_of(P.sb[0], P.cb[0], P.bf[0]);
+  const T a1 = (T)coef_of(P.sa[1], P.ca[1], P.af[1]), b1 = (T)coef_of(P.sb[1], P.cb[1], P.bf[1]);
+  const int64_t nvec = VEC ? n / V : n;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    if (VEC) {
+      const Vec x0 = reinterpret_cast<const Vec*>(P.x[0])[i], y0 = reinterpret_cast<const Vec*>(P.y[0])[i];
+      const Vec x1 = reinterpret_cast<const Vec*>(P.x[1])[i], y1 = reinterpret_cast<const Vec*>(P.y[1])[i];
+      Vec r0, r1;
+#pragma unroll
+      for (int j = 0; j < V; ++j) {
+        reinterpret_cast<T*>(&r0)[j] = a0 * reinterpret_cast<const T*>(&x0)[j] + b0 * reinterpret_cast<const T*>(&y0)[j];
+        reinterpret_cast<T*>(&r1)[j] = a1 * reinterpret_cast<const T*>(&x1)[j] + b1 * reinterpret_cast<const T*>(&y1)[j];
+      }
+      reinterpret_cast<Vec*>(P.out[0])[i] = r0;
+      reinterpret_cast<Vec*>(P.out[1])[i] = r1;
+    } else {
+      const T x0 = reinterpret_cast<const T*>(P.x[0])[i], y0 = reinterpret_cast<const T*>(P.y[0])[i];
+      const T x1 = reinterpret_cast<const T*>(P.x[1])[i], y1 = reinterpret_cast<const T*>(P.y[1])[i];
+      reinterpret_cast<T*>(P.out[0])[i] = a0 * x0 + b0 * y0;
+      reinterpret_cast<T*>(P.out[1])[i] = a1 * x1 + b1 * y1;
+    }
+  }
+  if (VEC) {
+    const int64_t t0 = nvec * V;
+    const int64_t gid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid < n - t0) {
+      const int64_t i = t0 + gid;
+      const T x0 = reinterpret_cast<const T*>(P.x[0])[i], y0 = reinterpret_cast<const T*>(P.y[0])[i];
+      const T x1 = reinterpret_cast<const T*>(P.x[1])[i], y1 = reinterpret_cast<const T*>(P.y[1])[i];
+      reinterpret_cast<T*>(P.out[0])[i] = a0 * x0 + b0 * y0;
+      reinterpret_cast<T*>(P.out[1])[i] = a1 * x1 + b1 * y1;
+    }
+  }
+}
+
 // ------------------------------------------------------------------ reductions -----------
 enum RKind : int { R_DOT = 0, R_SUMSQ, R_SUMABS, R_NNZ, R_MAXABS, R_MINABS, R_SUMPOW, R_MIN, R_MAX };
 
@@ -542,6 +597,28 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
   } else {
     if (al) axpby_dev_kernel<double, true><<<grid_for(n / 2 + 1, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
     else axpby_dev_kernel<double, false><<<grid_for(n, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
+  }
+  CUDA_TRY(cudaGetLastError());
+  count_launch();
+}
+
+void vec_axpby_pair_dev(int dtype, int64_t n, void* const out[2], const double* const sa[2], const double ca[2], const int af[2],
+                        const void* const x[2], const double* const sb[2], const double cb[2], const int bf[2], const void* const y[2],
+                        cudaStream_t s) {
+  if (n <= 0) return;
+  AxpbyPair P;
+  bool al = true;
+  for (int k = 0; k < 2; ++k) {
+    P.out[k] = out[k]; P.x[k] = x[k]; P.y[k] = y[k]; P.sa[k] = sa[k]; P.sb[k] = sb[k];
+    P.ca[k] = ca[k]; P.cb[k] = cb[k]; P.af[k] = af[k]; P.bf[k] = bf[k];
+    al = al && aligned16(out[k]) && aligned16(x[k]) && aligned16(y[k]);
+  }
+  if (dtype == JETS_F32) {
+    if (al) axpby_pair_kernel<float, true><<<grid_for(n / 4 + 1, 2), kThreads, 0, s>>>(P, n);
+    else axpby_pair_kernel<float, false><<<grid_for(n, 2), kThreads, 0, s>>>(P, n);
+  } else {
+    if (al) axpby_pair_kernel<double, true><<<grid_for(n / 2 + 1, 2), kThreads, 0, s>>>(P, n);
+    else axpby_pair_kernel<double, false><<<grid_for(n, 2), kThreads, 0, s>>>(P, n);
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();

@@ -850,6 +850,10 @@ struct Builder {
           if (b.nx > 0) side = std::min<int64_t>(side, NX / b.nx);
           ch = std::max(ch, side);
         }
+        // bundles that wait for a neighbour's "ready" flag run at the very END of the launch: small claims there, so
+        // that they even out the CTAs' finishing times (N=8 trace: 30-unit claims = 1.7 claims per CTA left the CTAs
+        // of the adjoint finishing up to 100 us apart, and the skew came back as start waits in the next forward)
+        if ((b.gate & ((1 << GF_LO_READY) | (1 << GF_HI_READY))) && b.ngroups * 4 <= max_groups) ch = std::min<int64_t>(ch, 4);
         ch = std::max<int64_t>(1, std::min<int64_t>(32, ch) >> shrink);
         any = any || ch > 1;
         b.chunk = (int32_t)ch;

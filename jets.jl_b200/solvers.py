@@ -169,6 +169,13 @@ def _apply_axpby_norm(out, A, x, sa, ca, af, so, co, of, nrm):
                                     so.h if so is not None else None, co, of, nrm.h))
 
 
+def _axpby_pair(out1, s1a, c1a, f1a, x1, s1b, c1b, f1b, y1, out2, s2a, c2a, f2a, x2, s2b, c2b, f2b, y2):
+    """Two axpby updates in one pass (jets_axpby_pair_dev); a None scalar means "use the constant"."""
+    h = lambda s: s.h if s is not None else None
+    check(lib.jets_axpby_pair_dev(out1._h, h(s1a), c1a, f1a, x1._h, h(s1b), c1b, f1b, y1._h,
+                                  out2._h, h(s2a), c2a, f2a, x2._h, h(s2b), c2b, f2b, y2._h))
+
+
 def _sprog(steps):
     """[(out, op, a, b|None), ...] scalar operations in ONE launch (jets_scalar_prog)."""
     n = len(steps)
@@ -216,8 +223,9 @@ class LsqrGraphFused(LsqrGraph):
             _sprog([(rho, "h", rhobar, beta), (c, "/", rhobar, rho), (s, "/", beta, rho), (theta, "*", s, alpha),
                     (t, "*", c, alpha), (rhobar, "n", t, None), (phi, "*", c, phibar), (phibar, "*", s, phibar),
                     (t1, "/", phi, rho), (t2, "/", theta, rho), (tab, "/", alpha, beta)])
-            _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                             # x += (phi/rho) w
-            _axpby(w, alpha, 0.0, L.COEF_INV, v, t2, 0.0, L.COEF_NEG, w)          # w = v~/alpha - (theta/rho) w
+            # x += (phi/rho) w and w = v~/alpha - (theta/rho) w in ONE pass (w read once, before it is overwritten)
+            _axpby_pair(x, None, 1.0, 0, x, t1, 0.0, 0, w,
+                        w, alpha, 0.0, L.COEF_INV, v, t2, 0.0, L.COEF_NEG, w)
 
         body()  # iteration 1; builds every plan outside the capture
         check(lib.jets_graph_begin())

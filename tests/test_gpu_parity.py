@@ -806,6 +806,23 @@ def test_apply_axpby_matches_separate_ops(D, kind):
         assert vals[0] == vals[1] == vals[2]
 
 
+@pytest.mark.parametrize("T,n", [(np.float64, 100_003), (np.float32, 4096), (np.float32, 7)])
+def test_axpby_pair_matches_two_updates(D, T, n):
+    """jets_axpby_pair_dev: LSQR's x += t1 w ; w = v/alpha - t2 w in one pass, outputs aliasing inputs -- bit-identical
+    to the two jets_axpby_dev calls in that order."""
+    B = D.B
+    L = B.solvers.L
+    sp = B.JetSpace(T, n)
+    x, w, v = B.rand(sp, seed=1), B.rand(sp, seed=2), B.rand(sp, seed=3)
+    t1, t2, al = B.solvers._S(0.37), B.solvers._S(1.9), B.solvers._S(2.5)
+    xr, wr = x.copy(), w.copy()
+    B.solvers._axpby(xr, None, 1.0, 0, xr, t1, 0.0, 0, wr)
+    B.solvers._axpby(wr, al, 0.0, L.COEF_INV, v, t2, 0.0, L.COEF_NEG, wr)
+    B.solvers._axpby_pair(x, None, 1.0, 0, x, t1, 0.0, 0, w, w, al, 0.0, L.COEF_INV, v, t2, 0.0, L.COEF_NEG, w)
+    assert_bits(x.to_host(), xr.to_host())
+    assert_bits(w.to_host(), wr.to_host())
+
+
 def test_vectorized_operator(O, D):
     """test/runtests.jl:797-838: B = vec(A) applied to vec(x) equals A*x, for a matrix-shaped space and
     for a block operator; vec(A') maps back to the domain."""
