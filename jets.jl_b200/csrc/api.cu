@@ -301,6 +301,9 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_PRE_STATE")) c.no_pre_state = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_FUSED_NORM")) c.no_fused_norm = atoi(v);
+    if (const char* v = getenv("JETS_B200_GROUP_STREAMS")) c.group_streams = atoi(v);
+    if (const char* v = getenv("JETS_B200_NO_TAIL_SPLIT")) c.no_tail_split = atoi(v);
+    if (const char* v = getenv("JETS_B200_TAIL_MIN_UNITS")) c.tail_min_units = atoll(v);
     if (const char* v = getenv("JETS_B200_NO_FIRST_STATIC")) c.no_first_static = atoi(v);
     if (const char* v = getenv("JETS_B200_TRACE")) {
       if (atoi(v)) {

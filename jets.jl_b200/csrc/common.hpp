@@ -77,6 +77,9 @@ struct Context {
   unsigned long long* trace_buf = nullptr;
   int64_t trace_count = 0;
   int no_first_static = 0;   // JETS_B200_NO_FIRST_STATIC=1: the first claim of a CTA goes through the atomic counter too (A/B)
+  int64_t tail_min_units = 0; // JETS_B200_TAIL_MIN_UNITS: split the tail of launches with at least this many full-height units (tests: 1)
+  int no_tail_split = 0;     // JETS_B200_NO_TAIL_SPLIT=1: no fine-grained sub-bundles over the last tile positions (A/B)
+  int group_streams = 0;     // JETS_B200_GROUP_STREAMS=n: at most n state streams per term group (tuning)
   int no_fused_norm = 0;     // JETS_B200_NO_FUSED_NORM=1: jets_apply_axpby_norm runs the norm as a separate pass (A/B)
   int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)
   uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last bundle launch (the only kernel that triggers its dependents early) writes
@@ -291,7 +294,7 @@ struct BGroupRec {   // 320 bytes
 static_assert(offsetof(BGroupRec, nsstreams) % 16 == 0 && offsetof(BGroupRec, terms) % 16 == 0 &&
               offsetof(BGroupRec, stages) % 16 == 0, "BGroupRec alignment");
 static_assert(sizeof(BGroupRec) == 320, "BGroupRec layout");
-struct BundleRec {   // 56 bytes: consecutive output rows of equal length walked by one CTA per tile position
+struct BundleRec {   // 64 bytes: consecutive output rows of equal length walked by one CTA per tile position
   int64_t unit_begin;          // first (bundle, position) unit of this bundle in the launch-wide enumeration
   int64_t len;                 // row length (elements)
   int32_t group_begin, ngroups;
@@ -301,6 +304,7 @@ struct BundleRec {   // 56 bytes: consecutive output rows of equal length walked
   int32_t claim_begin, chunk;  // dynamic scheduling: first claim of this bundle, units per claim
   int64_t pbase;               // first (unit, row) tile of this bundle in the launch-wide enumeration (norm partials)
   int32_t nrows, pad;
+  int32_t pos0, npos;          // the tile positions this record covers: [pos0, pos0 + npos) of ceil(len / tile)
 };
 
 struct FSeg {        // schedule segment: positions [pos_begin, ...) with `nactive` rows active

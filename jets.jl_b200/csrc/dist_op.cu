@@ -590,6 +590,12 @@ int jets_dist_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
     JETS_CHECK(in->length() == nin, JETS_ERR_SHAPE, "input shard has %lld elements, the rank-local operator expects %lld", (long long)in->length(), (long long)nin);
     JETS_CHECK(out->length() == nout, JETS_ERR_SHAPE, "output shard has %lld elements, the rank-local operator produces %lld", (long long)out->length(), (long long)nout);
     JETS_CHECK(buf_ok(in) && buf_ok(out), JETS_ERR_UNSUPPORTED, "distributed banded apply: in/out must be library-owned (guarded, 16-byte aligned) vectors");
+    if (D->pipe && D->pipe->have_prev_step) {
+      // pipelined host-buffer steps of this operator may still be in flight on the library's streams: the flag
+      // epochs are shared, so the apply is ordered after them
+      CUDA_TRY(cudaStreamWaitEvent(ctx().stream, D->pipe->ev_down, 0));
+      CUDA_TRY(cudaStreamWaitEvent(ctx().stream, D->pipe->ev_comp, 0));
+    }
     const jets_dist_op_s::Reg* reg = nullptr;
     if (!adj && (D->has_prev || D->has_next)) {
       auto it = D->regs.find(in->ptr());

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       if (++slot == NS) { slot = 0; par ^= 1; }
       __syncwarp();
     };
-    int64_t unit_end = B.unit_begin + (B.len + te - 1) / te;
+    int64_t unit_end = B.unit_begin + B.npos;
 
     // One lane issues one term group of unit `q` into state slot `my`.
     // stage 0: the whole group.  stage 1 (before griddepcontrol.wait): only the operator-STATE streams, which no
@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       const uint4 t01 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[0]));
       const uint4 t23 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[2]));
       const int64_t out_off = __ldg(&rec->out_off);
-      const int64_t tile_start = (q - B.unit_begin) * te;
+      const int64_t tile_start = (B.pos0 + (q - B.unit_begin)) * te;
       const int64_t rem = B.len - tile_start;
       const int nvalid = rem < te ? (int)rem : (int)te;
       const uint32_t bytes = lpad + (((uint32_t)nvalid * sizeof(T) + 15u) & ~15u) + rpad;
@@ -305,7 +305,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
         b = lo;
         B = P.bundles[b];
-        unit_end = B.unit_begin + (B.len + te - 1) / te;
+        unit_end = B.unit_begin + B.npos;
       }
     };
     int64_t q = blockIdx.x, q_end = P.nunits;
@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
         b = lo;
         B = P.bundles[b];
-        unit_end = B.unit_begin + (B.len + te - 1) / te;
+        unit_end = B.unit_begin + B.npos;
       }
     };
     // Without an early queue the FIRST claim of a CTA is static (claim blockIdx.x: the grid never exceeds the
@@ -344,13 +344,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     asm volatile("griddepcontrol.wait;" ::: "memory");
     if (lane == 0) JETS_TRACE(2, gtime());
-    if (first_static) claim_issue();
-    else if (dyn) {
+    // The NEXT ticket is fetched while the last group batch of the current claim is being issued -- early enough to
+    // hide the atomic, late enough not to reserve a unit this CTA will not start for a long time (traced on config 5:
+    // with the ticket fetched when a claim was opened, every CTA held one unstarted 280 us unit in reserve when the
+    // queue ran dry, and the CTAs finished 330 us apart).
+    if (dyn && !first_static) {
       claim_issue();
       c = claim_take();
       if (phase == 0 && c >= n_early) { phase = 1; claim_issue(); c = claim_take(); }
       have = c < P.nclaims;
-      if (have) { open_claim(); claim_issue(); }
+      if (have) open_claim();
     }
     while (have) {
       if (q >= q_end) {
@@ -363,7 +366,6 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
         if (c >= P.nclaims) break;
         open_claim();
-        claim_issue();
       }
       locate_unit();
       if ((B.gate >> 4) != cur_sig) {
@@ -409,8 +411,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         if (U > mine) U = (int)mine;
         if (U < 1) U = 1;
       }
+      const bool last_of_claim = dyn && q + (int64_t)U * stride >= q_end;
       if (U > 1) {
         const int n = U * B.ngroups;
+        if (last_of_claim) claim_issue();
         if (lane < n) {
           const int u = lane / B.ngroups, g = lane - u * B.ngroups;
           int my = slot + lane;
@@ -424,6 +428,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       } else {
         for (int g0 = 0; g0 < B.ngroups; g0 += G) {
           const int n = (B.ngroups - g0) < G ? (B.ngroups - g0) : G;
+          if (last_of_claim && g0 + G >= B.ngroups) claim_issue();
           if (lane < n) {
             int my = slot + lane;
             uint32_t mypar = par;

@@ -561,15 +561,23 @@ struct Builder {
     std::vector<BGroupRec> groups;
     std::vector<BundleRec> bundles;
     std::vector<char> early;         // per bundle: every row is an early row
+    std::vector<std::pair<int, int>> row_range;   // per bundle: [first, last) of the launch's row list
     int maxdist = 0, sstreams = 0, max_rows = 1;
   };
 
+  // state streams one term group (= one state slot) may carry; JETS_B200_GROUP_STREAMS (tuning): fewer streams per
+  // slot leave room for 16 KB tiles when every term has a state stream (config 1)
+  static int max_group_streams() {
+    const int v = ctx().group_streams;
+    return (v >= 1 && v <= kMaxStreams) ? v : kMaxStreams;
+  }
   static int64_t xkey(const PTerm& t) { return t.key | ((int64_t)t.in_alt << 56); }   // identity of an input tile stream
   static void simulate_bundles(const std::vector<PRow>& rows, int NX, int Bmax, bool accflag, BundleSim& o) {
     o = BundleSim{};
     size_t ri = 0;
     while (ri < rows.size()) {
       BundleRec B{};
+      const size_t ri0 = ri;
       B.len = rows[ri].len;
       B.gate = rows[ri].wait | (rows[ri].sig << 4);
       B.group_begin = (int32_t)o.groups.size();
@@ -610,7 +618,7 @@ struct Builder {
           first = false;
         };
         for (const PTerm& t : row.terms) {
-          if (cur.nterms > 0 && (cur.nterms == kGroupTerms || cur.nsstreams + (int)t.sptr.size() > kMaxStreams ||
+          if (cur.nterms > 0 && (cur.nterms == kGroupTerms || cur.nsstreams + (int)t.sptr.size() > max_group_streams() ||
                                  nst + (int)t.stages.size() > kGroupStages))
             flush(false);
           int gi = (int)o.groups.size();
@@ -656,6 +664,7 @@ struct Builder {
       o.max_rows = std::max(o.max_rows, nrows);
       o.bundles.push_back(B);
       o.early.push_back(all_early && nrows > 0);
+      o.row_range.push_back({(int)ri0, (int)ri});
     }
   }
 
@@ -801,6 +810,61 @@ struct Builder {
         if (eff > best + 1e-3) { best = eff; te = c; }
       }
     }
+    for (BundleRec& b : sim.bundles) { b.pos0 = 0; b.npos = (int32_t)((b.len + te - 1) / te); }
+    // Fine-grained tail.  A unit of a long bundle is a lot of work (config 5: 256 rows x 3 tiles = 12 MB, 280 us), the
+    // SMs do not run at the same speed, and the launch ends when the slowest CTA finishes its last unit: traced on
+    // config 5, the CTAs finish up to 330 us apart and idle 146 us on average (1.8 % of the launch).  So the LAST tile
+    // positions of every long bundle are enumerated again as sub-bundles of an eighth of its rows (an extra 2 input
+    // tiles per cut and position: negligible), claimed after all full-height units: the dynamic scheduler evens the
+    // finishing times out with them.
+    int G_tail = 1 << 30;
+    size_t tail_first = (size_t)-1, tail_last = 0;     // [tail_first, tail_last): the tail sub-bundles in sim.bundles
+    if (!ctx().no_tail_split && !ctx().static_sched && ctx().bundle_bmax <= 0) {
+      int64_t heavy_units = 0;
+      int big_rows = 0;
+      for (size_t i = 0; i < sim.bundles.size(); ++i)
+        if (!sim.early[i] && sim.bundles[i].nrows >= 16) { heavy_units += sim.bundles[i].npos; big_rows = std::max(big_rows, sim.bundles[i].nrows); }
+      const int64_t min_units = ctx().tail_min_units > 0 ? ctx().tail_min_units : 8 * (int64_t)grid;
+      if (heavy_units >= min_units) {
+        const int sub_rows = std::max(8, (big_rows + 7) / 8);
+        BundleSim sub;
+        simulate_bundles(rows, NX, sub_rows, accflag, sub);
+        G_tail = safe_lanes(sub, NX, NS);
+        // tail positions: about 1.5 full-height units per CTA in total, shared out over the long bundles by length
+        std::vector<BundleRec> mains, tails, rest_late;
+        std::vector<char> e_mains, e_tails, e_late;
+        std::vector<BGroupRec> groups = sim.groups;
+        const int32_t sub_group_base = (int32_t)groups.size();
+        groups.insert(groups.end(), sub.groups.begin(), sub.groups.end());
+        for (size_t i = 0; i < sim.bundles.size(); ++i) {
+          BundleRec b = sim.bundles[i];
+          const bool late = (b.gate & ((1 << GF_LO_READY) | (1 << GF_HI_READY))) && b.nrows < 16;
+          if (sim.early[i] || b.nrows < 16) {
+            (late ? rest_late : mains).push_back(b);
+            (late ? e_late : e_mains).push_back(sim.early[i]);
+            continue;
+          }
+          int32_t pt = (int32_t)std::min<int64_t>(b.npos / 3, (3 * (int64_t)grid * b.npos + 2 * heavy_units - 1) / (2 * heavy_units));
+          if (pt < 1) { mains.push_back(b); e_mains.push_back(0); continue; }
+          BundleRec m = b;
+          m.npos = b.npos - pt;
+          mains.push_back(m); e_mains.push_back(0);
+          for (size_t j = 0; j < sub.bundles.size(); ++j) {       // the sub-bundles made of this bundle's rows
+            if (sub.row_range[j].first < sim.row_range[i].first || sub.row_range[j].second > sim.row_range[i].second) continue;
+            BundleRec t = sub.bundles[j];
+            t.group_begin += sub_group_base;
+            t.pos0 = b.npos - pt;
+            t.npos = pt;
+            tails.push_back(t); e_tails.push_back(0);
+          }
+        }
+        sim.groups.swap(groups);
+        sim.bundles.clear(); sim.early.clear();
+        tail_first = mains.size(); tail_last = mains.size() + tails.size();
+        for (auto* v : {&mains, &tails, &rest_late}) sim.bundles.insert(sim.bundles.end(), v->begin(), v->end());
+        for (auto* v : {&e_mains, &e_tails, &e_late}) sim.early.insert(sim.early.end(), v->begin(), v->end());
+      }
+    }
     for (BGroupRec& gr : sim.groups)          // split every allocation index for the kernel (no division per term)
       for (int t = 0; t < gr.nterms; ++t) {
         BTerm& bt = gr.terms[t];
@@ -810,22 +874,21 @@ struct Builder {
     for (BundleRec& b : sim.bundles) {
       b.unit_begin = unit;
       b.pbase = rowtiles;
-      const int64_t u = (b.len + te - 1) / te;
-      unit += u;
-      rowtiles += u * b.nrows;
+      unit += b.npos;
+      rowtiles += (int64_t)b.npos * b.nrows;
     }
     f.nrowtiles = rowtiles;
     { static const int cw[6] = {16, 8, 16, 8, 30, 24}; f.consumer_warps = cw[variant >= 0 && variant < 6 ? variant : 0]; }
     f.variant = variant;
     f.NX = NX; f.NS = NS; f.sstreams = sim.sstreams;
-    f.G = safe_lanes(sim, NX, NS);
+    f.G = std::min(safe_lanes(sim, NX, NS), G_tail);
     f.tile_elems = (int)te;
     f.nbundles = (int32_t)sim.bundles.size();
     f.nunits = unit;
     f.nrows = (int32_t)rows.size();
     f.ntiles = unit;
     for (const BundleRec& b : sim.bundles) {        // units behind every cross-rank signal
-      const int64_t u = (b.len + te - 1) / te;
+      const int64_t u = b.npos;
       for (int s = 0; s < kGateFlags; ++s)
         if ((b.gate >> (4 + s)) & 1) f.sig_total[s] += (int32_t)u;
       if (b.gate) f.gated = true;
@@ -840,8 +903,9 @@ struct Builder {
     for (int shrink = 0; ; ++shrink) {
       nclaims = 0;
       bool any = false;
-      for (BundleRec& b : sim.bundles) {
-        const int64_t u = (b.len + te - 1) / te;
+      for (size_t bi = 0; bi < sim.bundles.size(); ++bi) {
+        BundleRec& b = sim.bundles[bi];
+        const int64_t u = b.npos;
         // equal work per claim ...
         int64_t ch = std::max<int64_t>(1, max_groups / std::max(1, b.ngroups));
         // ... and at least what the producer issues side by side for a short bundle (several units per batch)
@@ -854,6 +918,7 @@ struct Builder {
         // that they even out the CTAs' finishing times (N=8 trace: 30-unit claims = 1.7 claims per CTA left the CTAs
         // of the adjoint finishing up to 100 us apart, and the skew came back as start waits in the next forward)
         if ((b.gate & ((1 << GF_LO_READY) | (1 << GF_HI_READY))) && b.ngroups * 4 <= max_groups) ch = std::min<int64_t>(ch, 4);
+        if (bi >= tail_first && bi < tail_last) ch = 1;       // the tail exists for its granularity
         ch = std::max<int64_t>(1, std::min<int64_t>(32, ch) >> shrink);
         any = any || ch > 1;
         b.chunk = (int32_t)ch;
@@ -870,7 +935,7 @@ struct Builder {
       for (size_t i = 0; i < sim.bundles.size(); ++i) {
         const BundleRec& b = sim.bundles[i];
         lead = lead && sim.early[i];
-        if (lead) f.early_claims += ((b.len + te - 1) / te + b.chunk - 1) / b.chunk;
+        if (lead) f.early_claims += (b.npos + b.chunk - 1) / b.chunk;
       }
     }
     const size_t gb = (sim.groups.size() * sizeof(BGroupRec) + 255) & ~(size_t)255;

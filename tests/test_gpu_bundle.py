@@ -294,6 +294,9 @@ def test_chunked_host_pipeline_matches_monolithic_apply(D, nchunks):
     {"JETS_B200_FAST_VARIANT": "0"},
     {"JETS_B200_FAST_VARIANT": "1", "JETS_B200_BUNDLE_NX": "3"},
     {"JETS_B200_NO_PDL": "1"},
+    {"JETS_B200_TAIL_MIN_UNITS": "1"},                                  # fine-grained tail sub-bundles at test sizes
+    {"JETS_B200_TAIL_MIN_UNITS": "1", "JETS_B200_BUNDLE_NX": "4", "JETS_B200_BUNDLE_NS": "2"},
+    {"JETS_B200_NO_PRE_STATE": "1", "JETS_B200_NO_FIRST_STATIC": "1"},
 ])
 def test_tiny_rings_and_other_tile_shapes(env):
     """Re-runs the scenarios above with ring sizes that force recycling waits, group splits and

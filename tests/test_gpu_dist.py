@@ -24,12 +24,13 @@ def _free_port():
     return p
 
 
-def run_ranks(world, case, timeout=240):
+def run_ranks(world, case, timeout=240, extra_env=None):
     port = _free_port()
     procs = []
     for r in range(world):
         env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port),
                    JETS_DIST_CASE=json.dumps(case), JETS_B200_GATE_TIMEOUT_MS="20000")
+        env.update(extra_env or {})
         procs.append(subprocess.Popen([sys.executable, WORKER], env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
     outs = []
     try:
@@ -56,6 +57,15 @@ def test_banded_dist_op_vectors_match_single_gpu(world, halo, dtype, ragged):
     case = {"dtype": dtype, "nblk": 4 * world if halo == 1 else 3 * world, "halo": halo, "block_len": 40000, "ragged": 4 * ragged,
             "iters": 5, "chunks": 3, "seed": 11 * world + halo}
     res = run_ranks(world, case)
+    assert all(r["fails"] == [] for r in res), res
+
+
+@pytest.mark.gpu
+def test_banded_dist_op_with_tail_sub_bundles():
+    """The same comparison with the fine-grained tail forced on at test size (JETS_B200_TAIL_MIN_UNITS=1) and 16 local
+    block rows: gated bundles, their signals' unit counts and the flush markers must survive the re-enumeration."""
+    case = {"dtype": "float32", "nblk": 32, "halo": 1, "block_len": 20000, "ragged": 0, "iters": 4, "chunks": 2, "seed": 77}
+    res = run_ranks(2, case, extra_env={"JETS_B200_TAIL_MIN_UNITS": "1"})
     assert all(r["fails"] == [] for r in res), res
 
 
