@@ -273,10 +273,11 @@ int jets_apply(jets_op a, int mode, jets_buf out, jets_buf in, int accumulate);
  * temporary otherwise.                                                                          */
 int jets_apply_axpby(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar sa, double ca, int a_flags,
                      jets_scalar so, double co, int o_flags);
-/* The same, and norm2_out = norm(out, 2) of the vector just written (src/Jets.jl:834-848), with NO second pass over
- * it: the store epilogue leaves one Float64 sum of squares per (tile, warp) and one block adds them in a fixed
- * order -- deterministic whatever CTA computed which tile.  (Plans that are not one fused launch run a separate
- * norm pass.)  LSQR's beta = ||u||, alpha = ||v|| right after the Golub-Kahan updates.                          */
+/* The same, and norm2_out = norm(out, 2) of the vector just written (src/Jets.jl:834-848): LSQR's beta = ||u||,
+ * alpha = ||v|| right after the Golub-Kahan updates, one call.  The norm runs directly behind the launch that wrote
+ * the vector (for solver-sized vectors it is served from L2).  Folding the partial sums into the apply's store
+ * epilogue was built and measured in round 2: neutral on config 4 and 8 % slower on every OTHER launch of the fused
+ * kernel (instruction-issue pressure in its hot loop), so it was taken out again.                                */
 int jets_apply_axpby_norm(jets_op a, int mode, jets_buf out, jets_buf in, jets_scalar sa, double ca, int a_flags,
                           jets_scalar so, double co, int o_flags, jets_scalar norm2_out);
 /* Which engine the last plan for (op,mode) used: bit0 TMA-fused, bit1 LDG-fused, bit2 dense

@@ -150,12 +150,11 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
   if (coef) {
     check_real(a->dtype, "jets_apply_axpby");
     // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...
-    if (norm_out && ctx().no_fused_norm) {      // A/B: the norm as a pass of its own
-      if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef, nullptr)) {
-        vec_reduce(a->dtype, 1, out->ptr(), nullptr, out->length(), 2.0, norm_out, ctx().stream);
-        return;
-      }
-    } else if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef, norm_out)) return;
+    if (run_plan_axpby(*plan, a->dtype, in->ptr(), out->ptr(), *coef)) {
+      // the norm right behind the launch that wrote the vector: for solver-sized vectors it is served from L2
+      if (norm_out) vec_reduce(a->dtype, 1, out->ptr(), nullptr, out->length(), 2.0, norm_out, ctx().stream);
+      return;
+    }
     // ... else through a temporary owned by the operator (dense / staged plans)
     const size_t bytes = (size_t)out->length() * dsize(a->dtype);
     if (!a->axpby_tmp || a->axpby_tmp_bytes < bytes) {
@@ -300,7 +299,6 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_GRID")) c.grid_limit = atoi(v);
     if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_PRE_STATE")) c.no_pre_state = atoi(v);
-    if (const char* v = getenv("JETS_B200_NO_FUSED_NORM")) c.no_fused_norm = atoi(v);
     if (const char* v = getenv("JETS_B200_GROUP_STREAMS")) c.group_streams = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_TAIL_SPLIT")) c.no_tail_split = atoi(v);
     if (const char* v = getenv("JETS_B200_TAIL_MIN_UNITS")) c.tail_min_units = atoll(v);

@@ -80,7 +80,6 @@ struct Context {
   int64_t tail_min_units = 0; // JETS_B200_TAIL_MIN_UNITS: split the tail of launches with at least this many full-height units (tests: 1)
   int no_tail_split = 0;     // JETS_B200_NO_TAIL_SPLIT=1: no fine-grained sub-bundles over the last tile positions (A/B)
   int group_streams = 0;     // JETS_B200_GROUP_STREAMS=n: at most n state streams per term group (tuning)
-  int no_fused_norm = 0;     // JETS_B200_NO_FUSED_NORM=1: jets_apply_axpby_norm runs the norm as a separate pass (A/B)
   int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)
   uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last bundle launch (the only kernel that triggers its dependents early) writes
   int dist_early_ctas = 16;  // JETS_B200_DIST_EARLY_CTAS: CTAs that take the peer-store units of a distributed apply (0: all)
@@ -302,8 +301,8 @@ struct BundleRec {   // 64 bytes: consecutive output rows of equal length walked
   int32_t gate;                // bits 0-3: flag words the producer waits for before the unit's first load;
                                // bits 4-7: signals a finished unit of this bundle counts towards
   int32_t claim_begin, chunk;  // dynamic scheduling: first claim of this bundle, units per claim
-  int64_t pbase;               // first (unit, row) tile of this bundle in the launch-wide enumeration (norm partials)
-  int32_t nrows, pad;
+  int64_t pbase;               // first (unit, row) tile of this bundle in the launch-wide enumeration
+  int32_t nrows, nclaims;      // rows of the bundle; dynamic claims it is cut into (ceil(npos / chunk))
   int32_t pos0, npos;          // the tile positions this record covers: [pos0, pos0 + npos) of ceil(len / tile)
 };
 
@@ -422,7 +421,6 @@ struct Plan {
   std::vector<void*> tmps;       // device temporaries (owned)
   std::vector<size_t> tmp_bytes;
   std::vector<void*> blobs;      // device table blobs (owned)
-  double* nrm_partials = nullptr;  // norm partials of jets_apply_axpby_norm (in blobs once allocated)
   int engines = 0;
   // Validity: a plan holds raw pointers to the linearization points (mo) of the pointwise leaves it evaluated.
   // It stays valid while every one of those leaves still points at the same buffer (`points`); trees with more
@@ -455,7 +453,7 @@ std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel
 std::shared_ptr<Plan> get_plan(jets_op a, int mode, int accumulate);
 void run_plan(Plan& p, int dtype, char* in, char* out);
 struct ApplyCoef;
-bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef, double* norm_out = nullptr);  // false: plan is not one bundle launch
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef);  // false: plan is not one bundle launch
 
 // kernels_fused.cu
 void launch_fused(const DevFused& f, int dtype, const char* in, char* out, cudaStream_t s);
@@ -472,7 +470,6 @@ int bundle_smem_budget();
 struct ApplyCoef {
   const double* a_ptr = nullptr; double a_const = 1.0; int a_flags = 0;
   const double* o_ptr = nullptr; double o_const = 0.0; int o_flags = 0;
-  double* nrm_partials = nullptr;   // [row tiles][consumer warps] sums of squares of what the launch stores, or null
 };
 // Per-launch cross-rank wiring of a gated bundle launch: flag words in THIS rank's exchange arena that
 // neighbours raise (a unit whose bundle names flag k starts only once flags[k*stride] >= wait_val[k]),
@@ -527,9 +524,6 @@ void vec_axpby_pair_dev(int dtype, int64_t n, void* const out[2], const double* 
                         const void* const x[2], const double* const sb[2], const double cb[2], const int bf[2], const void* const y[2],
                         cudaStream_t s);
 void scalar_finish_norm(double* v, double p, cudaStream_t s);
-// out = sqrt(sum of partials[0..n)) summed in a fixed order (one block): the finish of the norm folded into an apply
-void norm_finish_partials(const double* partials, int64_t n, double* scratch, double* out, cudaStream_t s);
-size_t norm_finish_scratch_bytes();
 // restriction / its adjoint: out[i] (acc)= in[idx[i]]  or  out[idx[i]] (acc)= in[i]   (indices unique)
 void vec_gather(int dtype, void* out, const void* in, const void* idx, int idx64, int64_t n, int scatter, int acc, cudaStream_t s);
 

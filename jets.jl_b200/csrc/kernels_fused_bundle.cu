@@ -115,13 +115,17 @@ __device__ __forceinline__ unsigned long long gtime() {
 // Timeline of one CTA (profiles/trace_launch.py): 0 entry, 1 barriers initialised, 2 producer past
 // griddepcontrol.wait, 3 first tile landed (consumer), 4 first row tile stored, 5 producer issued its last group,
 // 6 consumer saw the end sentinel (all stores issued), 7 state bytes put in flight before the wait.
-#define JETS_TRACE(slot, val) do { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } while (0)
+// MODE 0 is the plain kernel; MODE 1 adds -- at compile time, so that the plain instantiation pays nothing for them
+// (measured on one box: the same features as run-time branches cost the plain config-5 launch 4 %, config 1 10 %) --
+// the cross-rank gating of the distributed apply (flag waits, flush markers, signals, alternative base pointers,
+// exit wait) and the launch timeline.
+#define JETS_TRACE(slot, val) do { if constexpr (MODE != 0) { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } } while (0)
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                    "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-template <typename T, int CW, int VPT>
+template <typename T, int CW, int VPT, int MODE>
 __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(const BundleParams P) {
   using Vec = typename VecOf<T>::type;
   constexpr int V = VecOf<T>::V;
@@ -157,14 +161,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   __syncthreads();                 // barriers initialised; nothing a previous kernel may write has been touched yet
   if (tid == 0) JETS_TRACE(1, gtime());
   if (tid < kConsumers) asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
-    // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
+  if constexpr (MODE != 0) {
+    if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
+      // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
 #pragma unroll
-    for (int k = 0; k < kGateFlags; ++k)
-      if (((P.sig_owned >> k) & 1) && P.sig_total[k] == 0 && P.gate.sig_addr[k] != nullptr) {
-        __threadfence_system();
-        st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
-      }
+      for (int k = 0; k < kGateFlags; ++k)
+        if (((P.sig_owned >> k) & 1) && P.sig_total[k] == 0 && P.gate.sig_addr[k] != nullptr) {
+          __threadfence_system();
+          st_release_sys(P.gate.sig_addr[k], P.gate.sig_val[k]);
+        }
+    }
   }
 
   if (tid >= kConsumers) {
@@ -195,7 +201,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     // stage 0: the whole group.  stage 1 (before griddepcontrol.wait): only the operator-STATE streams, which no
     // kernel of this stream writes (the host checked) -- their bytes are announced with a plain expect_tx, the
     // barrier's one arrival stays pending.  stage 2: the rest of a group whose state is already in flight.
-    auto issue = [&](const BGroupRec* rec, int64_t q, uint32_t xb, int my, uint32_t mypar, int stage) {
+    auto issue = [&](const BGroupRec* rec, int64_t q, uint32_t xb, int my, uint32_t mypar, auto stage_tag) {
+      constexpr int stage = decltype(stage_tag)::value;
       const int4 hd = __ldg(reinterpret_cast<const int4*>(&rec->nsstreams));  // nsstreams nterms xrel_mask flags
       const uint4 t01 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[0]));
       const uint4 t23 = __ldg(reinterpret_cast<const uint4*>(&rec->terms[2]));
@@ -212,8 +219,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       // ring position of the unit's first allocation (one division per group, none per term)
       const uint32_t xb_use = xb / (uint32_t)NX;
       const uint32_t xb_mod = xb - xb_use * (uint32_t)NX;
-      if (stage != 2) mbar_wait(sempty0 + 8 * my, mypar ^ 1);
-      if (stage == 1) {
+      if constexpr (stage != 2) mbar_wait(sempty0 + 8 * my, mypar ^ 1);
+      if constexpr (stage == 1) {
         if (nss > 0) {
           asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(sfull0 + 8 * my), "r"(bytes * (uint32_t)nss) : "memory");
           const uint32_t sb = sring0 + my * slot_bytes + (kPad - lpad);
@@ -224,6 +231,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
         return;
       }
+      (void)xrel_mask;
       uint32_t total = stage == 2 ? 0u : bytes * (uint32_t)nss;
       int xrelease = 0;
 #pragma unroll
@@ -242,11 +250,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
       }
       BMeta& M = meta[my];
-      const int oalt = (gflags >> BG_OUT_ALT_SHIFT) & 3;
-      char* obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
+      char* obase = P.out;
+      if constexpr (MODE != 0) {
+        const int oalt = (gflags >> BG_OUT_ALT_SHIFT) & 3;
+        obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
+      }
       M.out_tile = obase + (out_off + tile_start) * (int64_t)sizeof(T);
       M.rec = rec;
-      M.pad2[0] = B.pbase + (q - B.unit_begin) * B.nrows + __ldg(&rec->row_in_bundle);   // (unit, row) tile index
       const int fl = (tile_start == 0 ? F_BLK0 : 0) | (rem <= te ? F_BLKEND : 0) |
                      ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
                      ((gflags & BG_ACC) ? F_ACC : 0);
@@ -262,13 +272,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       for (int t = 0; t < kGroupTerms; ++t) {
         if (t < nterms && (tt[t].xflags & XF_LOAD)) {
           const int64_t px = __ldg(&rec->xptr[t]);
-          const int ialt = (xrel_mask >> (kXAltShift + 2 * t)) & 3;
-          const char* ibase = ialt == 0 ? P.in : ialt == 1 ? P.gate.in_alt[0] : ialt == 2 ? P.gate.in_alt[1] : P.gate.in_alt[2];
+          const char* ibase = P.in;
+          if constexpr (MODE != 0) {
+            const int ialt = (xrel_mask >> (kXAltShift + 2 * t)) & 3;
+            ibase = ialt == 0 ? P.in : ialt == 1 ? P.gate.in_alt[0] : ialt == 2 ? P.gate.in_alt[1] : P.gate.in_alt[2];
+          }
           const char* src = ((xrel_mask >> t) & 1) ? ibase + px : reinterpret_cast<const char*>(px);
           bulk_g2s(xring0 + tt[t].xrel * kBufBytes + (kPad - lpad), src + goff, bytes, sfull0 + 8 * my);
         }
       }
-      if (stage == 2) return;
+      if constexpr (stage == 2) return;
       const uint32_t sb = sring0 + my * slot_bytes + (kPad - lpad);
       for (int k = 0; k < nss; ++k) {
         const char* src = reinterpret_cast<const char*>(__ldg(&rec->sptr[k]));
@@ -297,7 +310,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       return phase == 0 ? t : n_early + t + ticket_base_v;
     };
     auto locate_claim = [&](int64_t c) {   // bundle of claim c (claims are bundle-major like units)
-      if (c < B.claim_begin || c >= B.claim_begin + ((unit_end - B.unit_begin) + B.chunk - 1) / B.chunk) {
+      if (c < B.claim_begin || c >= (int64_t)B.claim_begin + B.nclaims) {
         int lo = 0, hi = P.nbundles - 1;
         while (lo < hi) {
           const int mid = (lo + hi + 1) >> 1;
@@ -338,7 +351,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       // the previous kernel of the stream is still draining: put the operator state of this CTA's first unit in
       // flight now (plan tables and operator state are immutable for it); everything else waits below
       pre_groups = B.ngroups < G ? B.ngroups : G;
-      if (lane < pre_groups) issue(P.groups + B.group_begin + lane, q, 0u, lane < NS ? lane : lane - NS, 0u, 1);
+      if (lane < pre_groups) issue(P.groups + B.group_begin + lane, q, 0u, lane < NS ? lane : lane - NS, 0u, std::integral_constant<int, 1>{});
       __syncwarp();
       if (lane == 0) JETS_TRACE(7, (unsigned long long)pre_groups);
     }
@@ -368,6 +381,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         open_claim();
       }
       locate_unit();
+      if constexpr (MODE != 0) {
       if ((B.gate >> 4) != cur_sig) {
         // leaving a bundle whose units feed cross-rank signals: tell the consumers how many this CTA completed
         // (BEFORE any flag wait below -- a neighbour may be waiting for exactly this signal)
@@ -400,6 +414,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         waited |= B.gate & 15;
         __syncwarp();
       }
+      }
       // Short bundles: several units of the bundle are issued side by side, one lane per group, as
       // long as the batch needs no x buffer that one of its own groups has to release first.
       int U = 1;
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           int my = slot + lane;
           uint32_t mypar = par;
           if (my >= NS) { my -= NS; mypar ^= 1; }
-          issue(P.groups + B.group_begin + g, q + (int64_t)u * stride, xbase + (uint32_t)(u * B.nx), my, mypar, 0);
+          issue(P.groups + B.group_begin + g, q + (int64_t)u * stride, xbase + (uint32_t)(u * B.nx), my, mypar, std::integral_constant<int, 0>{});
         }
         slot += n;
         if (slot >= NS) { slot -= NS; par ^= 1; }
@@ -433,7 +448,8 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
             int my = slot + lane;
             uint32_t mypar = par;
             if (my >= NS) { my -= NS; mypar ^= 1; }
-            issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar, (g0 == 0 && lane < pre_groups) ? 2 : 0);
+            if (g0 == 0 && lane < pre_groups) issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar, std::integral_constant<int, 2>{});
+            else issue(P.groups + B.group_begin + g0 + lane, q, xbase, my, mypar, std::integral_constant<int, 0>{});
           }
           slot += n;
           if (slot >= NS) { slot -= NS; par ^= 1; }
@@ -456,6 +472,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     if (lane == 0) JETS_TRACE(5, gtime());
     flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
+    if constexpr (MODE != 0)
     if (P.gate.exit_wait && lane == 0) {
       // the last CTA to run out of work keeps the grid alive until the neighbours have finished reading this
       // rank's input (their flag words): everything that follows on the stream may then overwrite it
@@ -497,13 +514,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
     const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
-    bool tr_first = P.trace != nullptr && tid == 0, tr_store = tr_first;
+    bool tr_first = false, tr_store = false;
+    if constexpr (MODE != 0) tr_first = tr_store = P.trace != nullptr && tid == 0;
     while (true) {
       mbar_wait(sfull0 + 8 * slot, par);
-      if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; }
+      if constexpr (MODE != 0) { if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; } }
       const BMeta& M = meta[slot];
       const int flags = M.flags;
-      if (flags & (F_END | F_FLUSH)) {
+      if constexpr (MODE == 0) {
+        if (flags & F_END) break;
+      } else if (flags & (F_END | F_FLUSH)) {
         const int smask = (flags >> BG_SIG_SHIFT) & 15;
         const int cnt = M.nvalid;
         if (smask && cnt > 0) {
@@ -611,7 +631,6 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         }
       }
       if (flags & F_LAST) {
-        double ss = 0.0;               // sum of squares of what this thread stores (norm folded into the apply)
 #pragma unroll
         for (int i = 0; i < VPT; ++i) {
           const int e0 = (i * kConsumers + tid) * V;
@@ -628,36 +647,21 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
               for (int j = 0; j < V; ++j) vs[j] = acc[i][j];
             }
             *reinterpret_cast<Vec*>(out_tile + e0) = v;
-            if (P.coef.nrm_partials) {
-#pragma unroll
-              for (int j = 0; j < V; ++j) ss = __dadd_rn(ss, __dmul_rn((double)vs[j], (double)vs[j]));
-            }
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
-              if (e0 + j < nvalid) {
-                const T r = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
-                out_tile[e0 + j] = r;
-                if (P.coef.nrm_partials) ss = __dadd_rn(ss, __dmul_rn((double)r, (double)r));
-              }
+              if (e0 + j < nvalid) out_tile[e0 + j] = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
           }
         }
-        if (P.coef.nrm_partials) {
-          // fixed shuffle tree per warp, one partial per (unit, row) tile and warp: the result does not depend on
-          // which CTA happened to claim the unit
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) ss = __dadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
-          if ((tid & 31) == 0) P.coef.nrm_partials[(size_t)M.pad2[0] * CW + (tid >> 5)] = ss;
-        }
       }
-      if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; }
+      if constexpr (MODE != 0) { if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; } }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
   }
 }
 
-template <typename T, int CW, int VPT>
+template <typename T, int CW, int VPT, int MODE>
 void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
   constexpr int kBufBytes = CW * 32 * 16 * VPT + 2 * kPad;
   const size_t smem = kHdrAligned + (size_t)f.NX * kBufBytes + (size_t)f.NS * f.sstreams * kBufBytes;
@@ -665,7 +669,7 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
              JETS_ERR_INVALID, "internal: bundle kernel ring sizes NX=%d NS=%d do not fit", f.NX, f.NS);
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(jets_fused_bundle_kernel<T, CW, VPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    CUDA_TRY(cudaFuncSetAttribute(jets_fused_bundle_kernel<T, CW, VPT, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     attr_set = true;
   }
   int64_t grid = ctx().sm_count;
@@ -682,20 +686,28 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = ctx().no_pdl ? 0 : 1;
-  CUDA_TRY(cudaLaunchKernelEx(&cfg, jets_fused_bundle_kernel<T, CW, VPT>, P));
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, jets_fused_bundle_kernel<T, CW, VPT, MODE>, P));
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }
 
 template <typename T>
-void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s) {
+void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s, bool extras) {
+  if (extras) {
+    // gated (distributed) launches and traced ones: the tile shapes the planner picks for long rows and for short ones
+    switch (f.variant) {
+      case 2: launch_variant<T, 16, 2, 1>(f, P, s); return;
+      case 0: launch_variant<T, 16, 1, 1>(f, P, s); return;
+      default: JETS_FAIL(JETS_ERR_UNSUPPORTED, "the gated / traced bundle kernel is built for tile shapes 0 and 2 only (got %d)", f.variant);
+    }
+  }
   switch (f.variant) {
-    case 1: launch_variant<T, 8, 2>(f, P, s); break;
-    case 2: launch_variant<T, 16, 2>(f, P, s); break;
-    case 3: launch_variant<T, 8, 4>(f, P, s); break;
-    case 4: launch_variant<T, 30, 1>(f, P, s); break;
-    case 5: launch_variant<T, 24, 1>(f, P, s); break;
-    default: launch_variant<T, 16, 1>(f, P, s); break;
+    case 1: launch_variant<T, 8, 2, 0>(f, P, s); break;
+    case 2: launch_variant<T, 16, 2, 0>(f, P, s); break;
+    case 3: launch_variant<T, 8, 4, 0>(f, P, s); break;
+    case 4: launch_variant<T, 30, 1, 0>(f, P, s); break;
+    case 5: launch_variant<T, 24, 1, 0>(f, P, s); break;
+    default: launch_variant<T, 16, 1, 0>(f, P, s); break;
   }
 }
 
@@ -744,8 +756,11 @@ void launch_fused_bundle(const DevFused& f, int dtype, const char* in, char* out
     if (gate) { c.pdl_out_lo = 0; c.pdl_out_hi = ~(uintptr_t)0; }
     else { c.pdl_out_lo = lo; c.pdl_out_hi = hi; }
   }
-  if (dtype == JETS_F32) launch_dtype<float>(f, P, s);
-  else launch_dtype<double>(f, P, s);
+  // the plain kernel unless the launch is gated or traced (a traced launch with another tile shape stays untraced)
+  const bool extras = gate != nullptr || (P.trace != nullptr && (f.variant == 0 || f.variant == 2));
+  if (!extras) P.trace = nullptr;
+  if (dtype == JETS_F32) launch_dtype<float>(f, P, s, extras);
+  else launch_dtype<double>(f, P, s, extras);
 }
 
 }  // namespace jets

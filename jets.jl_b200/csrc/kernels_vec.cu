@@ -533,47 +533,6 @@ void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, do
   else reduce_dispatch<double>(kind, x, y, n, p, dev_out, s);
 }
 
-// sqrt of the sum of n f64 partials in a FIXED order, whatever block finishes when: block b adds its contiguous
-// share (thread t: elements t, t+256, ... left to right, then a fixed tree), the last block to finish adds the block
-// sums in block order.  `scratch` holds kNormFinishBlocks doubles + one counter word (re-armed by the last block).
-constexpr int kNormFinishBlocks = 128;
-__global__ void __launch_bounds__(256) norm_finish_kernel(const double* __restrict__ part, int64_t n, double* __restrict__ scratch,
-                                                          double* __restrict__ out) {
-  __shared__ double sm[256];
-  __shared__ bool last;
-  const int64_t per = (n + gridDim.x - 1) / gridDim.x;
-  const int64_t lo = (int64_t)blockIdx.x * per, hi = lo + per < n ? lo + per : n;
-  double s = 0.0;
-  for (int64_t i = lo + threadIdx.x; i < hi; i += 256) s = __dadd_rn(s, part[i]);
-  sm[threadIdx.x] = s;
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if ((int)threadIdx.x < o) sm[threadIdx.x] = __dadd_rn(sm[threadIdx.x], sm[threadIdx.x + o]);
-    __syncthreads();
-  }
-  unsigned int* counter = reinterpret_cast<unsigned int*>(scratch + kNormFinishBlocks);
-  if (threadIdx.x == 0) {
-    scratch[blockIdx.x] = sm[0];
-    __threadfence();
-    last = atomicAdd(counter, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (last && threadIdx.x == 0) {
-    __threadfence();
-    double t = 0.0;
-    for (unsigned b = 0; b < gridDim.x; ++b) t = __dadd_rn(t, reinterpret_cast<volatile double*>(scratch)[b]);
-    *out = sqrt(t);
-    *counter = 0u;
-  }
-}
-size_t norm_finish_scratch_bytes() { return (kNormFinishBlocks + 1) * sizeof(double); }
-void norm_finish_partials(const double* partials, int64_t n, double* scratch, double* out, cudaStream_t s) {
-  const int nb = (int)std::max<int64_t>(1, std::min<int64_t>(kNormFinishBlocks, (n + 1023) / 1024));
-  norm_finish_kernel<<<nb, 256, 0, s>>>(partials, n, scratch, out);
-  CUDA_TRY(cudaGetLastError());
-  count_launch();
-}
-
 void scalar_prog(const ScalarProg& p, cudaStream_t s) {
   if (p.n <= 0) return;
   scalar_prog_kernel<<<1, 1, 0, s>>>(p);

@@ -923,7 +923,8 @@ struct Builder {
         any = any || ch > 1;
         b.chunk = (int32_t)ch;
         b.claim_begin = (int32_t)nclaims;
-        nclaims += (u + ch - 1) / ch;
+        b.nclaims = (int32_t)((u + ch - 1) / ch);
+        nclaims += b.nclaims;
       }
       if (nclaims >= 8 * (int64_t)grid || !any) break;    // keep at least ~8 claims per CTA: halve the claims and retry
     }
@@ -1477,29 +1478,13 @@ std::shared_ptr<Plan> build_banded_plan(jets_op A_loc, int halo, const BandedSel
 
 // out = cA*(A in) + cO*out fused into the store epilogue when the whole apply is ONE bundle launch
 // that writes every output row (otherwise the caller stages through a temporary).
-bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef, double* norm_out) {
+bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& coef) {
   if (p.steps.size() != 1) return false;
   Step& st = p.steps[0];
   if (st.kind != ST_FUSED || !st.fused.bundle || st.acc != ACC_SET || st.src.which != 0 || st.dst.which != 1 ||
       !st.fused.covers_out)
     return false;
-  if (!norm_out) {
-    launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
-    return true;
-  }
-  // the norm of what the launch stores: per-(unit, row, warp) sums of squares from the store epilogue, finished in a
-  // fixed order by one block -- no second pass over the vector
-  const int64_t n = st.fused.nrowtiles * st.fused.consumer_warps;
-  if (n <= 0 || st.fused.nunits == 0) return false;
-  if (!p.nrm_partials) {
-    CUDA_TRY(cudaMalloc(&p.nrm_partials, (size_t)n * sizeof(double) + norm_finish_scratch_bytes()));
-    CUDA_TRY(cudaMemsetAsync(p.nrm_partials + n, 0, norm_finish_scratch_bytes(), ctx().stream));
-    p.blobs.push_back(p.nrm_partials);
-  }
-  ApplyCoef c = coef;
-  c.nrm_partials = p.nrm_partials;
-  launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &c);
-  norm_finish_partials(p.nrm_partials, n, p.nrm_partials + n, norm_out, ctx().stream);
+  launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
   return true;
 }
 
