@@ -323,10 +323,12 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     };
     int64_t q = blockIdx.x, q_end = P.nunits;
     int64_t c = 0;
+    bool ticket_pending = false;           // the next ticket has been requested already
     auto open_claim = [&]() {              // unit range of claim c
       locate_claim(c);
       q = B.unit_begin + (c - B.claim_begin) * B.chunk;
       q_end = q + B.chunk < unit_end ? q + B.chunk : unit_end;
+      ticket_pending = false;
     };
     auto locate_unit = [&]() {             // static mode: bundle of unit q (units are enumerated bundle-major)
       if (q >= unit_end || q < B.unit_begin) {
@@ -426,10 +428,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         if (U > mine) U = (int)mine;
         if (U < 1) U = 1;
       }
+      // Next ticket: light units (a claim of them is little work, and the producer runs through it in one or two
+      // batches) request it up front so that the atomic hides behind the claim; heavy units request it in their last
+      // group batch, see above.
       const bool last_of_claim = dyn && q + (int64_t)U * stride >= q_end;
+      if (dyn && !ticket_pending && (last_of_claim || 2 * B.ngroups <= G) && B.ngroups <= G) { claim_issue(); ticket_pending = true; }
       if (U > 1) {
         const int n = U * B.ngroups;
-        if (last_of_claim) claim_issue();
         if (lane < n) {
           const int u = lane / B.ngroups, g = lane - u * B.ngroups;
           int my = slot + lane;
@@ -443,7 +448,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       } else {
         for (int g0 = 0; g0 < B.ngroups; g0 += G) {
           const int n = (B.ngroups - g0) < G ? (B.ngroups - g0) : G;
-          if (last_of_claim && g0 + G >= B.ngroups) claim_issue();
+          if (last_of_claim && !ticket_pending && g0 + G >= B.ngroups) { claim_issue(); ticket_pending = true; }
           if (lane < n) {
             int my = slot + lane;
             uint32_t mypar = par;
