@@ -358,6 +358,25 @@ function mul_axpby!(out::B200Array, A::Jets.Jop, in::B200Array, sa::Union{B200Sc
                 handle(B).h, mode, out.h, in.h, nul(sa), ca, aflags, nul(so), co, oflags))
     out
 end
+# the same, and nrm = norm(out) of the vector just written (LSQR's beta = ||u||, alpha = ||v||), one call
+function mul_axpby_norm!(out::B200Array, A::Jets.Jop, in::B200Array, sa::Union{B200Scalar,Nothing}, ca::Real, aflags::Integer,
+                         so::Union{B200Scalar,Nothing}, co::Real, oflags::Integer, nrm::B200Scalar)
+    nul(s) = s === nothing ? C_NULL : s.h
+    mode = A isa Jets.JopAdjoint ? MODE_DFT : MODE_DF
+    B = A isa Jets.JopAdjoint ? A.op : A
+    check(ccall((:jets_apply_axpby_norm, LIB), Cint, (Ptr{Cvoid}, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}),
+                handle(B).h, mode, out.h, in.h, nul(sa), ca, aflags, nul(so), co, oflags, nrm.h))
+    out
+end
+# two axpby updates in ONE pass (CG: x += a p, r -= a q; LSQR: x += t1 w, w = v/alpha - t2 w); outputs may alias inputs
+function axpby_pair!(out1::B200Array, s1a, c1a::Real, f1a::Integer, x1::B200Array, s1b, c1b::Real, f1b::Integer, y1::B200Array,
+                     out2::B200Array, s2a, c2a::Real, f2a::Integer, x2::B200Array, s2b, c2b::Real, f2b::Integer, y2::B200Array)
+    nul(s) = s === nothing ? C_NULL : s.h
+    check(ccall((:jets_axpby_pair_dev, LIB), Cint,
+                (Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid},
+                 Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}, Ptr{Cvoid}, Cdouble, Cint, Ptr{Cvoid}),
+                out1.h, nul(s1a), c1a, f1a, x1.h, nul(s1b), c1b, f1b, y1.h, out2.h, nul(s2a), c2a, f2a, x2.h, nul(s2b), c2b, f2b, y2.h))
+end
 # graph = capture() do ... library calls ... end; launch(graph) replays them
 mutable struct B200Graph
     h::Ptr{Cvoid}
@@ -422,5 +441,7 @@ function normal_host!(host_out::Vector{T}, A::DistJop, host_in::Vector{T}; nchun
     host_out
 end
 join!(A::DistJop) = check(ccall((:jets_dist_op_join, LIB), Cint, (Ptr{Cvoid},), A.h))
+# collective: lets the neighbours map the domain shard x, so that forward applies on it read their halo blocks in place
+register!(A::DistJop, x::B200Array) = (check(ccall((:jets_dist_op_register, LIB), Cint, (Ptr{Cvoid}, Ptr{Cvoid}), A.h, x.h)); x)
 
 end # module
