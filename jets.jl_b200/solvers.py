@@ -52,6 +52,57 @@ def lsqr(A, b, iters=10, x0=None):
     return x, hist
 
 
+def lsqr_dist(op, b_own, iters=10):
+    """The same iteration on a block-row partitioned operator (``dist.DistOp``): every rank holds its shards of
+    u (range) and v, w, x (domain); ``A*v`` / ``A'*u`` are one ``jets_dist_apply`` each (halo exchange inside the
+    kernel launch), the norms are local sums of squares added over the ranks in rank order
+    (``jets_dist_sum_scalar``: bit-stable, the same on every rank) -- north_star's "scalars with all-reduce".
+    Returns (x_own, history of (alpha, beta)); the iterates equal ``lsqr`` on the whole operator up to the
+    rounding of the norms."""
+    B = op.B
+
+    def gnorm(x):
+        r = C.c_double()
+        check(lib.jets_dot(x._h, x._h, C.byref(r)))          # local sum of squares in Float64
+        t = C.c_double(r.value)
+        if lib.jets_dist_size() > 1:
+            check(lib.jets_dist_sum_scalar(C.byref(t)))
+        return t.value ** 0.5
+    x = J.zeros(op.own_space)
+    u = b_own.copy()
+    beta = gnorm(u)
+    J.lincomb_(u, [(1.0 / beta, u)])
+    v = J.zeros(op.own_space)
+    op.register(v)                                           # forward applies read the neighbours' halo of v in place
+    op.adjoint(v, u)
+    alpha = gnorm(v)
+    J.lincomb_(v, [(1.0 / alpha, v)])
+    w = v.copy()
+    phibar, rhobar = beta, alpha
+    tmp_u = J.zeros(op.range_space)
+    tmp_v = J.zeros(op.own_space)
+    hist = []
+    for _ in range(iters):
+        op.forward(tmp_u, v)                                 # u = A v - alpha u
+        J.lincomb_(u, [(1.0, tmp_u), (-alpha, u)])
+        beta = gnorm(u)
+        J.lincomb_(u, [(1.0 / beta, u)])
+        op.adjoint(tmp_v, u)                                 # v = A' u - beta v
+        J.lincomb_(v, [(1.0, tmp_v), (-beta, v)])
+        alpha = gnorm(v)
+        J.lincomb_(v, [(1.0 / alpha, v)])
+        rho = (rhobar * rhobar + beta * beta) ** 0.5
+        c, s = rhobar / rho, beta / rho
+        theta = s * alpha
+        rhobar = -c * alpha
+        phi = c * phibar
+        phibar = s * phibar
+        J.lincomb_(x, [(1.0, x), (phi / rho, w)])
+        J.lincomb_(w, [(1.0, v), (-theta / rho, w)])
+        hist.append((alpha, beta))
+    return x, hist
+
+
 class _S:
     """Device scalar (jets_scalar)."""
 

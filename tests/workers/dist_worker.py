@@ -137,6 +137,20 @@ def main():
             ok = np.linalg.norm(got.astype(np.float64) - n_ref[sl]) <= tol * np.linalg.norm(n_ref[sl])
         if not ok:
             fails.append(f"host pipeline rep {rep}: differs (max {np.abs(got - n_ref[sl]).max():.3e})")
+    # a whole solver on the partitioned operator: LSQR with one jets_dist_apply per product and rank-ordered norms
+    # (the iterate v is a REGISTERED vector that the solver overwrites every iteration: the pull path's exit handshake)
+    if case.get("lsqr", 1):
+        rhs = g.random(off[-1]).astype(T) + 0.5
+        its = 12
+        x_ref, h_ref = B.solvers.lsqr(A, B.to_device(rhs, B.range_(A)), its)
+        x_d, h_d = B.solvers.lsqr_dist(op, B.to_device(rhs[sl], own_dom), its)
+        tol = 1e-9 if T == np.float64 else 2e-3
+        xr = x_ref.to_host()[sl].astype(np.float64)
+        err = np.linalg.norm(x_d.to_host().astype(np.float64) - xr) / max(np.linalg.norm(xr), 1e-300)
+        if not err <= tol:
+            fails.append(f"distributed LSQR iterate off by {err:.3e} > {tol}")
+        if not all(abs(a - ar) <= tol * abs(ar) and abs(b - br) <= tol * abs(br) for (a, b), (ar, br) in zip(h_d, h_ref)):
+            fails.append("distributed LSQR alpha/beta history differs")
     if op.gate_timeouts != 0:
         fails.append(f"{op.gate_timeouts} work units timed out waiting for a neighbour")
     launches = op.info(4)
