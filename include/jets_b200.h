@@ -201,7 +201,8 @@ int jets_op_pointwise(jets_dtype dt, int64_t n, int fn, double p, jets_op* out);
 int jets_op_stencil(jets_dtype dt, int64_t n, int kind, jets_op* out);
 /* Matrix as operator (src/Jets.jl:325-326, :573-576; fixture JopBaz test/runtests.jl:27-33):
  * A is rows x cols, column-major (Julia layout), leading dimension = rows.  nrhs>1 applies A to
- * an (cols x nrhs) column-major matrix of right-hand sides (domain JetSpace(T,cols,nrhs)).     */
+ * an (cols x nrhs) column-major matrix of right-hand sides (domain JetSpace(T,cols,nrhs)).
+ * Complex eltypes: the adjoint applies the CONJUGATE transpose (mul!(m, A', d), :574).          */
 int jets_op_dense(jets_buf A, int64_t rows, int64_t cols, int64_t nrhs, jets_op* out);
 /* Restriction d = m[idx] with adjoint m[idx] = d, zero elsewhere -- the JetPack-style leaf the Jets
  * documentation composes with (docs/src/index.md:14-19; JetPack.jl itself is un-vendored, so the

@@ -795,7 +795,6 @@ int jets_op_dense(jets_buf A, int64_t rows, int64_t cols, int64_t nrhs, jets_op*
     JETS_CHECK(A->length() == rows * cols, JETS_ERR_SHAPE, "matrix buffer has %lld elements, expected %lld x %lld",
                (long long)A->length(), (long long)rows, (long long)cols);
     JETS_CHECK(rows < (1LL << 31) && cols < (1LL << 31), JETS_ERR_UNSUPPORTED, "matrix dimension too large");
-    check_real(A->dtype, "dense matrix operators");
     jets_op a = new_op(K_DENSE, A->dtype);
     a->dom = space1(cols * nrhs);
     a->rng = space1(rows * nrhs);

@@ -8,6 +8,7 @@
 // f32 products are accumulated in f32 over at most 256 (N) / 64 (T) terms and then carried in
 // f64, which keeps 1e-5 relative accuracy at K = 131072.
 #include "common.hpp"
+#include "cplx.cuh"
 
 namespace jets {
 namespace {
@@ -246,10 +247,183 @@ __global__ void __launch_bounds__(kThreads) gemv_t_kernel(const GemvParams P) {
   }
 }
 
+// ---------------------------------------------------------------- complex eltypes ---------
+// d = A m and m = A' d with A' the CONJUGATE transpose (_matmul_df'! src/Jets.jl:574: mul!(m, A', d)) on
+// interleaved ComplexF32 / ComplexF64 storage.  Same decomposition as the real kernels: N -- a lane owns V
+// consecutive rows (one 128-bit load per column) and the 8 warps split the columns; T -- a warp owns a column and
+// the lanes stride down it.  Products follow Julia's complex multiply (cplx.cuh); every partial is carried in f64.
+template <typename R> struct CVecOf;
+template <> struct CVecOf<float>  { using type = float4;  static constexpr int V = 2; };
+template <> struct CVecOf<double> { using type = double2; static constexpr int V = 1; };
+
+template <typename R>
+__device__ __forceinline__ void cfinish_store(Cx<R>* o, double re, double im, int acc) {
+  if (acc == ACC_SET) { o->re = (R)re; o->im = (R)im; }
+  else if (acc == ACC_ADD) { o->re = (R)((double)o->re + re); o->im = (R)((double)o->im + im); }
+  else { o->re = (R)((double)o->re - re); o->im = (R)((double)o->im - im); }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) cgemv_n_kernel(const GemvParams P) {
+  using Vec = typename CVecOf<R>::type;
+  using Z = Cx<R>;
+  constexpr int V = CVecOf<R>::V;
+  constexpr int TM = 32 * V;
+  constexpr int CU = 4;
+  __shared__ double red[kWarps][TM][2];
+  const int g = find_group(P.tile_ptr, P.ngroups, (int)blockIdx.x);
+  const int tile = (int)blockIdx.x - P.tile_ptr[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e_begin = P.row_ptr[g], e_end = P.row_ptr[g + 1];
+  const int64_t i0 = (int64_t)tile * TM + lane * V;
+  double are[V], aim[V];
+#pragma unroll
+  for (int k = 0; k < V; ++k) are[k] = aim[k] = 0.0;
+  int64_t out_off = 0;
+  int out_len = 0;
+  for (int e = e_begin; e < e_end; ++e) {
+    const DBlock b = P.blocks[e];
+    out_off = b.out_off;
+    out_len = b.rows;
+    const Z* A = reinterpret_cast<const Z*>(b.A);
+    const Z* x = reinterpret_cast<const Z*>(P.in) + b.in_off;
+    const int cw = (b.cols + kWarps - 1) / kWarps;
+    const int j_begin = warp * cw;
+    const int j_end = min(b.cols, j_begin + cw);
+    const bool vec_ok = ((int64_t)(tile + 1) * TM <= b.rows) && ((b.lda % V) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    for (int j0 = j_begin; j0 < j_end; j0 += 32) {
+      const int jl = j0 + lane;
+      const Z xl = (jl < j_end) ? x[jl] : Z(R(0));
+      const int nj = min(32, j_end - j0);
+      Z part[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) part[k] = Z(R(0));
+      if (vec_ok) {
+        int jj = 0;
+        for (; jj + CU <= nj; jj += CU) {
+          Vec a[CU];
+#pragma unroll
+          for (int u = 0; u < CU; ++u) a[u] = __ldcs(reinterpret_cast<const Vec*>(A + (int64_t)(j0 + jj + u) * b.lda + i0));
+#pragma unroll
+          for (int u = 0; u < CU; ++u) {
+            const Z xv(__shfl_sync(0xffffffffu, xl.re, jj + u), __shfl_sync(0xffffffffu, xl.im, jj + u));
+            const Z* as = reinterpret_cast<const Z*>(&a[u]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) part[k] = part[k] + as[k] * xv;
+          }
+        }
+        for (; jj < nj; ++jj) {
+          const Vec a = __ldcs(reinterpret_cast<const Vec*>(A + (int64_t)(j0 + jj) * b.lda + i0));
+          const Z xv(__shfl_sync(0xffffffffu, xl.re, jj), __shfl_sync(0xffffffffu, xl.im, jj));
+          const Z* as = reinterpret_cast<const Z*>(&a);
+#pragma unroll
+          for (int k = 0; k < V; ++k) part[k] = part[k] + as[k] * xv;
+        }
+      } else {
+        for (int jj = 0; jj < nj; ++jj) {
+          const Z xv(__shfl_sync(0xffffffffu, xl.re, jj), __shfl_sync(0xffffffffu, xl.im, jj));
+#pragma unroll
+          for (int k = 0; k < V; ++k)
+            if (i0 + k < b.rows) part[k] = part[k] + A[(int64_t)(j0 + jj) * b.lda + i0 + k] * xv;
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < V; ++k) { are[k] += (double)part[k].re; aim[k] += (double)part[k].im; }   // folded every 32 columns
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < V; ++k) { red[warp][lane * V + k][0] = are[k]; red[warp][lane * V + k][1] = aim[k]; }
+  __syncthreads();
+  if (threadIdx.x < TM) {
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) { sr += red[w][threadIdx.x][0]; si += red[w][threadIdx.x][1]; }
+    const int64_t i = (int64_t)tile * TM + threadIdx.x;
+    if (i < out_len) cfinish_store(reinterpret_cast<Z*>(P.out) + out_off + i, sr, si, P.acc);
+  }
+}
+
+template <typename R>
+__global__ void __launch_bounds__(kThreads) cgemv_t_kernel(const GemvParams P) {
+  using Vec = typename CVecOf<R>::type;
+  using Z = Cx<R>;
+  constexpr int V = CVecOf<R>::V;
+  constexpr int CW = 4;
+  constexpr int TN = kWarps * CW;
+  constexpr int U = 4;
+  constexpr int RC = 32 * U * V;    // rows per chunk
+  __shared__ __align__(16) Z xs[RC];
+  const int g = find_group(P.tile_ptr, P.ngroups, (int)blockIdx.x);
+  const int tile = (int)blockIdx.x - P.tile_ptr[g];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int e_begin = P.row_ptr[g], e_end = P.row_ptr[g + 1];
+  double are[CW], aim[CW];
+#pragma unroll
+  for (int c = 0; c < CW; ++c) are[c] = aim[c] = 0.0;
+  int64_t out_off = 0;
+  int out_len = 0;
+  for (int e = e_begin; e < e_end; ++e) {
+    const DBlock b = P.blocks[e];
+    out_off = b.out_off;
+    out_len = b.cols;
+    const Z* A = reinterpret_cast<const Z*>(b.A);
+    const Z* x = reinterpret_cast<const Z*>(P.in) + b.in_off;
+    const bool vec_ok = ((b.lda % V) == 0) && ((reinterpret_cast<uintptr_t>(A) & 15) == 0);
+    for (int r0 = 0; r0 < b.rows; r0 += RC) {
+      const int nr = min(RC, b.rows - r0);
+      __syncthreads();
+      for (int i = threadIdx.x; i < RC; i += kThreads) xs[i] = (i < nr) ? x[r0 + i] : Z(R(0));
+      __syncthreads();
+      Vec xv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) xv[u] = reinterpret_cast<const Vec*>(xs)[u * 32 + lane];
+#pragma unroll
+      for (int c = 0; c < CW; ++c) {
+        const int j = tile * TN + c * kWarps + warp;
+        if (j >= b.cols) continue;
+        const Z* col = A + (int64_t)j * b.lda + r0;
+        Z part(R(0));
+        if (vec_ok && nr == RC) {
+          Vec a[U];
+#pragma unroll
+          for (int u = 0; u < U; ++u) a[u] = __ldcs(reinterpret_cast<const Vec*>(col) + u * 32 + lane);
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const Z* as = reinterpret_cast<const Z*>(&a[u]);
+            const Z* bs = reinterpret_cast<const Z*>(&xv[u]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) part = part + conj(as[k]) * bs[k];
+          }
+        } else {
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const Z* bs = reinterpret_cast<const Z*>(&xv[u]);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+              const int i = (u * 32 + lane) * V + k;
+              if (i < nr) part = part + conj(col[i]) * bs[k];
+            }
+          }
+        }
+        are[c] += (double)part.re;
+        aim[c] += (double)part.im;
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < CW; ++c) {
+    double vr = are[c], vi = aim[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { vr += __shfl_xor_sync(0xffffffffu, vr, o); vi += __shfl_xor_sync(0xffffffffu, vi, o); }
+    const int j = tile * TN + c * kWarps + warp;
+    if (lane == 0 && j < out_len) cfinish_store(reinterpret_cast<Z*>(P.out) + out_off + j, vr, vi, P.acc);
+  }
+}
+
 }  // namespace
 
 void gemv_tile_count(int dtype, bool trans, int32_t out_len, int32_t* ntiles) {
-  const int V = dtype == JETS_F32 ? 4 : 2;
+  const int V = dtype == JETS_F32 ? 4 : dtype == JETS_C128 ? 1 : 2;
   const int per = trans ? (kWarps * 4) : 32 * V;
   *ntiles = (out_len + per - 1) / per;
 }
@@ -269,6 +443,18 @@ void launch_gemv(const Step& st, int dtype, const char* in, char* out, cudaStrea
   P.partials = st.gemv_partials;
   P.ntiles = (int32_t)st.gemv_tiles;
   const unsigned grid = (unsigned)(st.gemv_tiles * P.ksplit);
+  if (is_cplx(dtype)) {       // never split (emit_gemv leaves gemv_ksplit at 1 for complex eltypes)
+    if (dtype == JETS_C64) {
+      if (trans) cgemv_t_kernel<float><<<grid, kThreads, 0, s>>>(P);
+      else cgemv_n_kernel<float><<<grid, kThreads, 0, s>>>(P);
+    } else {
+      if (trans) cgemv_t_kernel<double><<<grid, kThreads, 0, s>>>(P);
+      else cgemv_n_kernel<double><<<grid, kThreads, 0, s>>>(P);
+    }
+    CUDA_TRY(cudaGetLastError());
+    count_launch();
+    return;
+  }
   if (dtype == JETS_F32) {
     if (trans) gemv_t_kernel<float><<<grid, kThreads, 0, s>>>(P);
     else gemv_n_kernel<float><<<grid, kThreads, 0, s>>>(P);

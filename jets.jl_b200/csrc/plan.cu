@@ -1162,7 +1162,7 @@ struct Builder {
     plan.blobs.push_back(blob);
     st.d_dblocks = reinterpret_cast<DBlock*>(blob);
     st.d_row_ptr = reinterpret_cast<int32_t*>(blob + nb_al);
-    if (!trans && st.gemv_tiles > 0 && st.gemv_tiles < 2 * (int64_t)ctx().sm_count) {
+    if (!trans && !is_cplx(dtype) && st.gemv_tiles > 0 && st.gemv_tiles < 2 * (int64_t)ctx().sm_count) {
       // a block-row shard of a wide operator has few row tiles: split every tile's blocks over several CTAs
       int min_entries = 1 << 30;
       for (size_t g = 0; g + 1 < row_ptr.size(); ++g) min_entries = std::min(min_entries, row_ptr[g + 1] - row_ptr[g]);

@@ -190,8 +190,6 @@ def test_complex_pointwise_jacobian(O, D):
     assert abs(complex(lhs) - complex(rhs)) <= 1e-11 * abs(complex(lhs))
     with pytest.raises(B.JetsError):
         B.JopPointwise(T, n, "exp")
-    with pytest.raises(B.JetsError):
-        B.JopDense(np.ones((3, 3), dtype=T))
 
 
 # ------------------------------------------------------------------ symmetric spaces --------
@@ -327,3 +325,60 @@ def test_state_plumbing(D):  # state/state!/perfstat/close: src/Jets.jl:264-290,
     ps = B.perfstat(Cmp)
     assert ps["engines"] == ["tma"] and ps["launches"] == 1
     assert B.close(A) is False and B.close(B.compose(S, B.JopDiagonal(w))) is None
+
+
+# ------------------------------------------------------------------ complex dense blocks ----
+@pytest.mark.parametrize("T", CT)
+@pytest.mark.parametrize("shape", [(1, 1, 300, 200), (2, 3, 128, 64), (3, 2, 77, 131), (1, 2, 1031, 516), (2, 1, 64, 2500)])
+def test_complex_dense_block_gemv(O, D, T, shape):
+    """Complex matrices as operators: d = A m, m = A' d with A' the conjugate transpose (_matmul_df!/_df'!
+    src/Jets.jl:573-574) under a block operator, ragged shapes included."""
+    nr, nc, rows, cols = shape
+    g = np.random.default_rng(41)
+    Bm = [[(crand(g, rows * cols, T) - T(0.5 + 0.25j)).reshape(rows, cols) for _ in range(nc)] for _ in range(nr)]
+    m = crand(g, nc * cols, T)
+    d = crand(g, nr * rows, T)
+
+    def scn(K):
+        A = K.blockop([[K.JopDense(Bm[r][c]) for c in range(nc)] for r in range(nr)])
+        lhs, rhs = K.dot_product_test(A, K.arr(m, K.domain(A)), K.arr(d, K.range_(A)))
+        return {"f": K.host(A * K.arr(m, K.domain(A))), "t": K.host(K.adjoint(A) * K.arr(d, K.range_(A))),
+                "dpt": np.array([lhs, rhs], dtype=np.complex128)}
+    o, dv = scn(O), scn(D)
+    M = np.block([[b.astype(np.complex128) for b in row] for row in Bm])
+    assert close(dv["f"], M @ m.astype(np.complex128), T) and close(dv["f"], o["f"], T)
+    assert close(dv["t"], M.conj().T @ d.astype(np.complex128), T) and close(dv["t"], o["t"], T)
+    assert abs(dv["dpt"][0] - dv["dpt"][1]) <= TOL[np.dtype(T)] * abs(dv["dpt"][0] + dv["dpt"][1])
+    Ad = D.blockop([[D.JopDense(Bm[r][c]) for c in range(nc)] for r in range(nr)])
+    Ad * D.arr(m, D.domain(Ad))
+    info = D.B.plan_info(Ad)
+    assert info["engines"] == ["gemv"] and info["launches"] == 1
+
+
+@pytest.mark.parametrize("T", CT)
+def test_complex_dense_in_composition_and_multi_rhs(O, D, T):
+    """A complex matrix composed with a complex diagonal (staged through a device temporary where the reference
+    allocates one, :525-539), and a matrix of right-hand sides (one GEMV per column: tcgen05 is Float32-only)."""
+    g = np.random.default_rng(42)
+    B, J = D.B, O.J
+    rows, cols, nrhs = 150, 90, 3
+    A = (crand(g, rows * cols, T) - T(0.5)).reshape(rows, cols)
+    w = crand(g, rows, T)
+    m, d = crand(g, cols, T), crand(g, rows, T)
+    Cd = B.JopDiagonal(w) @ B.JopDense(A)
+    Co = J.JopDiagonal(w) @ J.JopDense(A)
+    assert close((Cd * B.to_device(m)).to_host(), Co * m, T)
+    assert close((Cd.T * B.to_device(d)).to_host(), Co.T * d, T)
+    X = crand(g, cols * nrhs, T).reshape((cols, nrhs), order="F")
+    op = B.JopDense(A, nrhs=nrhs)
+    Y = op * B.to_device(X, B.domain(op))
+    assert Y.shape == (rows, nrhs) and close(Y.to_host(), A.astype(np.complex128) @ X.astype(np.complex128), T)
+    Xb = op.T * Y
+    assert close(Xb.to_host(), A.astype(np.complex128).conj().T @ Y.to_host().astype(np.complex128), T)
+    assert B.plan_info(op)["engines"] == ["gemv"]
+    # accumulate on top of a fused term inside one block row (Q1 order: fused SETs, dense adds)
+    Ad = B.blockop([[B.JopDense(A), B.JopDiagonal(w)]])
+    Ao = J.blockop([[J.JopDense(A), J.JopDiagonal(w)]])
+    x = np.concatenate([m, d])
+    assert close((Ad * B.to_device(x, B.domain(Ad))).to_host(), J.to_array(Ao * J.reshape(x.copy(), J.domain(Ao))), T)
+    assert close((Ad.T * B.to_device(d)).to_host(), J.to_array(Ao.T * d), T)
