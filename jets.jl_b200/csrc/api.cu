@@ -585,7 +585,6 @@ int jets_norm(jets_buf x, double p, double* out) {
 int jets_norm_weighted(jets_buf x, jets_buf w, double p, double* out) {
   return guard([&] {
     require_ready(); check_buf(x); check_buf(w);
-    JETS_CHECK(is_cplx(x->dtype), JETS_ERR_UNSUPPORTED, "weighted norms are implemented for the complex eltypes (JetSSpace)");
     JETS_CHECK(w->dtype == JETS_F64 && w->length() == x->length(), JETS_ERR_SHAPE, "weights must be Float64, one per element");
     const double* wp = reinterpret_cast<const double*>(w->ptr());
     int kind, finish = 0;

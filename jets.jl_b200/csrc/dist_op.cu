@@ -386,7 +386,9 @@ void pipe_step(jets_dist_op D, char* host_out, const char* host_in) {
 // Every block row needs the WHOLE domain (src/Jets.jl:1015-1030 with no zero blocks) and every rank's rows
 // contribute to every block column of the adjoint (:1039-1055): the forward all-gathers the domain shards,
 // the adjoint reduce-scatters the per-rank partial sums (NCCL over NVLink; the shards are equal-sized).
-int nccl_dtype(int dt) { return dt == JETS_F32 ? ncclFloat32 : ncclFloat64; }
+// complex shards travel as twice as many reals (a sum of complex numbers is the sum of the parts)
+int nccl_dtype(int dt) { return real_of(dt) == JETS_F32 ? ncclFloat32 : ncclFloat64; }
+size_t nccl_count(int dt, int64_t n) { return (size_t)n * (is_cplx(dt) ? 2 : 1); }
 
 void dense_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
   need_nccl();
@@ -396,13 +398,13 @@ void dense_apply(jets_dist_op D, int mode, jets_buf out, jets_buf in) {
   if (!adj) {
     JETS_CHECK(in->length() == D->shard_len, JETS_ERR_SHAPE, "input shard has %lld elements, expected %lld (domain / ranks)", (long long)in->length(), (long long)D->shard_len);
     JETS_CHECK(out->length() == nrng, JETS_ERR_SHAPE, "output has %lld elements, the rank-local rows produce %lld", (long long)out->length(), (long long)nrng);
-    NCCL_TRY(d.n.AllGather(in->ptr(), D->full->ptr(), (size_t)D->shard_len, nccl_dtype(D->dtype), d.comm, ctx().stream));
+    NCCL_TRY(d.n.AllGather(in->ptr(), D->full->ptr(), nccl_count(D->dtype, D->shard_len), nccl_dtype(D->dtype), d.comm, ctx().stream));
     ck(jets_apply(D->A, mode == JETS_MODE_F && !D->A->linear ? JETS_MODE_F : JETS_MODE_DF, out, D->full, 0));
   } else {
     JETS_CHECK(in->length() == nrng, JETS_ERR_SHAPE, "input has %lld elements, the rank-local rows take %lld", (long long)in->length(), (long long)nrng);
     JETS_CHECK(out->length() == D->shard_len, JETS_ERR_SHAPE, "output shard has %lld elements, expected %lld (domain / ranks)", (long long)out->length(), (long long)D->shard_len);
     ck(jets_apply(D->A, JETS_MODE_DFT, D->full, in, 0));
-    NCCL_TRY(d.n.ReduceScatter(D->full->ptr(), out->ptr(), (size_t)D->shard_len, nccl_dtype(D->dtype), ncclSum, d.comm, ctx().stream));
+    NCCL_TRY(d.n.ReduceScatter(D->full->ptr(), out->ptr(), nccl_count(D->dtype, D->shard_len), nccl_dtype(D->dtype), ncclSum, d.comm, ctx().stream));
   }
 }
 
@@ -549,7 +551,6 @@ int jets_dist_op_create_dense(jets_op A_loc, jets_dist_op* out) {
   return guard([&] {
     require_ready(); need_nccl();
     JETS_CHECK(A_loc && A_loc->refs > 0 && out, JETS_ERR_INVALID, "null or destroyed operator handle");
-    JETS_CHECK(!is_cplx(A_loc->dtype), JETS_ERR_UNSUPPORTED, "distributed dense apply: complex eltypes are not implemented");
     Dist& d = dist();
     const int64_t total = A_loc->dom.total();
     JETS_CHECK(total % d.size == 0, JETS_ERR_SHAPE, "the domain (%lld elements) does not split into %d equal shards", (long long)total, d.size);

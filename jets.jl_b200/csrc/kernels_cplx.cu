@@ -126,6 +126,22 @@ __global__ void __launch_bounds__(kThreads) creduce_pass1(const Cx<R>* __restric
   acc = c_block_reduce<KIND>(acc);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
+// the same pass over a REAL vector (a symmetric space with a real eltype, src/Jets.jl:408-441: conj is the identity,
+// the weights still count the mirrored positions)
+template <typename R, int KIND>
+__global__ void __launch_bounds__(kThreads) rreduce_pass1(const R* __restrict__ x, const double* __restrict__ w, int64_t n,
+                                                          int64_t chunk, double p, double* __restrict__ partial) {
+  const int64_t b0 = (int64_t)blockIdx.x * chunk;
+  int64_t b1 = b0 + chunk;
+  if (b1 > n) b1 = n;
+  double acc = c_identity<KIND>();
+  for (int64_t i = b0 + threadIdx.x; i < b1; i += kThreads) {
+    const double a = (double)x[i];
+    acc = c_combine<KIND>(acc, c_map<KIND>(a, 0.0, a, 0.0, w ? w[i] : 1.0, p));
+  }
+  acc = c_block_reduce<KIND>(acc);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) creduce_pass2(const double* __restrict__ partial, int np, int finish,
                                                           double p, double* __restrict__ out) {
@@ -157,6 +173,36 @@ void creduce_launch(const void* x, const void* y, const double* w, int64_t n, do
   CUDA_TRY(cudaGetLastError());
   count_launch(2);
 }
+template <typename R, int KIND>
+void rreduce_launch(const void* x, const double* w, int64_t n, double p, int finish, double* dev_out, cudaStream_t s) {
+  Context& c = ctx();
+  const int64_t quantum = (int64_t)kThreads * 4;
+  int64_t nb = (n + quantum - 1) / quantum;
+  const int64_t cap = (int64_t)c.sm_count * 8;
+  if (nb > cap) nb = cap;
+  if (nb < 1) nb = 1;
+  int64_t chunk = ((n + nb - 1) / nb + quantum - 1) / quantum * quantum;
+  if (chunk < quantum) chunk = quantum;
+  nb = n > 0 ? (n + chunk - 1) / chunk : 1;
+  JETS_CHECK((size_t)nb <= c.dev_scratch_elems, JETS_ERR_INVALID, "reduction scratch too small");
+  rreduce_pass1<R, KIND><<<(unsigned)nb, kThreads, 0, s>>>((const R*)x, w, n, chunk, p, c.dev_scratch);
+  creduce_pass2<KIND><<<1, kThreads, 0, s>>>(c.dev_scratch, (int)nb, finish, p, dev_out);
+  CUDA_TRY(cudaGetLastError());
+  count_launch(2);
+}
+template <typename R>
+void rreduce_dispatch(int kind, const void* x, const double* w, int64_t n, double p, int finish, double* out, cudaStream_t s) {
+  switch (kind) {
+    case 2: rreduce_launch<R, C_SUMSQ>(x, w, n, p, finish, out, s); break;
+    case 3: rreduce_launch<R, C_SUMABS>(x, w, n, p, finish, out, s); break;
+    case 4: rreduce_launch<R, C_NNZ>(x, w, n, p, finish, out, s); break;
+    case 5: rreduce_launch<R, C_MAXABS>(x, w, n, p, finish, out, s); break;
+    case 6: rreduce_launch<R, C_MINABS>(x, w, n, p, finish, out, s); break;
+    case 7: rreduce_launch<R, C_SUMPOW>(x, w, n, p, finish, out, s); break;
+    default: JETS_FAIL(JETS_ERR_INVALID, "bad weighted reduction kind %d", kind);
+  }
+}
+
 template <typename R>
 void creduce_dispatch(int kind, const void* x, const void* y, const double* w, int64_t n, double p, int finish,
                       double* out, cudaStream_t s) {
@@ -234,6 +280,8 @@ void cvec_abs(int dtype, void* out_real, const void* x, int64_t n, cudaStream_t 
 
 void cvec_reduce(int dtype, int kind, const void* x, const void* y, const double* w, int64_t n, double p, int finish,
                  double* dev_out, cudaStream_t s) {
+  if (dtype == JETS_F32) { rreduce_dispatch<float>(kind, x, w, n, p, finish, dev_out, s); return; }
+  if (dtype == JETS_F64) { rreduce_dispatch<double>(kind, x, w, n, p, finish, dev_out, s); return; }
   if (dtype == JETS_C64) creduce_dispatch<float>(kind, x, y, w, n, p, finish, dev_out, s);
   else creduce_dispatch<double>(kind, x, y, w, n, p, finish, dev_out, s);
 }

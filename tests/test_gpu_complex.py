@@ -227,6 +227,29 @@ def test_symmetric_space(O, D):  # runtests.jl:227-258
     assert x.A[2, 1] == 3 - 4j and x[(7, 2)] == 3 + 4j and x[(3, 2)] == 3 - 4j
 
 
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_symmetric_space_real_eltype(O, D, T):
+    """JetSSpace with a real eltype (src/Jets.jl:408-441: T is "usually" complex, not necessarily): conj is the
+    identity, the norms still count every stored element once per logical position it stands for."""
+    B, J = D.B, O.J
+    R = B.JetSSpace(T, (8, 4), (4, 4), indexmap)
+    x = B.rand(R, seed=22)
+    y = x.A
+    assert y.shape == (4, 4) and y.dtype == np.dtype(T) and x.to_host().shape == (8, 4)
+    xo = J.SymmetricArray(np.asfortranarray(y.copy()), (8, 4), indexmap)
+    assert np.array_equal(x.to_host(), xo.full())
+    tol = 1e-6 if T == np.float32 else 1e-12
+    for p in (2, 1, math.inf, -math.inf, 3.5):
+        assert np.isclose(float(B.norm(x, p)), float(J.norm(xo, p)), rtol=tol), p
+    assert np.isclose(float(B.norm(x)), math.sqrt(2 * np.linalg.norm(y.astype(np.float64)) ** 2), rtol=tol)
+    x[(1, 1)] = 0
+    assert float(B.norm(x, 0)) == 2 * np.count_nonzero(x.A)
+    x[(7, 2)] = 3
+    assert x.A[2, 1] == 3 and x[(3, 2)] == 3
+    z = x * 0.5 + B.rand(R, seed=23) * 0.25
+    assert z.issymmetric and z.space == R
+
+
 def test_symmetric_space_broadcast(D):  # runtests.jl:260-282
     B = D.B
     R = B.JetSSpace(np.complex128, (8, 4), (4, 4), indexmap)

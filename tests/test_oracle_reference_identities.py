@@ -493,6 +493,21 @@ def test_symmetric_space(g):  # :227-258
     assert x.A[2, 1] == 3 - 4j and x[(7, 2)] == 3 + 4j and x[(3, 2)] == 3 - 4j
 
 
+@pytest.mark.parametrize("T", [np.float32, np.float64])
+def test_symmetric_space_real_eltype(g, T):  # the same identities with a real eltype (conj is the identity)
+    R = J.JetSSpace(T, (8, 4), (4, 4), indexmap)
+    x = J.rand(R, g)
+    y = x.A
+    assert y.dtype == np.dtype(T) and x.full().shape == (8, 4)
+    assert np.array_equal(x.full()[4:, :], y) and np.array_equal(x.full()[:4, :], y)
+    tol = 1e-6 if T == np.float32 else 1e-14
+    assert np.isclose(J.norm(x), math.sqrt(2 * np.linalg.norm(y.astype(np.float64)) ** 2), rtol=tol)
+    assert np.isclose(J.norm(x, 1), 2 * np.sum(np.abs(y.astype(np.float64))), rtol=tol)
+    assert np.isclose(J.norm(x, math.inf), np.max(np.abs(y)), rtol=tol)
+    x[6, 1] = 0
+    assert J.norm(x, 0) == 2 * np.count_nonzero(y)
+
+
 def test_symmetric_space_broadcast(g):  # :260-282
     R = J.JetSSpace(np.complex128, (8, 4), (4, 4), indexmap)
     u, v, w = J.rand(R, g), J.rand(R, g), J.rand(R, g)

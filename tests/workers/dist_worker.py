@@ -158,6 +158,7 @@ def main():
         fails.append(f"a distributed apply took {launches} launches, expected 1")
     if use_nccl and case.get("dense"):
         fails += dense_case(B, D, T, g, rank, world)
+        fails += dense_case(B, D, np.dtype(np.complex64 if T == np.float32 else np.complex128), g, rank, world)
     dist.barrier()
     op.close()
     B.check(B.lib.jets_dist_shutdown())
@@ -170,24 +171,28 @@ def dense_case(B, D, T, g, rank, world):
     """Row-partitioned JopBlock of dense blocks: all-gather forward, reduce-scatter adjoint (NCCL)."""
     fails = []
     nb, k = 2 * world, 96
-    mats = {(r, c): g.random((k, k)).astype(T) for r in range(nb) for c in range(nb)}
+    cplx = np.issubdtype(T, np.complexfloating)
+
+    def draw(*shape):
+        return (g.random(shape) + (1j * g.random(shape) if cplx else 0) - 0.5).astype(T)
+    mats = {(r, c): draw(k, k) for r in range(nb) for c in range(nb)}
     A = B.blockop([[B.JopDense(mats[(r, c)]) for c in range(nb)] for r in range(nb)])
     nloc = nb // world
     r0 = rank * nloc
     A_loc = B.blockop([[B.JopDense(mats[(r0 + i, c)]) for c in range(nb)] for i in range(nloc)])
     op = D.DistOp(B, A_loc, dense=True)
-    x = g.random(nb * k).astype(T)
-    y = g.random(nb * k).astype(T)
+    x = draw(nb * k)
+    y = draw(nb * k)
     d_ref = (A * B.to_device(x, B.domain(A))).to_host()
     m_ref = (A.T * B.to_device(y, B.range_(A))).to_host()
     sl = slice(r0 * k, (r0 + nloc) * k)
     d = op.forward(B.zeros(B.range_(A_loc)), B.to_device(x[sl], op.own_space)).to_host()
     m = op.adjoint(B.zeros(op.own_space), B.to_device(y[sl], B.range_(A_loc))).to_host()
-    tol = 1e-12 if T == np.float64 else 1e-5
+    tol = 1e-12 if T in (np.float64, np.complex128) else 1e-5
     for name, got, ref in (("forward", d, d_ref[sl]), ("adjoint", m, m_ref[sl])):
-        err = np.linalg.norm(got.astype(np.float64) - ref) / np.linalg.norm(ref)
+        err = np.linalg.norm(got.astype(np.complex128) - ref) / np.linalg.norm(ref)
         if not err <= tol:
-            fails.append(f"dense {name}: off by {err:.3e} > {tol}")
+            fails.append(f"dense {name} ({T}): off by {err:.3e} > {tol}")
     op.close()
     return fails
 
