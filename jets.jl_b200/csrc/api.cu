@@ -956,7 +956,8 @@ int jets_op_block(int32_t R, int32_t C, const jets_op* ops, int dadom, jets_op* 
         lin = lin && ops[i]->linear;
         JETS_CHECK(ops[i]->dtype == a->dtype, JETS_ERR_DTYPE, "block operator with mixed eltypes");
         JETS_CHECK(ops[i]->dom.len.size() == 1 && ops[i]->rng.len.size() == 1, JETS_ERR_UNSUPPORTED,
-                   "nested block spaces are not supported");
+                   "block operators as blocks of a block operator are rejected: the reference's own forward is wrong for them "
+                   "(JetBlock_df! accumulates into a temporary shared by the block columns, src/Jets.jl:1012-1024)");
       }
       // spaces from the first block row / column (src/Jets.jl:927-928); every block must agree
       for (int c = 0; c < C; ++c) a->dom.len.push_back(ops[(size_t)c * R]->dom.total());

@@ -191,6 +191,8 @@ class BlockArray:
 
     def __getitem__(self, i):
         j, k = self._find(i)
+        if isinstance(self.arrays[j], BlockArray):
+            return self.arrays[j][k + 1]
         return self.arrays[j].reshape(-1, order="F")[k]
 
     def __setitem__(self, i, v):
@@ -198,13 +200,17 @@ class BlockArray:
             self.assign(v) if isinstance(v, (BlockArray, np.ndarray)) else fill_(self, v)
             return
         j, k = self._find(i)
+        if isinstance(self.arrays[j], BlockArray):
+            self.arrays[j][k + 1] = v
+            return
         flat = self.arrays[j].reshape(-1, order="F")
         flat[k] = v
         self.arrays[j][...] = flat.reshape(self.arrays[j].shape, order="F")
 
     def similar(self, T=None):  # :829-832
         T = self.dtype if T is None else T
-        return BlockArray([np.empty(a.shape, dtype=T) for a in self.arrays], self.indices)
+        return BlockArray([a.similar(T) if isinstance(a, BlockArray) else np.empty(a.shape, dtype=T) for a in self.arrays],
+                          self.indices)
 
     def copy(self):
         return BlockArray([a.copy() for a in self.arrays], self.indices)
@@ -264,7 +270,8 @@ def bmap(f: Callable, *args):
     out = []
     for i in range(len(ref.arrays)):
         blk = [_blk(a, i, ref.indices[i], ref.arrays[i].shape) for a in args]
-        out.append(np.asarray(f(*blk)))
+        res = f(*blk)   # blocks that are BlockArrays themselves (a JetBSpace of JetBSpaces) recurse through their operators
+        out.append(res if isinstance(res, BlockArray) else np.asarray(res))
     return BlockArray(out, ref.indices)
 
 
@@ -459,6 +466,8 @@ def norm(x, p=2):
 
 
 def _norm1(a, p):
+    if isinstance(a, BlockArray):   # norm(_x, p) of a block that is a BlockArray itself (:834-848, recursively)
+        return norm(a, p)
     v = np.asarray(a).reshape(-1)
     if p == 2:
         return np.linalg.norm(v)
@@ -479,7 +488,7 @@ def dot(x, y):
     if isinstance(x, BlockArray):
         a = x.dtype.type(0)
         for xi, yi in zip(x.arrays, y.arrays):
-            a = a + np.vdot(xi.reshape(-1, order="F"), yi.reshape(-1, order="F"))
+            a = a + (dot(xi, yi) if isinstance(xi, BlockArray) else np.vdot(xi.reshape(-1, order="F"), yi.reshape(-1, order="F")))
         return a
     return np.vdot(np.asarray(x).reshape(-1, order="F"), np.asarray(y).reshape(-1, order="F"))
 
@@ -487,9 +496,9 @@ def dot(x, y):
 def extrema(x):  # :870-878
     if not isinstance(x, BlockArray):
         return np.min(x), np.max(x)
-    mn, mx = np.min(x.arrays[0]), np.max(x.arrays[0])
+    mn, mx = extrema(x.arrays[0])
     for a in x.arrays[1:]:
-        _mn, _mx = np.min(a), np.max(a)
+        _mn, _mx = extrema(a)
         if _mn < mn:
             mn = _mn
         if _mx > mx:
@@ -512,7 +521,7 @@ def to_array(x):
         return np.asarray(x)
     out = np.empty(len(x), dtype=x.dtype)
     for (a, b), blk in zip(x.indices, x.arrays):
-        out[a - 1:b] = blk.reshape(-1, order="F")
+        out[a - 1:b] = to_array(blk).reshape(-1, order="F")   # vec(x.arrays[i]); a nested block flattens the same way
     return out
 
 
@@ -530,7 +539,7 @@ def reshape(x, R):
         blocks = []
         for (a, b), s in zip(R.indices, R.spaces):
             v = flat[a - 1:b]
-            blocks.append(v.reshape(s.n, order="F"))
+            blocks.append(reshape(v, s))   # reshape(view(x, indices), R.spaces[i]): recursive for a nested block space
         return BlockArray(blocks, R.indices)
     if isinstance(x, BlockArray):
         return to_array(x).reshape(R.n, order="F")
@@ -973,7 +982,7 @@ def JetBlock_f(d, m, *, ops, dom, rng, **kw):  # :988-1008
     dtmp = zeros(range_(ops[0, 0])) if nc > 1 else None
     for ir in range(nr):
         _d = getblock(d, ir + 1)
-        if nc > 1 and dtmp.shape != range_(ops[ir, 0]).n:
+        if nc > 1 and dtmp.shape != range_(ops[ir, 0]).size():
             dtmp = zeros(range_(ops[ir, 0]))
         for ic in range(nc):
             _m = getblock(m, ic + 1)
@@ -989,7 +998,7 @@ def JetBlock_df(d, m, *, ops, dom, rng, **kw):  # :1010-1032
     dtmp = zeros(range_(ops[0, 0])) if nc > 1 else None
     for ir in range(nr):
         _d = getblock(d, ir + 1)
-        if nc > 1 and dtmp.shape != range_(ops[ir, 0]).n:
+        if nc > 1 and dtmp.shape != range_(ops[ir, 0]).size():
             dtmp = zeros(range_(ops[ir, 0]))
         for ic in range(nc):
             _m = getblock(m, ic + 1)
@@ -1008,7 +1017,7 @@ def JetBlock_dft(m, d, *, ops, dom, rng, **kw):  # :1034-1057
         _m = getblock(m, ic + 1)
         if nr > 1:
             _m[...] = 0  # the adjoint DOES zero its output
-            if mtmp.shape != domain(ops[0, ic]).n:
+            if mtmp.shape != domain(ops[0, ic]).size():
                 mtmp = zeros(domain(ops[0, ic]))
         for ir in range(nr):
             _d = getblock(d, ir + 1)

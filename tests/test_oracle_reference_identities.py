@@ -638,3 +638,37 @@ def test_blockop_accepts_keyword_arguments(g):  # :697-702
     assert isinstance(x, J.Jop)
     x = J.JopBlock(np.array([[JopBaz(g.random((2, 2)))], [JopBaz(g.random((2, 2)))]], dtype=object), foo=3, bar=4)
     assert isinstance(x, J.Jop) and state(x)["foo"] == 3 and state(x)["bar"] == 4
+
+
+# ---- block operators as blocks of a block operator -------------------------------------------
+def test_nested_block_operator_is_broken_in_the_reference(g):
+    """JetBSpace accepts any JetAbstractSpace as a block (src/Jets.jl:736-751) and reshape / zeros / norm / dot recurse
+    through nested BlockArrays, so a JopBlock whose blocks are JopBlocks can be WRITTEN -- but JetBlock_df! never
+    zeroes its output (`_d .+= mul!(dtmp, ...)`, :1024, quirk Q1) and the outer operator hands every inner one the
+    same `dtmp`, so the inner row sums pile up across block columns: the forward result is wrong and the
+    reference's own dot_product_test fails.  (A single block COLUMN of inner operators is fine: `mul!(_d, op, _m)`
+    overwrites, :1026.)  That is why jets_op_block rejects children with block spaces instead of "supporting" them."""
+    n = 7
+    leaves = {}
+
+    def inner(tag, R, C):
+        leaves[tag] = [[J.JopDiagonal(g.random(n)) if (r + c) % 2 == 0 else J.JopStencil(np.float64, n, "fdiff") for c in range(C)]
+                       for r in range(R)]
+        return J.blockop(leaves[tag])
+    A = J.blockop([[inner((r, c), 3, 2) for c in range(2)] for r in range(2)])
+    assert J.nblocks(A) == (2, 2) and J.size(A) == (42, 28)
+    flat = J.blockop([[leaves[(R, C)][r][c] for C in range(2) for c in range(2)] for R in range(2) for r in range(3)])
+    m = g.random(28)
+    x = J.reshape(m.copy(), J.domain(A))
+    assert isinstance(J.getblock(x, 1), J.BlockArray) and J.to_array(x).tobytes() == m.tobytes()   # nested views of one vector
+    y, yf = J.to_array(A * x), J.to_array(flat * J.reshape(m.copy(), J.domain(flat)))
+    assert not np.allclose(y, yf)                              # the accumulated dtmp
+    lhs, rhs = J.dot_product_test(A, x, A * x)
+    assert not np.isclose(lhs, rhs, rtol=1e-6)                 # the reference's own self-test rejects it
+    d = g.random(42)
+    z = J.to_array(A.T * J.reshape(d.copy(), J.range_(A)))      # the adjoint zeroes `_m` (:1044) and is right
+    assert np.allclose(z, J.to_array(flat.T * J.reshape(d.copy(), J.range_(flat))), rtol=1e-13)
+    col = J.blockop([[inner(("c", r), 2, 1)] for r in range(2)])   # one block column of inner operators: overwrite, correct
+    mc = g.random(n)
+    flatc = J.blockop([[leaves[("c", R)][r][0]] for R in range(2) for r in range(2)])
+    assert np.array_equal(J.to_array(col * mc), J.to_array(flatc * mc))
