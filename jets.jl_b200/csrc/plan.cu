@@ -822,11 +822,12 @@ struct Builder {
     if (!ctx().no_tail_split && !ctx().static_sched && ctx().bundle_bmax <= 0) {
       int64_t heavy_units = 0;
       int big_rows = 0;
+      const int min_rows = ctx().tail_min_rows;
       for (size_t i = 0; i < sim.bundles.size(); ++i)
-        if (!sim.early[i] && sim.bundles[i].nrows >= 16) { heavy_units += sim.bundles[i].npos; big_rows = std::max(big_rows, sim.bundles[i].nrows); }
+        if (!sim.early[i] && sim.bundles[i].nrows >= min_rows) { heavy_units += sim.bundles[i].npos; big_rows = std::max(big_rows, sim.bundles[i].nrows); }
       const int64_t min_units = ctx().tail_min_units > 0 ? ctx().tail_min_units : 8 * (int64_t)grid;
       if (heavy_units >= min_units) {
-        const int sub_rows = std::max(8, (big_rows + 7) / 8);
+        const int sub_rows = std::max(ctx().tail_sub_min, (big_rows + ctx().tail_div - 1) / ctx().tail_div);
         BundleSim sub;
         simulate_bundles(rows, NX, sub_rows, accflag, sub);
         G_tail = safe_lanes(sub, NX, NS);
@@ -838,8 +839,8 @@ struct Builder {
         groups.insert(groups.end(), sub.groups.begin(), sub.groups.end());
         for (size_t i = 0; i < sim.bundles.size(); ++i) {
           BundleRec b = sim.bundles[i];
-          const bool late = (b.gate & ((1 << GF_LO_READY) | (1 << GF_HI_READY))) && b.nrows < 16;
-          if (sim.early[i] || b.nrows < 16) {
+          const bool late = (b.gate & ((1 << GF_LO_READY) | (1 << GF_HI_READY))) && b.nrows < min_rows;
+          if (sim.early[i] || b.nrows < min_rows) {
             (late ? rest_late : mains).push_back(b);
             (late ? e_late : e_mains).push_back(sim.early[i]);
             continue;
