@@ -295,6 +295,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_BUNDLE_NS")) c.bundle_ns = atoi(v);
     if (const char* v = getenv("JETS_B200_BUNDLE_BMAX")) c.bundle_bmax = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_PDL")) c.no_pdl = atoi(v);
+    if (const char* v = getenv("JETS_B200_VEC_PDL")) c.vec_pdl = atoi(v);
     if (const char* v = getenv("JETS_B200_STATIC_SCHED")) c.static_sched = atoi(v);
     if (const char* v = getenv("JETS_B200_GRID")) c.grid_limit = atoi(v);
     if (const char* v = getenv("JETS_B200_DIST_EARLY_CTAS")) c.dist_early_ctas = atoi(v);

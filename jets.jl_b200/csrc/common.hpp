@@ -9,6 +9,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/jets_b200.h"
@@ -72,6 +73,7 @@ struct Context {
   int bundle_ns = 0;
   int bundle_bmax = 0;
   int no_pdl = 0;
+  int vec_pdl = 0;        // JETS_B200_VEC_PDL=1: the vector kernels (reductions, axpby, scalar programs) launch with PDL too (A/B: measured slower)
   // JETS_B200_TRACE=1: every bundle launch writes a per-CTA timeline (globaltimer) into a ring of launch records
   static constexpr int kTraceLaunches = 64, kTraceCtas = 160;
   unsigned long long* trace_buf = nullptr;
@@ -84,7 +86,7 @@ struct Context {
   int no_tail_split = 0;     // JETS_B200_NO_TAIL_SPLIT=1: no fine-grained sub-bundles over the last tile positions (A/B)
   int group_streams = 0;     // JETS_B200_GROUP_STREAMS=n: at most n state streams per term group (tuning)
   int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)
-  uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last bundle launch (the only kernel that triggers its dependents early) writes
+  uintptr_t pdl_out_lo = 0, pdl_out_hi = 0;   // what the last launch that lets its dependents start early (bundle / PDL vector kernel) writes
   int dist_early_ctas = 16;  // JETS_B200_DIST_EARLY_CTAS: CTAs that take the peer-store units of a distributed apply (0: all)
   int grid_limit = 0;    // JETS_B200_GRID=n: launch the fused kernels with at most n CTAs (leaves SMs to concurrent kernels)
   int static_sched = 0;  // JETS_B200_STATIC_SCHED=1: deal units round-robin instead of claiming them dynamically        // JETS_B200_NO_PDL=1: launch without programmatic stream serialization
@@ -542,5 +544,38 @@ void cvec_reduce(int dtype, int kind, const void* x, const void* y, const double
                  int finish, double* dev_out, cudaStream_t s);
 
 inline void count_launch(int n = 1) { ctx().launches += n; }
+
+// Programmatic dependent launch for the small vector kernels (reductions, axpby, scalar programs: the kernels between
+// the applies of a solver iteration) -- OFF by default (JETS_B200_VEC_PDL=1): inside the captured LSQR iteration it
+// measured 1.5-5 % SLOWER than plain kernel nodes (profiles/r02_ab_vec_pdl.log), without PDL griddepcontrol.* are
+// no-ops.  Every such kernel starts with pdl_enter(): griddepcontrol.wait FIRST, then
+// griddepcontrol.launch_dependents -- so the next kernel of the stream is launched (and runs its own prologue up to
+// its wait) while this one does its work, but never while the kernel BEFORE this one is still running: at most two
+// consecutive kernels of the stream overlap, which is what the "operator state before the wait" rule of the bundle
+// kernel (Context::pdl_out_lo/hi = what the previous launch writes) assumes.  `wlo`/`wbytes`: what the launch writes.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_enter() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kern)(KArgs...), unsigned grid, unsigned block, cudaStream_t s, const void* wlo, size_t wbytes,
+                       Args&&... args) {
+  Context& c = ctx();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(block);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (c.no_pdl || !c.vec_pdl) ? 0 : 1;
+  CUDA_TRY(cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...));
+  c.pdl_out_lo = reinterpret_cast<uintptr_t>(wlo);
+  c.pdl_out_hi = c.pdl_out_lo + wbytes;
+}
+#endif
 
 }  // namespace jets

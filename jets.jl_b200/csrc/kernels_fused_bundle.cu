@@ -151,8 +151,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   // Programmatic dependent launch: the next kernel of the stream may start its own prologue while
   // this grid drains; this grid's prologue (barrier init, plan-table fetch: immutable data) ran
   // while the previous grid drained.  Nothing the previous kernel may have written -- or may still
-  // be reading -- is touched before griddepcontrol.wait.
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // be reading -- is touched before griddepcontrol.wait.  The dependents are released AFTER this grid's own
+  // wait (below): the next kernel then never overlaps the kernel BEFORE this one, so "what the previous launch
+  // writes" (Context::pdl_out_lo/hi) is all the host has to know to allow operator-state loads before the wait --
+  // and nothing is lost, its CTAs cannot become resident before this grid's CTAs exit anyway.
   if (tid >= kConsumers) {         // warm L2/L1 with the head of the plan tables (first records of the first bundle)
     const int64_t o = (int64_t)(tid - kConsumers) * 128;
     if (o < P.table_bytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char*>(P.groups) + o));
@@ -160,7 +162,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
   BundleRec B = P.bundles[0];
   __syncthreads();                 // barriers initialised; nothing a previous kernel may write has been touched yet
   if (tid == 0) JETS_TRACE(1, gtime());
-  if (tid < kConsumers) asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid < kConsumers) {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  }
   if constexpr (MODE != 0) {
     if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
       // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)

@@ -93,6 +93,7 @@ struct LinArgs {
 
 template <typename T, int K, bool VEC>
 __global__ void __launch_bounds__(kThreads) lincomb_kernel(T* __restrict__ out, int64_t n, LinArgs a) {
+  pdl_enter();
   using Vec = typename VecOf<T>::type;
   constexpr int V = VEC ? VecOf<T>::V : 1;
   const int64_t nvec = VEC ? n / V : n;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(kThreads) axpby_dev_kernel(T* __restrict__ out
                                                              int bf, const T* y) {
   using Vec = typename VecOf<T>::type;
   constexpr int V = VEC ? VecOf<T>::V : 1;
+  pdl_enter();   // the device scalars are produced by the kernels before this one
   double A = sa ? *sa : ca;
   if (af & JETS_COEF_INV) A = 1.0 / A;
   if (af & JETS_COEF_NEG) A = -A;
@@ -233,6 +235,7 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(kThreads) axpby_pair_kernel(const AxpbyPair P, int64_t n) {
   using Vec = typename VecOf<T>::type;
   constexpr int V = VEC ? VecOf<T>::V : 1;
+  pdl_enter();
   const T a0 = (T)coef_of(P.sa[0], P.ca[0], P.af[0]), b0 = (T)coef_of(P.sb[0], P.cb[0], P.bf[0]);
   const T a1 = (T)coef_of(P.sa[1], P.ca[1], P.af[1]), b1 = (T)coef_of(P.sb[1], P.cb[1], P.bf[1]);
   const int64_t nvec = VEC ? n / V : n;
@@ -321,6 +324,7 @@ __global__ void __launch_bounds__(kThreads) reduce_pass1(const T* __restrict__ x
                                                          double* __restrict__ partial) {
   using Vec = typename VecOf<T>::type;
   constexpr int V = VecOf<T>::V;
+  pdl_enter();
   const int64_t b0 = (int64_t)blockIdx.x * chunk;
   int64_t b1 = b0 + chunk;
   if (b1 > n) b1 = n;
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(kThreads) reduce_pass1(const T* __restrict__ x
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) reduce_pass2(const double* __restrict__ partial, int np,
                                                          int finish, double p, double* __restrict__ out) {
+  pdl_enter();
   double v = r_identity<KIND>();
   for (int i = threadIdx.x; i < np; i += kThreads) v = r_combine<KIND>(v, partial[i]);
   v = block_reduce<KIND>(v);
@@ -401,8 +406,9 @@ void reduce_launch(const void* x, const void* y, int64_t n, double p, int finish
   if (chunk < quantum) chunk = quantum;
   nb = n > 0 ? (n + chunk - 1) / chunk : 1;
   JETS_CHECK((size_t)nb <= c.dev_scratch_elems, JETS_ERR_INVALID, "reduction scratch too small");
-  reduce_pass1<T, KIND><<<(unsigned)nb, kThreads, 0, s>>>((const T*)x, (const T*)y, n, chunk, p, c.dev_scratch);
-  reduce_pass2<KIND><<<1, kThreads, 0, s>>>(c.dev_scratch, (int)nb, finish, p, dev_out);
+  launch_pdl(reduce_pass1<T, KIND>, (unsigned)nb, kThreads, s, c.dev_scratch, (size_t)nb * sizeof(double), (const T*)x, (const T*)y, n, chunk, p,
+             c.dev_scratch);
+  launch_pdl(reduce_pass2<KIND>, 1u, kThreads, s, dev_out, sizeof(double), (const double*)c.dev_scratch, (int)nb, finish, p, dev_out);
   CUDA_TRY(cudaGetLastError());
   count_launch(2);
 }
@@ -439,12 +445,14 @@ __device__ __forceinline__ double scalar_eval(char op, double x, double y) {
 // A short straight-line program of scalar operations in ONE launch (the scalar recurrences of a
 // CG/LSQR iteration); operations see the results of the ones before them.
 __global__ void scalar_prog_kernel(const ScalarProg p) {
+  pdl_enter();
   for (int i = 0; i < p.n; ++i) {
     const double x = p.a[i] ? *p.a[i] : 0.0, y = p.b[i] ? *p.b[i] : 0.0;
     *p.out[i] = scalar_eval(p.op[i], x, y);
   }
 }
 __global__ void scalar_op_kernel(double* out, char op, const double* a, const double* b) {
+  pdl_enter();
   const double x = a ? *a : 0.0, y = b ? *b : 0.0;
   double r;
   switch (op) {
@@ -482,10 +490,10 @@ template <typename T, bool VEC>
 static void lincomb_k(T* out, int64_t n, int k, const LinArgs& a, cudaStream_t s) {
   const unsigned g = grid_for(VEC ? n / VecOf<T>::V + 1 : n, 2);
   switch (k) {
-    case 1: lincomb_kernel<T, 1, VEC><<<g, kThreads, 0, s>>>(out, n, a); break;
-    case 2: lincomb_kernel<T, 2, VEC><<<g, kThreads, 0, s>>>(out, n, a); break;
-    case 3: lincomb_kernel<T, 3, VEC><<<g, kThreads, 0, s>>>(out, n, a); break;
-    default: lincomb_kernel<T, 4, VEC><<<g, kThreads, 0, s>>>(out, n, a); break;
+    case 1: launch_pdl(lincomb_kernel<T, 1, VEC>, g, kThreads, s, out, (size_t)n * sizeof(T), out, n, a); break;
+    case 2: launch_pdl(lincomb_kernel<T, 2, VEC>, g, kThreads, s, out, (size_t)n * sizeof(T), out, n, a); break;
+    case 3: launch_pdl(lincomb_kernel<T, 3, VEC>, g, kThreads, s, out, (size_t)n * sizeof(T), out, n, a); break;
+    default: launch_pdl(lincomb_kernel<T, 4, VEC>, g, kThreads, s, out, (size_t)n * sizeof(T), out, n, a); break;
   }
 }
 
@@ -535,12 +543,12 @@ void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, do
 
 void scalar_prog(const ScalarProg& p, cudaStream_t s) {
   if (p.n <= 0) return;
-  scalar_prog_kernel<<<1, 1, 0, s>>>(p);
+  launch_pdl(scalar_prog_kernel, 1u, 1u, s, nullptr, 0, p);
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }
 void scalar_op(double* out, char op, const double* a, const double* b, cudaStream_t s) {
-  scalar_op_kernel<<<1, 1, 0, s>>>(out, op, a, b);
+  launch_pdl(scalar_op_kernel, 1u, 1u, s, out, sizeof(double), out, op, a, b);
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }
@@ -551,11 +559,11 @@ void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca,
   if (n <= 0) return;
   const bool al = aligned16(out) && aligned16(x) && (!y || aligned16(y));
   if (dtype == JETS_F32) {
-    if (al) axpby_dev_kernel<float, true><<<grid_for(n / 4 + 1, 2), kThreads, 0, s>>>((float*)out, n, sa, ca, af, (const float*)x, sb, cb, bf, (const float*)y);
-    else axpby_dev_kernel<float, false><<<grid_for(n, 2), kThreads, 0, s>>>((float*)out, n, sa, ca, af, (const float*)x, sb, cb, bf, (const float*)y);
+    if (al) launch_pdl(axpby_dev_kernel<float, true>, grid_for(n / 4 + 1, 2), kThreads, s, out, (size_t)n * sizeof(float), (float*)out, n, sa, ca, af, (const float*)x, sb, cb, bf, (const float*)y);
+    else launch_pdl(axpby_dev_kernel<float, false>, grid_for(n, 2), kThreads, s, out, (size_t)n * sizeof(float), (float*)out, n, sa, ca, af, (const float*)x, sb, cb, bf, (const float*)y);
   } else {
-    if (al) axpby_dev_kernel<double, true><<<grid_for(n / 2 + 1, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
-    else axpby_dev_kernel<double, false><<<grid_for(n, 2), kThreads, 0, s>>>((double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
+    if (al) launch_pdl(axpby_dev_kernel<double, true>, grid_for(n / 2 + 1, 2), kThreads, s, out, (size_t)n * sizeof(double), (double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
+    else launch_pdl(axpby_dev_kernel<double, false>, grid_for(n, 2), kThreads, s, out, (size_t)n * sizeof(double), (double*)out, n, sa, ca, af, (const double*)x, sb, cb, bf, (const double*)y);
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();
@@ -572,12 +580,16 @@ void vec_axpby_pair_dev(int dtype, int64_t n, void* const out[2], const double* 
     P.ca[k] = ca[k]; P.cb[k] = cb[k]; P.af[k] = af[k]; P.bf[k] = bf[k];
     al = al && aligned16(out[k]) && aligned16(x[k]) && aligned16(y[k]);
   }
+  // what the launch writes, as one range (for the next bundle launch's "operator state before the wait" rule)
+  const char* wlo = std::min((const char*)out[0], (const char*)out[1]);
+  const size_t whi_off = (size_t)n * dsize(dtype);
+  const char* whi = std::max((const char*)out[0], (const char*)out[1]) + whi_off;
   if (dtype == JETS_F32) {
-    if (al) axpby_pair_kernel<float, true><<<grid_for(n / 4 + 1, 2), kThreads, 0, s>>>(P, n);
-    else axpby_pair_kernel<float, false><<<grid_for(n, 2), kThreads, 0, s>>>(P, n);
+    if (al) launch_pdl(axpby_pair_kernel<float, true>, grid_for(n / 4 + 1, 2), kThreads, s, wlo, whi - wlo, P, n);
+    else launch_pdl(axpby_pair_kernel<float, false>, grid_for(n, 2), kThreads, s, wlo, whi - wlo, P, n);
   } else {
-    if (al) axpby_pair_kernel<double, true><<<grid_for(n / 2 + 1, 2), kThreads, 0, s>>>(P, n);
-    else axpby_pair_kernel<double, false><<<grid_for(n, 2), kThreads, 0, s>>>(P, n);
+    if (al) launch_pdl(axpby_pair_kernel<double, true>, grid_for(n / 2 + 1, 2), kThreads, s, wlo, whi - wlo, P, n);
+    else launch_pdl(axpby_pair_kernel<double, false>, grid_for(n, 2), kThreads, s, wlo, whi - wlo, P, n);
   }
   CUDA_TRY(cudaGetLastError());
   count_launch();
