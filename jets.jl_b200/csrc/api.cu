@@ -147,6 +147,7 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
     plan = build_plan(a, mode, accumulate, io_ok, engine);
     a->plans[key] = plan;
   }
+  if (ctx().capturing) ctx().capture_keep.push_back(plan);
   if (coef) {
     check_real(a->dtype, "jets_apply_axpby");
     // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...
@@ -288,6 +289,7 @@ int jets_init(int device) {
     CUDA_TRY(cudaMallocHost(&c.host_scratch, 64 * sizeof(double)));
     c.dev_scratch_elems = (size_t)c.sm_count * 8 + 64;
     CUDA_TRY(cudaMalloc(&c.dev_scratch, (c.dev_scratch_elems + 64) * sizeof(double)));
+    CUDA_TRY(cudaMemset(c.dev_scratch, 0, (c.dev_scratch_elems + 64) * sizeof(double)));   // result slots; slot 60 = the reductions' block ticket
     if (const char* v = getenv("JETS_B200_FAST_VARIANT")) c.fast_variant = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_FAST")) c.no_fast = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_BUNDLE")) c.no_bundle = atoi(v);
@@ -728,6 +730,7 @@ int jets_graph_begin(void) {
     require_ready();
     CUDA_TRY(cudaStreamBeginCapture(ctx().stream, cudaStreamCaptureModeThreadLocal));
     ctx().capturing = true;
+    ctx().capture_keep.clear();
   });
 }
 int jets_graph_end(void** exec_out) {
@@ -739,6 +742,8 @@ int jets_graph_end(void** exec_out) {
     cudaGraphExec_t e = nullptr;
     CUDA_TRY(cudaGraphInstantiate(&e, g, 0));
     cudaGraphDestroy(g);
+    ctx().graph_keep[e] = std::move(ctx().capture_keep);
+    ctx().capture_keep.clear();
     *exec_out = e;
   });
 }
@@ -746,7 +751,12 @@ int jets_graph_launch(void* e) {
   return guard([&] { require_ready(); CUDA_TRY(cudaGraphLaunch(reinterpret_cast<cudaGraphExec_t>(e), ctx().stream)); });
 }
 int jets_graph_destroy(void* e) {
-  return guard([&] { if (e) cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(e)); });
+  return guard([&] {
+    if (!e) return;
+    cudaStreamSynchronize(ctx().stream);          // replays in flight still read the pinned plans
+    cudaGraphExecDestroy(reinterpret_cast<cudaGraphExec_t>(e));
+    ctx().graph_keep.erase(e);
+  });
 }
 
 // ------------------------------------------------------------------ leaves ---------------

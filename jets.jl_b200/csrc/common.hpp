@@ -94,6 +94,10 @@ struct Context {
   double* dev_scratch = nullptr;   // device partials for reductions
   size_t dev_scratch_elems = 0;
   bool capturing = false;
+  // Plans launched while a CUDA graph is being captured: the graph holds raw pointers into their tables and
+  // temporaries, so the executable graph keeps them alive (a later point! may replace the operator's cached plan).
+  std::vector<std::shared_ptr<void>> capture_keep;
+  std::map<void*, std::vector<std::shared_ptr<void>>> graph_keep;
 };
 Context& ctx();
 void require_ready();

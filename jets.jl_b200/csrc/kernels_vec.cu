@@ -3,6 +3,7 @@
 // BlockArray broadcast is a single streaming pass; reductions are two-pass, fixed-order, f64
 // accumulated, warp-shuffle trees -- no atomics, bit-reproducible run to run.
 #include <algorithm>
+#include <cstdlib>
 #include "common.hpp"
 #include "cplx.cuh"
 
@@ -317,11 +318,15 @@ __device__ __forceinline__ double block_reduce(double v) {
   return r;  // valid in thread 0
 }
 
-// pass 1: CTA b reduces the contiguous chunk [b*chunk, (b+1)*chunk) -> partial[b]
+// ONE launch: CTA b reduces the contiguous chunk [b*chunk, (b+1)*chunk) -> partial[b]; the CTA that draws the last
+// ticket then combines the partials in index order (thread t takes partial[t], partial[t + 256], ...: the order does not
+// depend on which CTA finishes last, so the result is deterministic) and applies `finish`: 0 none, 1 sqrt, 2 ^(1/p).
+// The ticket wraps back to 0 by itself (atomicInc).  Reductions share the context's partial buffer: one at a time.
 template <typename T, int KIND>
 __global__ void __launch_bounds__(kThreads) reduce_pass1(const T* __restrict__ x, const T* __restrict__ y,
                                                          int64_t n, int64_t chunk, double p,
-                                                         double* __restrict__ partial) {
+                                                         double* partial, unsigned int* ticket, int finish,
+                                                         double* __restrict__ out) {
   using Vec = typename VecOf<T>::type;
   constexpr int V = VecOf<T>::V;
   pdl_enter();
@@ -373,14 +378,30 @@ __global__ void __launch_bounds__(kThreads) reduce_pass1(const T* __restrict__ x
 #pragma unroll
   for (int u = 1; u < kUnroll; ++u) v = r_combine<KIND>(v, acc[u]);
   v = block_reduce<KIND>(v);
-  if (threadIdx.x == 0) partial[blockIdx.x] = v;
+  __shared__ int is_last;
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = v;
+    __threadfence();                                   // the partial is visible before the ticket is drawn
+    is_last = ticket ? atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1 : 0;   // no ticket: a second launch finishes (A/B)
+  }
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  const int np = (int)gridDim.x;
+  double r = r_identity<KIND>();
+  for (int i = threadIdx.x; i < np; i += kThreads) r = r_combine<KIND>(r, __ldcg(partial + i));
+  r = block_reduce<KIND>(r);
+  if (threadIdx.x == 0) {
+    if (finish == 1) r = sqrt(r);
+    else if (finish == 2) r = pow(r, 1.0 / p);
+    out[0] = r;
+  }
 }
 
-// pass 2: one CTA combines the partials in index order; finish: 0 none, 1 sqrt, 2 ^(1/p)
+// the finish as a launch of its own (JETS_B200_REDUCE_TWO_PASS=1: the A/B baseline of the single-launch reduction)
 template <int KIND>
 __global__ void __launch_bounds__(kThreads) reduce_pass2(const double* __restrict__ partial, int np,
                                                          int finish, double p, double* __restrict__ out) {
-  pdl_enter();
   double v = r_identity<KIND>();
   for (int i = threadIdx.x; i < np; i += kThreads) v = r_combine<KIND>(v, partial[i]);
   v = block_reduce<KIND>(v);
@@ -406,11 +427,13 @@ void reduce_launch(const void* x, const void* y, int64_t n, double p, int finish
   if (chunk < quantum) chunk = quantum;
   nb = n > 0 ? (n + chunk - 1) / chunk : 1;
   JETS_CHECK((size_t)nb <= c.dev_scratch_elems, JETS_ERR_INVALID, "reduction scratch too small");
-  launch_pdl(reduce_pass1<T, KIND>, (unsigned)nb, kThreads, s, c.dev_scratch, (size_t)nb * sizeof(double), (const T*)x, (const T*)y, n, chunk, p,
-             c.dev_scratch);
-  launch_pdl(reduce_pass2<KIND>, 1u, kThreads, s, dev_out, sizeof(double), (const double*)c.dev_scratch, (int)nb, finish, p, dev_out);
+  static const bool two_pass = getenv("JETS_B200_REDUCE_TWO_PASS") && atoi(getenv("JETS_B200_REDUCE_TWO_PASS"));
+  unsigned int* ticket = two_pass ? nullptr : reinterpret_cast<unsigned int*>(c.dev_scratch + c.dev_scratch_elems + 60);
+  launch_pdl(reduce_pass1<T, KIND>, (unsigned)nb, kThreads, s, dev_out, sizeof(double), (const T*)x, (const T*)y, n, chunk, p,
+             c.dev_scratch, ticket, finish, dev_out);
+  if (two_pass) reduce_pass2<KIND><<<1, kThreads, 0, s>>>(c.dev_scratch, (int)nb, finish, p, dev_out);
   CUDA_TRY(cudaGetLastError());
-  count_launch(2);
+  count_launch(two_pass ? 2 : 1);
 }
 
 template <typename T>
