@@ -144,10 +144,16 @@ static void apply_impl(jets_op a, int mode, jets_buf out, jets_buf in, int accum
   auto it = a->plans.find(key);
   if (it != a->plans.end() && it->second->valid()) plan = it->second;
   else {
+    for (auto p = a->plans.begin(); p != a->plans.end();)      // stale plans hold the old linearization points: drop them now
+      p = p->second->valid() ? std::next(p) : a->plans.erase(p);
     plan = build_plan(a, mode, accumulate, io_ok, engine);
     a->plans[key] = plan;
   }
-  if (ctx().capturing) ctx().capture_keep.push_back(plan);
+  if (ctx().capturing) {        // the graph replays raw pointers into the plan's tables and the operator's state
+    ctx().capture_keep.push_back(plan);
+    a->refs++;
+    ctx().capture_keep.push_back(std::shared_ptr<void>(a, [](void* p) { op_release(reinterpret_cast<jets_op>(p)); }));
+  }
   if (coef) {
     check_real(a->dtype, "jets_apply_axpby");
     // out = cA*(A in) + cO*out: in the kernel's store epilogue when the apply is one bundle launch ...

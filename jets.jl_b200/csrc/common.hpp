@@ -437,6 +437,7 @@ struct Plan {
   // linearization point (every linear operator) are never invalidated by anybody's point!.
   static constexpr size_t kMaxTrackedPoints = 64;
   std::vector<std::pair<jets_op, const void*>> points;
+  std::vector<jets_buf> point_bufs;   // those buffers, retained: a plan pinned by a captured CUDA graph outlives a later point!
   bool uses_point = false;
   uint64_t version = 0;
   bool valid() const;
@@ -524,7 +525,13 @@ void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, do
                 double* dev_out, cudaStream_t s);
 void scalar_op(double* out, char op, const double* a, const double* b, cudaStream_t s);
 constexpr int kMaxScalarProg = 16;
-struct ScalarProg { double* out[kMaxScalarProg]; const double* a[kMaxScalarProg]; const double* b[kMaxScalarProg]; char op[kMaxScalarProg]; int n; };
+struct ScalarProg {
+  double* out[kMaxScalarProg]; const double* a[kMaxScalarProg]; const double* b[kMaxScalarProg]; char op[kMaxScalarProg]; int n;
+  // filled in by scalar_prog(): which earlier step produces an operand (-1: read it from memory) and whether a step is
+  // the last one that writes its scalar -- so the kernel loads every memory operand at once, evaluates the steps from
+  // registers / shared memory and stores once (11 dependent global round trips took 6 us inside the LSQR iteration)
+  int8_t asrc[kMaxScalarProg], bsrc[kMaxScalarProg]; uint8_t store[kMaxScalarProg];
+};
 void scalar_prog(const ScalarProg& p, cudaStream_t s);
 void vec_axpby_dev(int dtype, void* out, int64_t n, const double* sa, double ca, int af,
                    const void* x, const double* sb, double cb, int bf, const void* y,

@@ -118,8 +118,16 @@ __device__ __forceinline__ unsigned long long gtime() {
 // MODE 0 is the plain kernel; MODE 1 adds -- at compile time, so that the plain instantiation pays nothing for them
 // (measured on one box: the same features as run-time branches cost the plain config-5 launch 4 %, config 1 10 %) --
 // the cross-rank gating of the distributed apply (flag waits, flush markers, signals, alternative base pointers,
-// exit wait) and the launch timeline.
-#define JETS_TRACE(slot, val) do { if constexpr (MODE != 0) { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } } while (0)
+// exit wait) and the launch timeline.  MODE 2 is the plain kernel with the axpby store epilogue (out = cA*acc + cO*out,
+// jets_apply_axpby): the producer prefetches the old output tile into L2 when it issues the row tile's last group and
+// the consumers load it BEFORE they evaluate that group's terms -- read right before the store it is a dependent DRAM
+// load per row tile (ncu on config 4's fused iteration: 64 us per launch for 268 MB, 0.64 of the copy peak).  In
+// MODE 1 the epilogue stays a run-time switch; MODE 0 does not know it.
+#define JETS_AXPBY (MODE == 2 || (MODE == 1 && P.axpby != 0))
+#define JETS_TRACE(slot, val) do { if constexpr (MODE == 1) { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } } while (0)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
                    "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
@@ -166,7 +174,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
-  if constexpr (MODE != 0) {
+  if constexpr (MODE == 1) {
     if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
       // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
 #pragma unroll
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
       BMeta& M = meta[my];
       char* obase = P.out;
-      if constexpr (MODE != 0) {
+      if constexpr (MODE == 1) {
         const int oalt = (gflags >> BG_OUT_ALT_SHIFT) & 3;
         obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
       }
@@ -266,6 +274,9 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
                      ((gflags & BG_ROW_FIRST) ? F_FIRST : 0) | ((gflags & BG_ROW_LAST) ? F_LAST : 0) |
                      ((gflags & BG_ACC) ? F_ACC : 0);
       *reinterpret_cast<int4*>(&M.nvalid) = make_int4(nvalid, fl, nterms, xrelease);
+      if constexpr (MODE == 2) {
+        if ((fl & F_LAST) && nvalid * (int)sizeof(T) >= 16) bulk_prefetch_l2(M.out_tile, (uint32_t)(nvalid * (int)sizeof(T)) & ~15u);
+      }
       *reinterpret_cast<uint4*>(&M.terms[0]) = *reinterpret_cast<uint4*>(&tt[0]);
       *reinterpret_cast<uint4*>(&M.terms[2]) = *reinterpret_cast<uint4*>(&tt[2]);
       if (total == 0) {
@@ -278,7 +289,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         if (t < nterms && (tt[t].xflags & XF_LOAD)) {
           const int64_t px = __ldg(&rec->xptr[t]);
           const char* ibase = P.in;
-          if constexpr (MODE != 0) {
+          if constexpr (MODE == 1) {
             const int ialt = (xrel_mask >> (kXAltShift + 2 * t)) & 3;
             ibase = ialt == 0 ? P.in : ialt == 1 ? P.gate.in_alt[0] : ialt == 2 ? P.gate.in_alt[1] : P.gate.in_alt[2];
           }
@@ -388,7 +399,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         open_claim();
       }
       locate_unit();
-      if constexpr (MODE != 0) {
+      if constexpr (MODE == 1) {
       if ((B.gate >> 4) != cur_sig) {
         // leaving a bundle whose units feed cross-rank signals: tell the consumers how many this CTA completed
         // (BEFORE any flag wait below -- a neighbour may be waiting for exactly this signal)
@@ -482,7 +493,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     if (lane == 0) JETS_TRACE(5, gtime());
     flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
-    if constexpr (MODE != 0)
+    if constexpr (MODE == 1)
     if (P.gate.exit_wait && lane == 0) {
       // the last CTA to run out of work keeps the grid alive until the neighbours have finished reading this
       // rank's input (their flag words): everything that follows on the stream may then overwrite it
@@ -513,7 +524,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     int slot = 0;
     uint32_t par = 0;
     T cA = T(1), cO = T(0);
-    if (P.axpby) {   // device scalars of the caller (read after griddepcontrol.wait: a previous kernel may produce them)
+    if (JETS_AXPBY) {   // device scalars of the caller (read after griddepcontrol.wait: a previous kernel may produce them)
       double a = P.coef.a_ptr ? *P.coef.a_ptr : P.coef.a_const;
       if (P.coef.a_flags & JETS_COEF_INV) a = 1.0 / a;
       if (P.coef.a_flags & JETS_COEF_NEG) a = -a;
@@ -525,13 +536,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
     const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
     bool tr_first = false, tr_store = false;
-    if constexpr (MODE != 0) tr_first = tr_store = P.trace != nullptr && tid == 0;
+    if constexpr (MODE == 1) tr_first = tr_store = P.trace != nullptr && tid == 0;
     while (true) {
       mbar_wait(sfull0 + 8 * slot, par);
-      if constexpr (MODE != 0) { if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; } }
+      if constexpr (MODE == 1) { if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; } }
       const BMeta& M = meta[slot];
       const int flags = M.flags;
-      if constexpr (MODE == 0) {
+      if constexpr (MODE != 1) {
         if (flags & F_END) break;
       } else if (flags & (F_END | F_FLUSH)) {
         const int smask = (flags >> BG_SIG_SHIFT) & 15;
@@ -627,6 +638,16 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       };
+      Vec oldv[VPT];
+      if constexpr (MODE == 2) {       // the old output tile, in flight while the terms are evaluated
+        if (flags & F_LAST) {
+#pragma unroll
+          for (int i = 0; i < VPT; ++i) {
+            const int e0 = (i * kConsumers + tid) * V;
+            if (e0 + V <= nvalid) oldv[i] = *reinterpret_cast<const Vec*>(out_tile + e0);
+          }
+        }
+      }
       // interior tiles (neither block end inside the tile) run the mask-free instantiation
       if (flags & (F_BLK0 | F_BLKEND)) run_terms(std::true_type{});
       else run_terms(std::false_type{});
@@ -647,8 +668,10 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           if (e0 + V <= nvalid) {
             Vec v;
             T* vs = reinterpret_cast<T*>(&v);
-            if (P.axpby) {
-              const Vec old = *reinterpret_cast<const Vec*>(out_tile + e0);
+            if (JETS_AXPBY) {
+              Vec old;
+              if constexpr (MODE == 2) old = oldv[i];
+              else old = *reinterpret_cast<const Vec*>(out_tile + e0);
               const T* os = reinterpret_cast<const T*>(&old);
 #pragma unroll
               for (int j = 0; j < V; ++j) vs[j] = cA * acc[i][j] + cO * os[j];
@@ -660,11 +683,11 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           } else {
 #pragma unroll
             for (int j = 0; j < V; ++j)
-              if (e0 + j < nvalid) out_tile[e0 + j] = P.axpby ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
+              if (e0 + j < nvalid) out_tile[e0 + j] = JETS_AXPBY ? cA * acc[i][j] + cO * out_tile[e0 + j] : acc[i][j];
           }
         }
       }
-      if constexpr (MODE != 0) { if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; } }
+      if constexpr (MODE == 1) { if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; } }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
@@ -703,6 +726,13 @@ void launch_variant(const DevFused& f, BundleParams& P, cudaStream_t s) {
 
 template <typename T>
 void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s, bool extras) {
+  if (P.axpby && !extras) {
+    switch (f.variant) {
+      case 2: launch_variant<T, 16, 2, 2>(f, P, s); return;
+      case 0: launch_variant<T, 16, 1, 2>(f, P, s); return;
+      default: JETS_FAIL(JETS_ERR_UNSUPPORTED, "the axpby store epilogue is built for tile shapes 0 and 2 only (got %d)", f.variant);
+    }
+  }
   if (extras) {
     // gated (distributed) launches and traced ones: the tile shapes the planner picks for long rows and for short ones
     switch (f.variant) {

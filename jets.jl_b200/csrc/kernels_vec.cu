@@ -467,12 +467,26 @@ __device__ __forceinline__ double scalar_eval(char op, double x, double y) {
 }
 // A short straight-line program of scalar operations in ONE launch (the scalar recurrences of a
 // CG/LSQR iteration); operations see the results of the ones before them.
-__global__ void scalar_prog_kernel(const ScalarProg p) {
+__global__ void __launch_bounds__(32) scalar_prog_kernel(const ScalarProg p) {
+  __shared__ double av[kMaxScalarProg], bv[kMaxScalarProg], val[kMaxScalarProg];
   pdl_enter();
-  for (int i = 0; i < p.n; ++i) {
-    const double x = p.a[i] ? *p.a[i] : 0.0, y = p.b[i] ? *p.b[i] : 0.0;
-    *p.out[i] = scalar_eval(p.op[i], x, y);
+  const int t = threadIdx.x;
+  if (t < kMaxScalarProg) {                 // lanes 0..15 fetch the first operands, lanes 16..31 the second ones: one round trip
+    if (t < p.n) av[t] = (p.asrc[t] < 0 && p.a[t]) ? *p.a[t] : 0.0;
+  } else {
+    const int k = t - kMaxScalarProg;
+    if (k < p.n) bv[k] = (p.bsrc[k] < 0 && p.b[k]) ? *p.b[k] : 0.0;
   }
+  __syncwarp();
+  if (t == 0) {
+    for (int i = 0; i < p.n; ++i) {
+      const double x = p.asrc[i] < 0 ? av[i] : val[p.asrc[i]];
+      const double y = p.bsrc[i] < 0 ? bv[i] : val[p.bsrc[i]];
+      val[i] = scalar_eval(p.op[i], x, y);
+    }
+  }
+  __syncwarp();
+  if (t < p.n && p.store[t]) *p.out[t] = val[t];
 }
 __global__ void scalar_op_kernel(double* out, char op, const double* a, const double* b) {
   pdl_enter();
@@ -564,9 +578,20 @@ void vec_reduce(int dtype, int kind, const void* x, const void* y, int64_t n, do
   else reduce_dispatch<double>(kind, x, y, n, p, dev_out, s);
 }
 
-void scalar_prog(const ScalarProg& p, cudaStream_t s) {
-  if (p.n <= 0) return;
-  launch_pdl(scalar_prog_kernel, 1u, 1u, s, nullptr, 0, p);
+void scalar_prog(const ScalarProg& prog, cudaStream_t s) {
+  if (prog.n <= 0) return;
+  ScalarProg p = prog;
+  for (int i = 0; i < p.n; ++i) {
+    p.asrc[i] = p.bsrc[i] = -1;
+    p.store[i] = 1;
+    for (int j = 0; j < i; ++j) {           // the latest earlier step that writes the operand
+      if (p.a[i] && p.out[j] == p.a[i]) p.asrc[i] = (int8_t)j;
+      if (p.b[i] && p.out[j] == p.b[i]) p.bsrc[i] = (int8_t)j;
+    }
+    for (int j = i + 1; j < p.n; ++j)
+      if (p.out[j] == p.out[i]) p.store[i] = 0;     // overwritten later in the same program
+  }
+  launch_pdl(scalar_prog_kernel, 1u, 32u, s, nullptr, 0, p);
   CUDA_TRY(cudaGetLastError());
   count_launch();
 }

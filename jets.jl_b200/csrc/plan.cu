@@ -1417,6 +1417,7 @@ struct Builder {
 Plan::~Plan() {
   for (void* p : tmps) cudaFree(p);
   for (void* p : blobs) cudaFree(p);
+  for (jets_buf b : point_bufs) jets_buf_destroy(b);
 }
 bool Plan::valid() const {
   if (!uses_point) return true;
@@ -1438,6 +1439,7 @@ struct PointScope {
       std::sort(pts.begin(), pts.end());
       pts.erase(std::unique(pts.begin(), pts.end()), pts.end());
       p.points = std::move(pts);
+      for (auto& pr : p.points) { pr.first->mo->refs++; p.point_bufs.push_back(pr.first->mo); }
     } else {
       p.points.assign(Plan::kMaxTrackedPoints + 1, {nullptr, nullptr});   // marker: too many to track -> epoch
     }
@@ -1483,7 +1485,7 @@ bool run_plan_axpby(Plan& p, int dtype, char* in, char* out, const ApplyCoef& co
   if (p.steps.size() != 1) return false;
   Step& st = p.steps[0];
   if (st.kind != ST_FUSED || !st.fused.bundle || st.acc != ACC_SET || st.src.which != 0 || st.dst.which != 1 ||
-      !st.fused.covers_out)
+      !st.fused.covers_out || (st.fused.variant != 0 && st.fused.variant != 2))   // the epilogue's tile shapes
     return false;
   launch_fused_bundle(st.fused, dtype, in, out, ctx().stream, &coef);
   return true;

@@ -17,7 +17,11 @@ Sd = B.blockop([[B.JopStencil(T8, n4, "lap") if i == j else B.JopZeroBlock(sp, s
 A4 = Bd - 0.5 * Sd
 rhs4 = B.rand(B.range_(A4), seed=4002)
 tag = " ".join(f"{k}={v}" for k, v in os.environ.items() if k.startswith("JETS_B200_")) or "default"
+only = os.environ.get("AB_LSQR_ONLY", "unfused,fused").split(",")
+iters = int(os.environ.get("AB_LSQR_ITERS", iters))
 for name, cls in (("unfused", B.solvers.LsqrGraph), ("fused", B.solvers.LsqrGraphFused)):
+    if name not in only:
+        continue
     G = cls(A4, rhs4)
     G.run(5)
     torch.cuda.synchronize()

@@ -869,3 +869,38 @@ def test_copy_gives_an_independent_linearization_point(D):  # copy(A, false) src
     assert np.array_equal((G * B.to_device(m1)).to_host(), (F * B.to_device(m1)).to_host())
     At = B.copy(B.JopDiagonal(w).T)
     assert np.array_equal((At * B.to_device(dm)).to_host(), w * dm)
+
+
+def test_captured_graph_keeps_its_plans_alive(D):
+    """A CUDA graph captured through jets_graph_begin/_end holds raw pointers into the plan tables of the applies it
+    recorded.  point! replaces the operator's cached plan; the executable graph pins the one it captured, so a replay
+    still computes -- with the linearization point it was captured with (the caller keeps that vector alive)."""
+    import ctypes as C
+    B = D.B
+    g = np.random.default_rng(91)
+    n = 20_000
+    w, mo1, mo2, m = (g.random(n) for _ in range(4))
+    F = B.JopDiagonal(w) @ B.JopPointwise(np.float64, n, "square")
+    mo1_d, mo2_d = B.to_device(mo1), B.to_device(mo2)
+    A = B.jacobian_(F, mo1_d)
+    md, dd = B.to_device(m), B.zeros(B.range_(A))
+    B.mul_(dd, A, md)                                   # builds the plan outside the capture
+    ref1 = dd.to_host().copy()
+    assert np.array_equal(ref1, w * (2 * mo1 * m))
+    B.check(B.lib.jets_graph_begin())
+    try:
+        B.mul_(dd, A, md)
+    finally:
+        gh = C.c_void_p()
+        B.check(B.lib.jets_graph_end(C.byref(gh)))
+    try:
+        B.jacobian_(F, mo2_d)                           # new point on the SHARED jet (:364-366): A's cached plan is stale ...
+        B.mul_(dd, A, md)                               # ... and is rebuilt here (the old one is dropped from the cache)
+        assert np.array_equal(dd.to_host(), w * (2 * mo2 * m))
+        dd.fill_(0.0)
+        for _ in range(3):
+            B.check(B.lib.jets_graph_launch(gh))        # ... while the graph replays the plan it captured
+        B.sync()
+        assert np.array_equal(dd.to_host(), ref1)
+    finally:
+        B.check(B.lib.jets_graph_destroy(gh))
