@@ -509,6 +509,21 @@ def run_ours(args):
     del S, op
     import gc
     gc.collect()
+    # Calibration on THIS box: the boxes of the pool differ by several per cent for one binary (clocks, HBM stacks), and
+    # `peak` was measured by the driver on another one -- so the line also carries what a plain device-to-device copy
+    # of 4 GB (8 GB of traffic per copy, far beyond L2) achieves here, right now, timed the same way.
+    try:
+        n_cal = 1 << 30
+        ca, cb = torch.empty(n_cal, dtype=torch.float32, device="cuda"), torch.empty(n_cal, dtype=torch.float32, device="cuda")
+        ca.uniform_()
+        ms_cal = time_steps(torch, stream, lambda: cb.copy_(ca), 10, 3)
+        same_box = 2 * n_cal * 4 / (ms_cal * 1e-3) / 1e9
+        line["roofline"]["same_box_copy_gbps"] = round(same_box, 1)
+        line["roofline"]["frac_of_same_box_copy"] = round(achieved / same_box, 4)
+        del ca, cb
+    except Exception as ex:  # a calibration must never cost the bench line
+        line["roofline"]["same_box_copy_gbps"] = None
+        line["roofline"]["same_box_copy_error"] = str(ex)
     if world > 1:
         try:
             line["dense_structure"] = dense_structure_workload(B, torch, dist, stream, rank, world, peak, barrier)

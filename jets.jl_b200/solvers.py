@@ -170,16 +170,9 @@ class LsqrGraph:
             _axpby(v, None, 1.0, 0, tmp_v, beta, 0.0, L.COEF_NEG, v)         # v = A' u - beta v
             check(lib.jets_norm_dev(v._h, 2.0, alpha.h))
             _axpby(v, alpha, 0.0, L.COEF_INV, v)
-            _sop(rho, "h", rhobar, beta)
-            _sop(c, "/", rhobar, rho)
-            _sop(s, "/", beta, rho)
-            _sop(theta, "*", s, alpha)
-            _sop(t1, "*", c, alpha)
-            _sop(rhobar, "n", t1)
-            _sop(phi, "*", c, phibar)
-            _sop(phibar, "*", s, phibar)
-            _sop(t1, "/", phi, rho)
-            _sop(t2, "/", theta, rho)
+            _sprog([(rho, "h", rhobar, beta), (c, "/", rhobar, rho), (s, "/", beta, rho), (theta, "*", s, alpha),
+                    (t1, "*", c, alpha), (rhobar, "n", t1, None), (phi, "*", c, phibar), (phibar, "*", s, phibar),
+                    (t1, "/", phi, rho), (t2, "/", theta, rho)])      # the scalar recurrences: one launch
             _axpby(x, None, 1.0, 0, x, t1, 0.0, 0, w)                        # x += (phi/rho) w
             _axpby(w, None, 1.0, 0, v, t2, 0.0, L.COEF_NEG, w)               # w = v - (theta/rho) w
 
