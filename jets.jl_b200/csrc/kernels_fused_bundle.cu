@@ -122,9 +122,10 @@ __device__ __forceinline__ unsigned long long gtime() {
 // jets_apply_axpby): the producer prefetches the old output tile into L2 when it issues the row tile's last group and
 // the consumers load it BEFORE they evaluate that group's terms -- read right before the store it is a dependent DRAM
 // load per row tile (ncu on config 4's fused iteration: 64 us per launch for 268 MB, 0.64 of the copy peak).  In
-// MODE 1 the epilogue stays a run-time switch; MODE 0 does not know it.
-#define JETS_AXPBY (MODE == 2 || (MODE == 1 && P.axpby != 0))
-#define JETS_TRACE(slot, val) do { if constexpr (MODE == 1) { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } } while (0)
+// the gated modes the epilogue stays a run-time switch; MODE 0 does not know it.  MODE 3 = MODE 1 + the launch timeline
+// (the per-slot "first tile / first store traced yet?" checks were 4.5 % of the consumers' stall samples in the gated launch).
+#define JETS_AXPBY (MODE == 2 || ((MODE & 1) != 0 && P.axpby != 0))
+#define JETS_TRACE(slot, val) do { if constexpr (MODE == 3) { if (P.trace) P.trace[(size_t)blockIdx.x * 8 + (slot)] = (val); } } while (0)
 __device__ __forceinline__ void bulk_prefetch_l2(const void* src, uint32_t bytes) {
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     asm volatile("griddepcontrol.wait;" ::: "memory");
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   }
-  if constexpr (MODE == 1) {
+  if constexpr ((MODE & 1) != 0) {
     if (P.gate.flags != nullptr && blockIdx.x == 0 && tid == 0) {
       // signals this launch owns but no unit feeds (e.g. "halo consumed" when no row reads that halo)
 #pragma unroll
@@ -264,7 +265,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
       }
       BMeta& M = meta[my];
       char* obase = P.out;
-      if constexpr (MODE == 1) {
+      if constexpr ((MODE & 1) != 0) {
         const int oalt = (gflags >> BG_OUT_ALT_SHIFT) & 3;
         obase = oalt == 0 ? P.out : oalt == 1 ? P.gate.out_alt[0] : oalt == 2 ? P.gate.out_alt[1] : P.gate.out_alt[2];
       }
@@ -289,7 +290,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         if (t < nterms && (tt[t].xflags & XF_LOAD)) {
           const int64_t px = __ldg(&rec->xptr[t]);
           const char* ibase = P.in;
-          if constexpr (MODE == 1) {
+          if constexpr ((MODE & 1) != 0) {
             const int ialt = (xrel_mask >> (kXAltShift + 2 * t)) & 3;
             ibase = ialt == 0 ? P.in : ialt == 1 ? P.gate.in_alt[0] : ialt == 2 ? P.gate.in_alt[1] : P.gate.in_alt[2];
           }
@@ -399,7 +400,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
         open_claim();
       }
       locate_unit();
-      if constexpr (MODE == 1) {
+      if constexpr ((MODE & 1) != 0) {
       if ((B.gate >> 4) != cur_sig) {
         // leaving a bundle whose units feed cross-rank signals: tell the consumers how many this CTA completed
         // (BEFORE any flag wait below -- a neighbour may be waiting for exactly this signal)
@@ -493,7 +494,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     }
     if (lane == 0) JETS_TRACE(5, gtime());
     flush_marker(F_END);   // end-of-work sentinel (reports the last bundle's units as well)
-    if constexpr (MODE == 1)
+    if constexpr ((MODE & 1) != 0)
     if (P.gate.exit_wait && lane == 0) {
       // the last CTA to run out of work keeps the grid alive until the neighbours have finished reading this
       // rank's input (their flag words): everything that follows on the stream may then overwrite it
@@ -536,13 +537,13 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
     const unsigned char* xr_p = smem + kHdrAligned + kPad + tid * 16;                   // vector 0 of x buffer 0
     const unsigned char* sl_p = xr_p + (size_t)NX * kBufBytes;                          // vector 0, stream 0, slot 0
     bool tr_first = false, tr_store = false;
-    if constexpr (MODE == 1) tr_first = tr_store = P.trace != nullptr && tid == 0;
+    if constexpr (MODE == 3) tr_first = tr_store = P.trace != nullptr && tid == 0;
     while (true) {
       mbar_wait(sfull0 + 8 * slot, par);
-      if constexpr (MODE == 1) { if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; } }
+      if constexpr (MODE == 3) { if (tr_first) { JETS_TRACE(3, gtime()); tr_first = false; } }
       const BMeta& M = meta[slot];
       const int flags = M.flags;
-      if constexpr (MODE != 1) {
+      if constexpr ((MODE & 1) == 0) {
         if (flags & F_END) break;
       } else if (flags & (F_END | F_FLUSH)) {
         const int smask = (flags >> BG_SIG_SHIFT) & 15;
@@ -687,7 +688,7 @@ __global__ void __launch_bounds__(CW * 32 + 32, 1) jets_fused_bundle_kernel(cons
           }
         }
       }
-      if constexpr (MODE == 1) { if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; } }
+      if constexpr (MODE == 3) { if (tr_store && (flags & F_LAST)) { JETS_TRACE(4, gtime()); tr_store = false; } }
       sl_p += slot_bytes;
       if (++slot == NS) { slot = 0; par ^= 1; sl_p -= (size_t)NS * slot_bytes; }
     }
@@ -733,8 +734,15 @@ void launch_dtype(const DevFused& f, BundleParams& P, cudaStream_t s, bool extra
       default: JETS_FAIL(JETS_ERR_UNSUPPORTED, "the axpby store epilogue is built for tile shapes 0 and 2 only (got %d)", f.variant);
     }
   }
+  if (extras && P.trace) {
+    switch (f.variant) {
+      case 2: launch_variant<T, 16, 2, 3>(f, P, s); return;
+      case 0: launch_variant<T, 16, 1, 3>(f, P, s); return;
+      default: JETS_FAIL(JETS_ERR_UNSUPPORTED, "the traced bundle kernel is built for tile shapes 0 and 2 only (got %d)", f.variant);
+    }
+  }
   if (extras) {
-    // gated (distributed) launches and traced ones: the tile shapes the planner picks for long rows and for short ones
+    // gated (distributed) launches: the tile shapes the planner picks for long rows and for short ones
     switch (f.variant) {
       case 2: launch_variant<T, 16, 2, 1>(f, P, s); return;
       case 0: launch_variant<T, 16, 1, 1>(f, P, s); return;
