@@ -541,7 +541,7 @@ def run_ours(args):
             ow = line["other_workloads"]
             line["roofline"]["others"] = {   # compact copy of the secondary configs' fractions of the HBM peak
                 "c1": ow["config1_blockdiag_4x4_1e6_f64"].get("frac_of_hbm_peak"),
-                "c1_back_to_back": ow["config1_blockdiag_4x4_1e6_f64"].get("frac_of_hbm_peak_back_to_back"),
+                "c1_synchronised_each_step": ow["config1_blockdiag_4x4_1e6_f64"].get("frac_of_hbm_peak_synchronised_each_step"),
                 "c2": ow["config2_chain_1e8_f32"].get("frac_of_hbm_peak"),
                 "c3a": ow["config3a_dense_64x64_2048_f32_gemv"].get("frac_of_hbm_peak"),
                 "c3b": ow["config3b_dense_64x64_2048_f32_64rhs_tcgen05"].get("frac_of_hbm_peak"),
@@ -676,6 +676,11 @@ def extra_workloads(B, torch, stream, peak):
         B.mul_(m2, At, d)
     ms_flush = time_steps(torch, stream, step1f, 20, 3, flush)
     lhs, rhs = B.dot_product_test(A, m, B.rand(B.range_(A), seed=1003))
+    # Primary figure: the K steps between ONE pair of events (the bench contract's timing, and how a solver loop issues
+    # the applies); the per-step-synchronised figure is kept beside it (it adds one launch latency per step and forbids
+    # the overlap of one launch's tail with the next one's prologue).
+    ms_sync = ms
+    ms = ms_b2b
     gbs = 2 * 192e6 / (ms * 1e-3) / 1e9
     # calibration: what a plain device copy of the SAME traffic (96 MB read + 96 MB write per launch, two
     # launches per step, the same rotation over 6 buffer pairs) takes -- at 40 us per launch the ramp and
@@ -695,11 +700,12 @@ def extra_workloads(B, torch, stream, peak):
                                              "frac_of_hbm_peak": round(gbs / peak, 4), "algorithmic_bytes_per_step": 384_000_000,
                                              "dot_product_test_rel": abs(lhs - rhs) / abs(lhs + rhs), "engine": B.plan_info(A),
                                              "l2": f"{NSETS} independent operator/vector sets cycled ({NSETS * 192} MB working set >> 126 MB L2)",
-                                             "ms_per_step_back_to_back": round(ms_b2b, 4),
-                                             "frac_of_hbm_peak_back_to_back": round(2 * 192e6 / (ms_b2b * 1e-3) / 1e9 / peak, 4),
+                                             "timing": "48 steps (8 rounds over the 6 sets) between one pair of CUDA events",
+                                             "ms_per_step_synchronised_each_step": round(ms_sync, 4),
+                                             "frac_of_hbm_peak_synchronised_each_step": round(2 * 192e6 / (ms_sync * 1e-3) / 1e9 / peak, 4),
                                              "ms_per_step_single_set_after_256MB_write_flush": round(ms_flush, 4),
                                              "size_matched_device_copy_ms_per_step": round(ms_copy, 4),
-                                             "frac_of_size_matched_copy": round(ms_copy / ms, 4)}
+                                             "frac_of_size_matched_copy": round(ms_copy / ms_sync, 4)}   # both synchronised per step
     del A, At, W, m, d, m2, sets
     # config 2: diagonal ∘ fdiff ∘ jacobian(pointwise square), 1e8 elements, Float32
     n = 100_000_000
