@@ -405,3 +405,7 @@ def test_complex_dense_in_composition_and_multi_rhs(O, D, T):
     x = np.concatenate([m, d])
     assert close((Ad * B.to_device(x, B.domain(Ad))).to_host(), J.to_array(Ao * J.reshape(x.copy(), J.domain(Ao))), T)
     assert close((Ad.T * B.to_device(d)).to_host(), J.to_array(Ao.T * d), T)
+    # signed sums of complex matrices: the second GEMV subtracts from what the first one stored
+    A2 = (crand(g, rows * cols, T) - T(0.5j)).reshape(rows, cols)
+    Sd, So = B.JopDense(A) - B.JopDense(A2), J.JopDense(A) - J.JopDense(A2)
+    assert close((Sd * B.to_device(m)).to_host(), So * m, T) and close((Sd.T * B.to_device(d)).to_host(), So.T * d, T)
