@@ -366,7 +366,9 @@ __global__ void __launch_bounds__(kThreads, 1) jets_fused_tma_kernel(const Fused
           FastIO<T> io;
           io.b0 = sbase + gt.stream0 * kBufBytes + kPad + ld.e0[0] * (int)sizeof(T);
           io.stride = kBufBytes;
-          if (!eval_fast<T>(gt.pattern, io, rec->stages + gt.stage0, first, last, val)) {
+          bool done = false;
+          if constexpr (!IsCx<T>::value) done = eval_fast<T>(gt.pattern, io, rec->stages + gt.stage0, first, last, val);
+          if (!done) {     // generic chains, and every chain of a complex space (conj-aware stages live in the interpreter)
             ld.base = sbase + gt.stream0 * kBufBytes;
             T wv[1][W];
             eval_term<T, HL, HR, 1, HEAVY>(rec->stages + gt.stage0, gt.nstages, ld, p0, len, wv);
@@ -495,23 +497,16 @@ void launch_one(const DevFused& f, const FusedParams& P, cudaStream_t s) {
   count_launch();
 }
 
-// Complex spaces run on the LDG engine only (the TMA engines are not instantiated for them).
-template <typename T, int HL, int HR>
-void launch_ldg_only(const FusedParams& P, cudaStream_t s) {
-  const int64_t Q = P.nitems * P.S;
-  int64_t grid = (int64_t)ctx().sm_count * 8;
-  if (grid > Q) grid = Q > 0 ? Q : 1;
-  jets_fused_ldg_kernel<T, HL, HR, false><<<(unsigned)grid, kLdgThreads, 0, s>>>(P);
-  CUDA_TRY(cudaGetLastError());
-  count_launch();
-}
+// Complex spaces (interleaved re/im): the interpreter kernels, TMA-staged like the real ones when every stream is
+// aligned and guarded (a ComplexF64 halo element is exactly the 16-byte pad of a staged tile), guarded loads otherwise.
+// The straight-line pattern kernels (fast / bundle) are not instantiated for them; x^2 is the only pointwise function.
 template <typename T>
 void launch_halo_cplx(const DevFused& f, const FusedParams& P, cudaStream_t s) {
-  JETS_CHECK(!f.use_tma && !f.heavy, JETS_ERR_UNSUPPORTED, "internal: complex plans run on the LDG engine");
-  if (f.hl == 0 && f.hr == 0) launch_ldg_only<T, 0, 0>(P, s);
-  else if (f.hl == 0 && f.hr == 1) launch_ldg_only<T, 0, 1>(P, s);
-  else if (f.hl == 1 && f.hr == 0) launch_ldg_only<T, 1, 0>(P, s);
-  else if (f.hl == 1 && f.hr == 1) launch_ldg_only<T, 1, 1>(P, s);
+  JETS_CHECK(!f.heavy, JETS_ERR_UNSUPPORTED, "internal: complex plans know x^2 only");
+  if (f.hl == 0 && f.hr == 0) launch_one<T, 0, 0, false>(f, P, s);
+  else if (f.hl == 0 && f.hr == 1) launch_one<T, 0, 1, false>(f, P, s);
+  else if (f.hl == 1 && f.hr == 0) launch_one<T, 1, 0, false>(f, P, s);
+  else if (f.hl == 1 && f.hr == 1) launch_one<T, 1, 1, false>(f, P, s);
   else JETS_FAIL(JETS_ERR_UNSUPPORTED, "fused halo (%d,%d) not instantiated", f.hl, f.hr);
 }
 

@@ -381,8 +381,8 @@ struct Builder {
       for (size_t r = 0; r < out_sp.len.size(); ++r)
         if (((dst.off + oo[r]) * esz) % 16) tma = false;
     }
-    if (engine == 2 || is_cplx(dtype)) tma = false;   // complex spaces: LDG engine (generic interpreter)
-    all_fast = all_fast && tma;
+    if (engine == 2) tma = false;
+    all_fast = all_fast && tma && !is_cplx(dtype);    // complex spaces: the interpreter kernels (TMA-staged or guarded loads)
     // Fast-kernel shape (measured on B200, profiles/README.md): 16 consumer warps x 2 vectors per
     // thread (16 KB tiles) amortises the per-slot work best -- 81% of HBM peak on config 5, 98% on
     // config 2 vs 53% / 87% with 8 KB tiles.  Blocks shorter than a few tiles keep 8 KB tiles.
@@ -465,7 +465,6 @@ struct Builder {
       t.rows.push_back(row);
     }
     if ((all_fast ? fast_nslots(variant, t.max_streams) : fused_nslots(t.max_streams)) < 2) tma = false;
-    if (is_cplx(dtype)) tma = false;
     t.tma_ok = tma;
     bool use_tma = tma;
     if (engine == 2) use_tma = false;

@@ -133,7 +133,7 @@ def test_complex_diagonal_fixture(O, D, T, n):  # runtests.jl:3-8, :915-917
     assert close(f, Ao * mh, T) and close(t, Ao.T * dh, T)
     lhs, rhs = B.dot_product_test(A, m, d)
     assert abs(complex(lhs) - complex(rhs)) <= 10 * TOL[np.dtype(T)] * abs(complex(lhs))
-    assert B.plan_info(A)["engines"] == ["ldg"]
+    assert B.plan_info(A)["engines"] == ["tma"]      # library-owned, aligned vectors: the TMA-staged interpreter
     l2, r2 = B.linearity_test(A)
     assert close(l2.to_host(), r2.to_host(), T)
 
@@ -173,6 +173,33 @@ def test_complex_block_sum_composite(O, D, T):
         Mt = B.to_matrix(Ad.T)
         assert np.linalg.norm(M.conj().T - Mt) <= 1e-12 * np.linalg.norm(M)
         assert np.linalg.norm(M @ mh - f) <= 1e-12 * np.linalg.norm(f)
+
+
+@pytest.mark.parametrize("T", CT)
+@pytest.mark.parametrize("n", [5000, 20_011])
+def test_complex_tma_and_ldg_engines_agree_bitwise(D, T, n):
+    """Complex spaces on both interpreter engines: operands staged in shared memory by cp.async.bulk (block starts
+    16-byte aligned) or read with guarded loads (forced, or chosen by the planner for the odd ComplexF32 block length)
+    -- stencil halos across the staged tile's pad, conjugating adjoint stages and row sums must give the same bits."""
+    B = D.B
+    g = np.random.default_rng(17)
+    W = [[crand(g, n, T) for _ in range(3)] for _ in range(2)]
+    m, d = crand(g, 3 * n, T), crand(g, 2 * n, T)
+    a = 0.75 - 0.5j
+    res = {}
+    for eng in ("auto", "ldg"):
+        B.set_fused_engine(eng)
+        try:
+            A = B.blockop([[B.JopDiagonal(W[r][c]) @ B.JopStencil(T, n, "lap") if c != 1 else a * (B.JopStencil(T, n, "fdiff") @ B.JopDiagonal(W[r][c]))
+                            for c in range(3)] for r in range(2)])
+            f = (A * B.to_device(m, B.domain(A))).to_host()
+            t = (A.T * B.to_device(d, B.range_(A))).to_host()
+            res[eng] = (f, t, B.plan_info(A)["engines"])
+        finally:
+            B.set_fused_engine("auto")
+    aligned = (n * np.dtype(T).itemsize) % 16 == 0
+    assert res["auto"][2] == (["tma"] if aligned else ["ldg"]) and res["ldg"][2] == ["ldg"]
+    assert bits(res["auto"][0], res["ldg"][0]) and bits(res["auto"][1], res["ldg"][1])
 
 
 def test_complex_pointwise_jacobian(O, D):
