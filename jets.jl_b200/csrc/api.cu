@@ -311,6 +311,7 @@ int jets_init(int device) {
     if (const char* v = getenv("JETS_B200_GROUP_STREAMS")) c.group_streams = atoi(v);
     if (const char* v = getenv("JETS_B200_NO_TAIL_SPLIT")) c.no_tail_split = atoi(v);
     if (const char* v = getenv("JETS_B200_TAIL_MIN_UNITS")) c.tail_min_units = atoll(v);
+    if (const char* v = getenv("JETS_B200_TILE_ELEMS")) c.tile_elems = atoll(v);
     if (const char* v = getenv("JETS_B200_TAIL_MIN_ROWS")) c.tail_min_rows = std::max(2, atoi(v));
     if (const char* v = getenv("JETS_B200_TAIL_DIV")) c.tail_div = std::max(2, atoi(v));
     if (const char* v = getenv("JETS_B200_TAIL_SUB_MIN")) c.tail_sub_min = std::max(1, atoi(v));

@@ -83,6 +83,7 @@ struct Context {
   int tail_min_rows = 16;    // JETS_B200_TAIL_MIN_ROWS: bundles with at least this many rows are cut into sub-bundles at the tail
   int tail_div = 8;          // JETS_B200_TAIL_DIV: sub-bundles of 1/div of the rows ...
   int tail_sub_min = 8;      // JETS_B200_TAIL_SUB_MIN: ... but at least this many
+  int64_t tile_elems = 0;    // JETS_B200_TILE_ELEMS: force the tile length of the bundle kernel (tuning; rounded to 128 bytes, capped by the buffer)
   int no_tail_split = 0;     // JETS_B200_NO_TAIL_SPLIT=1: no fine-grained sub-bundles over the last tile positions (A/B)
   int group_streams = 0;     // JETS_B200_GROUP_STREAMS=n: at most n state streams per term group (tuning)
   int no_pre_state = 0;      // JETS_B200_NO_PRE_STATE=1: never fetch operator state before griddepcontrol.wait (A/B)

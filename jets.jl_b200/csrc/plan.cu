@@ -797,9 +797,14 @@ struct Builder {
       if (units(sim, cap) >= 2 * (int64_t)grid || sim.max_rows <= 1) break;
       Bmax = std::max(1, std::min(Bmax, sim.max_rows) / 2);
     }
-    // tile length: the largest one (within 25% of the capacity) whose unit count fills whole waves
+    // Tile length.  With at least four units per CTA the full buffer: every unit costs a pipeline bubble (~2.6 us per
+    // CTA on config 1: the rings hold little more than one unit, so the next unit's loads wait for this unit's slots) and
+    // full buffers keep the most bytes in flight -- measured on config 1, 848-element tiles (8 whole waves) 74.9 us per
+    // pair, 1024-element ones (6.6 waves, ragged) 68.3 us; the dynamic scheduler evens the ragged last wave out.  With
+    // fewer units per CTA a ragged wave is a large part of the launch: the largest tile (within 25 % of the capacity)
+    // whose unit count fills whole waves.
     int64_t te = cap;
-    {
+    if (ctx().static_sched || units(sim, cap) < 4 * (int64_t)grid) {
       const int64_t step = 128 / (int64_t)esz;
       double best = -1;
       for (int64_t c = cap; c >= cap - cap / 4 && c >= step; c -= step) {
@@ -809,6 +814,7 @@ struct Builder {
         if (eff > best + 1e-3) { best = eff; te = c; }
       }
     }
+    if (ctx().tile_elems > 0) te = std::min<int64_t>(cap, std::max<int64_t>(128 / (int64_t)esz, ctx().tile_elems / (128 / (int64_t)esz) * (128 / (int64_t)esz)));
     for (BundleRec& b : sim.bundles) { b.pos0 = 0; b.npos = (int32_t)((b.len + te - 1) / te); }
     // Fine-grained tail.  A unit of a long bundle is a lot of work (config 5: 256 rows x 3 tiles = 12 MB, 280 us), the
     // SMs do not run at the same speed, and the launch ends when the slowest CTA finishes its last unit: traced on
