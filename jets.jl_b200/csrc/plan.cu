@@ -967,6 +967,12 @@ struct Builder {
       fprintf(stderr, "[jets plan] bundle engine: rows=%zu bundles=%zu groups=%lld (max %lld per bundle) x-allocs=%lld units=%lld tile=%lld elems "
               "variant=%d NX=%d NS=%d sstreams=%d G=%d chunk=%d dyn=%d\n", rows.size(), sim.bundles.size(), (long long)ng, (long long)maxg,
               (long long)nxsum, (long long)unit, (long long)te, variant, NX, NS, sim.sstreams, f.G, chunk, f.sched != nullptr);
+      if (atoi(getenv("JETS_B200_PLAN_DEBUG")) >= 2)
+        for (size_t i = 0; i < sim.bundles.size(); ++i) {
+          const BundleRec& b = sim.bundles[i];
+          fprintf(stderr, "[jets plan]   bundle %zu: rows=%d groups=%d x-allocs=%d positions=%d (from %d) claim=%d units gate=0x%x early=%d\n", i, b.nrows,
+                  b.ngroups, b.nx, b.npos, b.pos0, b.chunk, (unsigned)b.gate, (int)sim.early[i]);
+        }
     }
     return true;
   }
