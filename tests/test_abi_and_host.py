@@ -101,3 +101,18 @@ def test_complex_eltypes_are_in_the_abi():
     assert (L.F32, L.F64, L.C64, L.C128) == (0, 1, 2, 3)
     src = open(HEADER).read()
     assert "JETS_C64 = 2" in src and "JETS_C128 = 3" in src
+
+
+def test_every_tuning_switch_is_documented():
+    """Every environment switch the library, the host mirror or the bench reads is listed in DESIGN.md (section 7a)."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    names = set()
+    for f in glob.glob(os.path.join(root, "jets.jl_b200", "csrc", "*")):
+        names |= set(re.findall(r'getenv\("(JETS_[A-Z0-9_]+)"\)', open(f).read()))
+    for f in glob.glob(os.path.join(root, "jets.jl_b200", "*.py")) + [os.path.join(root, "bench.py")]:
+        names |= set(re.findall(r'environ(?:\.get\(|\[)"(JETS_[A-Z0-9_]+)"', open(f).read()))
+    design = open(os.path.join(root, "DESIGN.md")).read()
+    missing = sorted(n for n in names if n not in design)
+    assert names and not missing, missing
