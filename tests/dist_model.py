@@ -63,3 +63,21 @@ def adjoint(J, part, comm, A_loc, d_own):
         last = from_next[b - (n - h)] if (from_next is not None and b >= n - h) else None
         out.append(_column(J, A_loc, h + b, d_own, first, last))
     return out
+
+
+# ---- dense block structure (csrc/dist_op.cu: dense_apply) ------------------------------------------------------
+def dense_forward(J, comm, A_loc, x_shard):
+    """Every block row needs the whole domain (:1015-1030 without zero blocks): all-gather the equal shards, apply the
+    rank's rows.  comm.allgather(a) -> the shards of all ranks concatenated in rank order."""
+    full = comm.allgather(x_shard)
+    return J.to_array(A_loc * J.reshape(full, J.domain(A_loc)))
+
+
+def dense_adjoint(J, comm, A_loc, d_rows, nranks, rank):
+    """The rank's rows contribute to every block column (:1039-1055): full-length partial, summed over the ranks,
+    every rank keeps its shard (reduce-scatter).  Complex shards travel as twice as many reals, like the device path."""
+    part = J.to_array(J.adjoint(A_loc) * J.reshape(d_rows, J.range_(A_loc)))
+    cplx = np.iscomplexobj(part)
+    flat = np.ascontiguousarray(part).view(part.real.dtype) if cplx else part
+    mine = comm.reduce_scatter(flat)
+    return mine.view(part.dtype) if cplx else mine
