@@ -111,6 +111,33 @@ def scn_restriction(K, T):
     return {"fwd": f, "adj": t}
 
 
+def _crand(g, n, T):
+    rt = np.float32 if np.dtype(T) == np.complex64 else np.float64
+    return ((g.random(n).astype(rt) - rt(0.5)) + 1j * (g.random(n).astype(rt) - rt(0.5))).astype(T)
+
+
+def scn_cdense(K, T):  # complex matrices as operators: d = A m, m = A' d with the conjugate transpose (src/Jets.jl:573-574)
+    g = np.random.default_rng(108)
+    shapes = [(77, 40), (77, 131)], [(130, 40), (130, 131)]
+    mats = [[_crand(g, s[0] * s[1], T).reshape(s) for s in row] for row in shapes]
+    A = K.blockop([[K.JopDense(M) for M in row] for row in mats])
+    m, d = _crand(g, 40 + 131, T), _crand(g, 77 + 130, T)
+    f, t = _apply(K, A, m, d)
+    return {"fwd_red": f, "adj_red": t}
+
+
+def scn_cblock(K, T):  # complex diagonals, a complex scalar multiple and stencils in a 2x2 JopBlock (conj in the adjoint)
+    g = np.random.default_rng(109)
+    n = 512
+    w = [_crand(g, n, T) for _ in range(3)]
+    A = K.blockop([[K.JopDiagonal(_dev(K, w[0])), K.compose(K.JopDiagonal(_dev(K, w[1])), K.JopStencil(T, n, "fdiff"))],
+                   [(0.5 - 1.25j) * K.JopDiagonal(_dev(K, w[2])), K.JopStencil(T, n, "lap")]])
+    m, d = _crand(g, 2 * n, T), _crand(g, 2 * n, T)
+    f, t = _apply(K, A, m, d)
+    # numpy's SIMD complex multiply may contract where the device rounds every real operation: tolerance keys
+    return {"fwd_red": f, "adj_red": t}
+
+
 SCENARIOS = {
     "block_diag_f64": (scn_block_diag, np.float64), "block_diag_f32": (scn_block_diag, np.float32),
     "chain_f32": (scn_chain, np.float32), "chain_f64": (scn_chain, np.float64),
@@ -119,6 +146,8 @@ SCENARIOS = {
     "vectors_f32": (scn_vectors, np.float32), "vectors_f64": (scn_vectors, np.float64),
     "dense_f32": (scn_dense, np.float32), "dense_f64": (scn_dense, np.float64),
     "restriction_f64": (scn_restriction, np.float64),
+    "cdense_c64": (scn_cdense, np.complex64), "cdense_c128": (scn_cdense, np.complex128),
+    "cblock_c64": (scn_cblock, np.complex64), "cblock_c128": (scn_cblock, np.complex128),
 }
 
 

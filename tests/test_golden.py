@@ -16,13 +16,15 @@ GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"
 
 def compare(name, res):
     T = SCENARIOS[name][1]
-    tol = 1e-5 if np.dtype(T) == np.float32 else 1e-12
+    tol = 1e-5 if np.dtype(T) in (np.dtype(np.float32), np.dtype(np.complex64)) else 1e-12
     keys = [k.split("/", 1)[1] for k in GOLD.files if k.startswith(name + "/")]
     assert sorted(keys) == sorted(res), (sorted(keys), sorted(res))
     for k in keys:
         want, got = GOLD[f"{name}/{k}"], np.asarray(res[k])
         assert want.shape == got.shape, (name, k, want.shape, got.shape)
         if k.endswith("_red"):
+            if np.iscomplexobj(want):      # complex results as (re, im) pairs
+                want, got = np.ascontiguousarray(want).view(want.real.dtype), np.ascontiguousarray(got).view(got.real.dtype)
             w64, g64 = want.astype(np.float64).ravel(), got.astype(np.float64).ravel()
             fin = np.isfinite(w64)
             assert np.array_equal(fin, np.isfinite(g64))
