@@ -22,6 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import itertools
+import weakref
 import math
 from typing import Sequence
 
@@ -711,6 +712,58 @@ class JopAdjoint(Jop):
 
 def _is_lin(A):
     return isinstance(A, (JopLn, JopAdjoint))
+
+
+class Jet:
+    """The jet behind an operator (src/Jets.jl:133-142), device edition.  ``dom``, ``rng``, the linearization point and the
+    state are the reference's fields; the three mappings f!/df!/df'! live in libjets_b200 behind the operator handle --
+    the primitive registry (``jets_op_*``) takes the place of plugin closures on the device -- so a Jet is obtained from
+    an operator (``jet(A)``) and cannot be built from host closures: ``Jet(dom=..., f=...)`` raises
+    JETS_ERR_UNSUPPORTED, the device path's ``error("not implemented")`` (:131).  ``jet(F)`` and ``jet(JopLn(F))`` are
+    the SAME object, as in the reference (:364-366), and every accessor that takes a Jop takes a Jet:
+    ``domain / range_ / shape / state / state_ / point / point_ / perfstat / close``."""
+
+    def __init__(self, *args, **kw):
+        raise JetsError(5, "Jet(dom, rng, f!, df!, df'!) takes host closures, which cannot run on the device: build the "
+                           "operator from the library's leaves (JopDiagonal, JopPointwise, JopStencil, JopDense, "
+                           "JopRestriction, JopZeroBlock) and the combinators, and use jet(A) for its jet")
+
+    @classmethod
+    def _of(cls, A):
+        j = object.__new__(cls)
+        j._h, j.dom, j.rng, j.meta = A._h, A.dom, A.rng, A.meta
+        return j
+
+    _mode = L.MODE_F
+
+    @property
+    def mo(self):
+        return self.meta.get("mo")
+
+    @property
+    def s(self):
+        return self.meta
+
+    def close(self):      # the handle belongs to the operator(s) of this jet
+        return None
+
+    def __repr__(self):
+        return f"Jet({self.dom} -> {self.rng})"
+
+
+def jet(A):
+    """jet(A) (src/Jets.jl:236-238): the jet of an operator; the adjoint's jet is its parent's."""
+    if isinstance(A, Jet):
+        return A
+    if isinstance(A, JopAdjoint):
+        return jet(A.op)
+    j = _JETS.get(id(A.meta))        # operators that share a state dictionary share a jet (jacobian! :364-366)
+    if j is None or j.meta is not A.meta:
+        j = _JETS[id(A.meta)] = Jet._of(A)
+    return j
+
+
+_JETS = weakref.WeakValueDictionary()
 
 
 def domain(A):

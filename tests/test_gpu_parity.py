@@ -904,3 +904,30 @@ def test_captured_graph_keeps_its_plans_alive(D):
         assert np.array_equal(dd.to_host(), ref1)
     finally:
         B.check(B.lib.jets_graph_destroy(gh))
+
+
+def test_jet_accessor(O, D):
+    """jet(A) (src/Jets.jl:236-238, exported): F and its JopLn view share ONE jet, the adjoint's jet is its parent's,
+    jacobian(F, mo) makes a new one; the accessors that take a Jop take the Jet (domain / range / shape / state /
+    point / point!).  A Jet cannot be built from host closures on the device path."""
+    B, J = D.B, O.J
+    g = np.random.default_rng(92)
+    n = 4000
+    w, mo1, mo2, m = (g.random(n) for _ in range(4))
+    F = B.JopDiagonal(w) @ B.JopPointwise(np.float64, n, "square")
+    A = B.jacobian_(F, B.to_device(mo1))
+    assert B.jet(F) is B.jet(A) and B.jet(B.adjoint(A)) is B.jet(A) and B.jet(B.jet(A)) is B.jet(A)
+    j = B.jet(A)
+    assert isinstance(j, B.Jet) and B.domain(j) == B.domain(A) and B.range_(j) == B.range_(A) and B.shape(j) == B.shape(A)
+    assert B.state(j) is B.state(A) and np.array_equal(B.point(j).to_host(), mo1)
+    Jn = B.jacobian(F, B.to_device(mo1))
+    assert B.jet(Jn) is not B.jet(F)                       # jacobian copies the jet (:374)
+    B.point_(j, B.to_device(mo2))                          # point!(jet(F), mo): every operator on this jet sees it
+    assert np.array_equal((A * B.to_device(m)).to_host(), w * (2 * mo2 * m))
+    assert np.array_equal((Jn * B.to_device(m)).to_host(), w * (2 * mo1 * m))
+    # the oracle's jets behave the same way
+    Fo = J.JopDiagonal(w) @ J.JopPointwise(np.float64, n, "square")
+    Ao = J.jacobian_(Fo, mo1.copy())
+    assert J.jet(Fo) is J.jet(Ao) and J.jet(J.adjoint(Ao)) is J.jet(Ao) and J.jet(J.jacobian(Fo, mo1.copy())) is not J.jet(Fo)
+    with pytest.raises(B.JetsError):
+        B.Jet(dom=B.JetSpace(np.float64, n), rng=B.JetSpace(np.float64, n), f=lambda d, m: d)
